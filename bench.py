@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py — agent-days/s of the per-day agent update on B200 (BASELINE.json metric).
+
+Workload (BASELINE.json configs[2], the configuration the metric is quoted on): 64 independent replicas x 1M
+synthetic agents (S=4 subcultures, H=10 neighbourhoods, Barabási–Albert links with minimum 5 social + 10
+neighbour), sharded over the N ranks with no communication (each rank steps its 64/N replicas in one launch per
+weekday).  A STEP is one simulated weekday of every replica: update_habit + congestion + choose + statistics
+(src/simulation.rs:108-135).  Inputs are far larger than L2 (>= 1.2 GB per rank per step), so no flush is needed.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+Under torchrun (N > 1) one process per GPU; time = max over ranks of the CUDA-event time of the K launches.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "agent_days_per_sec"
+UNIT = "agent-days/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100, help="timed weekdays")
+    ap.add_argument("--warmup", type=int, default=5, help="untimed weekdays")
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--replicas", type=int, default=64, help="total replicas over all ranks (BASELINE config 3)")
+    ap.add_argument("--agents", type=int, default=1_000_000)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-baseline-days", type=int, default=8)
+    return ap.parse_args()
+
+
+def weekdays_calendar(n_weekdays):
+    """Smallest calendar [0, n_days) whose day loop (days 1..n_days-1, day%7<5) holds n_weekdays weekdays."""
+    n_days, k = 1, 0
+    while k < n_weekdays:
+        k += (n_days % 7 < 5)
+        n_days += 1
+    return n_days
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_inputs(args, replica_ids, pinned=False):
+    import motivate_b200 as mb
+    pops, tabs = [], []
+    for r in replica_ids:
+        p = mb.synth_population(args.agents, 4, 10, 5, 10, seed=r)        # master seed 0, replica r -> seed r
+        if pinned:
+            import torch
+            p._pins = []
+            for k, v in list(p.arrays.items()):
+                if v is None or v.nbytes == 0:
+                    continue
+                t = torch.empty(v.nbytes, dtype=torch.uint8, pin_memory=True)      # page-locked host buffer
+                a = t.numpy().view(v.dtype).reshape(v.shape)
+                a[...] = v
+                p.arrays[k] = a
+                p._pins.append(t)
+            p._struct = None
+        pops.append(p)
+        tabs.append(mb.synth_tables(4, 10, args.agents, seed=r))
+    return pops, tabs
+
+
+def cpu_reference_throughput(args, n_threads, n_days, warm_days=1):
+    """The reference's CPU path (one single-threaded replica per rayon worker, src/main.rs:89-121) on this box's
+    cores, via the oracle port rebuilt here with -O3 -march=native: agent-days/s over n_days weekdays."""
+    import motivate_b200 as mb
+    from oracle.binding import OracleSimulation
+    base = [mb.synth_population(args.agents, 4, 10, 5, 10, seed=s) for s in range(min(2, n_threads))]
+    tabs = [mb.synth_tables(4, 10, args.agents, seed=s) for s in range(len(base))]
+    prm = mb.make_params()
+    sims = [OracleSimulation(base[i % len(base)], tabs[i % len(base)], prm, native=True) for i in range(n_threads)]
+    w = mb.weather_pattern(warm_days + n_days + 2, seed=0)
+
+    def work(sim, lo, hi):
+        for d in range(lo, hi):
+            sim.step(int(w[d]), int(w[d] != w[d - 1]))          # ctypes releases the GIL
+
+    def run(lo, hi):
+        th = [threading.Thread(target=work, args=(s, lo, hi)) for s in sims]
+        t0 = time.perf_counter()
+        [t.start() for t in th]; [t.join() for t in th]
+        return time.perf_counter() - t0
+
+    run(1, 1 + warm_days)
+    dt = run(1 + warm_days, 1 + warm_days + n_days)
+    for s in sims:
+        s.close()
+    return n_threads * args.agents * n_days / dt, dt
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    # bounded sample: one replica per core, K weekdays each (the reference's own parallelism)
+    per_step = []
+    import motivate_b200 as mb
+    from oracle.binding import OracleSimulation
+    base = [mb.synth_population(args.agents, 4, 10, 5, 10, seed=s) for s in range(min(2, cores))]
+    tabs = [mb.synth_tables(4, 10, args.agents, seed=s) for s in range(len(base))]
+    prm = mb.make_params()
+    sims = [OracleSimulation(base[i % len(base)], tabs[i % len(base)], prm, native=True) for i in range(cores)]
+    n_days = weekdays_calendar(args.warmup + args.steps)
+    w = mb.weather_pattern(n_days, seed=0)
+    wk = [d for d in range(1, n_days) if d % 7 < 5]
+    prev = [int(w[0])]
+
+    def step_all(d):
+        th = [threading.Thread(target=s.step, args=(int(w[d]), int(w[d] != prev[0]))) for s in sims]
+        [t.start() for t in th]; [t.join() for t in th]
+        prev[0] = int(w[d])
+
+    for d in wk[:args.warmup]:
+        step_all(d)
+    t0 = time.perf_counter()
+    for d in wk[args.warmup:args.warmup + args.steps]:
+        step_all(d)
+    dt = time.perf_counter() - t0
+    value = cores * args.agents * args.steps / dt
+    sample = f"{cores} replicas x {args.agents} agents x {args.steps} weekdays, one single-threaded replica per core"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, note="CPU arm: bounded sample, " + sample),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(args, note=None):
+    c = {"workload": f"C3: {args.replicas} independent replicas x {args.agents} agents, 4 subcultures, 10 neighbourhoods, "
+                     "BA links min 5 social + 10 neighbour (mean 30/agent), steps = weekdays of the 2-year calendar",
+         "replicas": args.replicas, "agents_per_replica": args.agents, "parallelism": f"replica-sharded x{args.gpus}, no communication",
+         "l2": "inputs larger than L2 (>=1.2 GB streamed per rank per step); no flush needed"}
+    if note:
+        c["note"] = note
+    return c
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            print(f"bench.py: --gpus {args.gpus} needs torchrun with {args.gpus} ranks", file=sys.stderr)
+            sys.exit(2)
+    import torch
+    import torch.distributed as dist
+
+    import motivate_b200 as mb
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if args.replicas % world:
+        raise SystemExit("--replicas must be divisible by the number of ranks")
+    per = args.replicas // world
+    my_ids = list(range(rank * per, (rank + 1) * per))
+    pops, tabs = make_inputs(args, my_ids)
+    prm = mb.make_params()
+    n_days = weekdays_calendar(args.warmup + args.steps)
+    w = mb.weather_pattern(n_days, seed=0)
+    warm_end = weekdays_calendar(args.warmup)               # days [0, warm_end) hold the warm-up weekdays
+
+    sim = mb.Simulation(pops, tabs, prm, device=local_rank)
+    alg_bytes = sum(sim.algorithmic_bytes_per_day(r) for r in range(per))
+    if args.warmup:
+        sim.run_async(w, 0, warm_end)
+    sim.sync()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sim.run_async(w, warm_end if args.warmup else 0, n_days)
+    sim.sync()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms, launches = sim.last_run_stats()
+    clocks = sampler.stop()
+    assert launches == args.steps, (launches, args.steps)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    max_ms = float(t.item())
+    # sanity: statistics rows are populated (work was not skipped)
+    days, rows = sim.fetch_rows()
+    assert len(days) == 1 + args.warmup + args.steps and all(int(r[-1, 0]) > 0 or int(r[-1, 1]) >= 0 for r in rows)
+    sim.close()
+
+    total_agents = args.agents * args.replicas
+    value = total_agents * args.steps / (max_ms * 1e-3)
+    peak, peak_src = peaks()
+    ach = alg_bytes * args.steps / (ms * 1e-3) / 1e9
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(args),
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                     "traffic": profile_traffic(), "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg_bytes,
+                     "kernel": "day kernel (one launch per weekday per rank), rank 0"},
+        "clocks": clocks,
+    }
+
+    if not args.no_e2e:
+        out["e2e"] = e2e(args, my_ids, prm, w, n_days, local_rank, world, dist if world > 1 else None, torch)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        v, dt = cpu_reference_throughput(args, cores, args.cpu_baseline_days)
+        out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                               "sample": f"{cores} replicas x {args.agents} agents x {args.cpu_baseline_days} weekdays "
+                                         f"({dt:.1f} s), one single-threaded replica per core, oracle -O3 -march=native"}
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def profile_traffic():
+    """dram bytes per launch of the day kernel from the committed ncu capture, if one exists."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+def e2e(args, my_ids, prm, w, n_days, local_rank, world, dist, torch):
+    """Same metric through the public call a host makes, with HOST buffers: mvb_create_batch (population H2D from
+    pinned memory) + mvb_run over the same calendar (weather in, statistics rows D2H) + mvb_destroy."""
+    import motivate_b200 as mb
+    pops, tabs = make_inputs(args, my_ids, pinned=True)
+    h2d = sum(sum(v.nbytes for v in p.arrays.values() if v is not None) for p in pops) + n_days
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    sim = mb.Simulation(pops, tabs, prm, device=local_rank)
+    days, rows = sim.run(w, n_days)
+    sim.close()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    weekdays = len(days) - 1
+    d2h = sum(r.nbytes for r in rows)
+    return {"value": args.agents * args.replicas * weekdays / dt, "unit": UNIT,
+            "h2d_bytes_per_step": h2d / weekdays, "d2h_bytes_per_step": d2h / weekdays,
+            "weekdays": weekdays, "seconds": dt,
+            "what": "mvb_create_batch (H2D of populations from pinned host memory) + mvb_run (rows D2H) + mvb_destroy"}
+
+
+if __name__ == "__main__":
+    main()

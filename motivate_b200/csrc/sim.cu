@@ -1,0 +1,542 @@
+// sim.cu — C ABI of libmotivate_b200 (include/motivate_b200.h): handle lifecycle, the
+// weekday loop of src/simulation.rs:95-136 driven on one CUDA stream, state access.
+// Kernels live in day_kernels.cuh.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstring>
+#include <memory>
+#include <new>
+#include <vector>
+
+#include "day_kernels.cuh"
+#include "mvb_internal.h"
+
+using namespace mvb;
+
+namespace {
+
+struct DevBuf {                       // owning device allocation
+    void* p = nullptr;
+    size_t bytes = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes) { o.p = nullptr; o.bytes = 0; }
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t n) {
+        if (p) { cudaFree(p); p = nullptr; }
+        bytes = n;
+        return cudaMalloc(&p, n ? n : 1);
+    }
+    template <class T> T* as() const { return (T*)p; }
+};
+
+// The graph of one population, shareable between replicas (scenario sweeps).
+struct Graph {
+    uint32_t N = 0;
+    uint64_t Es = 0, En = 0;
+    DevBuf s_rowptr, s_col, n_rowptr, n_col;
+    const void* key[4] = {nullptr, nullptr, nullptr, nullptr};   // caller pointers it was built from
+};
+
+struct Replica {
+    uint32_t N = 0, S = 0, H = 0;
+    uint32_t rec_width = 0, rec_off = 0;
+    std::shared_ptr<Graph> graph;
+    DevBuf stat, ws, habit, mode[2], norm, pa, tables_f, tables_u, cong;
+    std::vector<uint32_t> h_stat;       // host mirror of the packed static words (ownership edits)
+    bool per_agent = false;
+};
+
+}  // namespace
+
+struct mvb_sim {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    mvb_params prm{};
+    std::vector<Replica> reps;
+    DevBuf d_reps;                       // RepDev[R]
+    std::vector<RepDev> h_reps;
+    uint32_t rec_stride = 0;             // u32 per record row (all replicas)
+    uint32_t max_blocks_x = 0;
+    size_t smem_bytes = 0;
+    bool any_per_agent = false;
+    // record ring: rows [0, rec_cap); row `cursor` holds the census of the current state
+    DevBuf rec;
+    uint32_t rec_cap = 0, cursor = 0;
+    std::vector<uint32_t> row_days;      // Day column of rows 0..cursor
+    uint32_t parity = 0;                 // which mode buffer holds current_mode
+    uint8_t prev_weather = 0;
+    bool stepped = false;
+    float last_ms = 0.f;
+    uint64_t last_launches = 0;
+    bool timing_valid = false;
+};
+
+namespace {
+
+constexpr uint32_t kBlock = 256;
+
+int upload_reps(mvb_sim* s) {
+    MVB_CUDA(cudaMemcpyAsync(s->d_reps.p, s->h_reps.data(), sizeof(RepDev) * s->h_reps.size(),
+                             cudaMemcpyHostToDevice, s->stream));
+    return MVB_OK;
+}
+
+// Make sure rows cursor+1 .. cursor+n exist and are zero.
+int ensure_rows(mvb_sim* s, uint32_t n) {
+    if ((uint64_t)s->cursor + n < s->rec_cap) return MVB_OK;
+    const uint32_t new_cap = std::max<uint64_t>((uint64_t)s->cursor + n + 1, (uint64_t)s->rec_cap * 2);
+    DevBuf nb;
+    MVB_CUDA(nb.alloc(sizeof(uint32_t) * (size_t)new_cap * s->rec_stride));
+    MVB_CUDA(cudaMemsetAsync(nb.p, 0, nb.bytes, s->stream));
+    if (s->rec.p)
+        MVB_CUDA(cudaMemcpyAsync(nb.p, s->rec.p, sizeof(uint32_t) * (size_t)(s->cursor + 1) * s->rec_stride,
+                                 cudaMemcpyDeviceToDevice, s->stream));
+    MVB_CUDA(cudaStreamSynchronize(s->stream));
+    std::swap(s->rec.p, nb.p);
+    std::swap(s->rec.bytes, nb.bytes);
+    s->rec_cap = new_cap;
+    return MVB_OK;
+}
+
+int launch_census(mvb_sim* s, uint32_t row) {
+    uint32_t* rec = s->rec.as<uint32_t>() + (size_t)row * s->rec_stride;
+    MVB_CUDA(cudaMemsetAsync(rec, 0, sizeof(uint32_t) * s->rec_stride, s->stream));
+    dim3 grid(s->max_blocks_x, (unsigned)s->reps.size());
+    census_kernel<<<grid, kBlock, s->smem_bytes, s->stream>>>(s->d_reps.as<RepDev>(), s->parity, rec);
+    MVB_CUDA(cudaGetLastError());
+    return MVB_OK;
+}
+
+int launch_day(mvb_sim* s, uint8_t weather, uint8_t changed) {
+    int rc = ensure_rows(s, 1);
+    if (rc) return rc;
+    const uint32_t* prev = s->rec.as<uint32_t>() + (size_t)s->cursor * s->rec_stride;
+    uint32_t* next = s->rec.as<uint32_t>() + (size_t)(s->cursor + 1) * s->rec_stride;
+    dim3 grid(s->max_blocks_x, (unsigned)s->reps.size());
+    AgentWeights uw{s->prm.consistency, s->prm.social_connectivity, s->prm.subculture_connectivity,
+                    s->prm.neighbourhood_connectivity, s->prm.average_weight};
+    if (s->any_per_agent)
+        day_kernel_simple<true><<<grid, kBlock, s->smem_bytes, s->stream>>>(
+            s->d_reps.as<RepDev>(), s->parity, prev, next, weather, changed, uw);
+    else
+        day_kernel_simple<false><<<grid, kBlock, s->smem_bytes, s->stream>>>(
+            s->d_reps.as<RepDev>(), s->parity, prev, next, weather, changed, uw);
+    MVB_CUDA(cudaGetLastError());
+    s->cursor++;
+    s->parity ^= 1u;
+    s->stepped = true;
+    s->last_launches++;
+    return MVB_OK;
+}
+
+int check_tables(const mvb_tables* t) {
+    if (!t || !t->supportiveness || !t->capacity || !t->desirability || t->n_subcultures == 0 ||
+        t->n_subcultures > 256 || t->n_neighbourhoods == 0 || t->n_neighbourhoods > 65536) {
+        set_error("bad tables (need 1..256 subcultures, 1..65536 neighbourhoods, non-null arrays)");
+        return MVB_ERR_ARG;
+    }
+    return MVB_OK;
+}
+
+int upload_tables(mvb_sim* s, Replica& r, const mvb_tables* t) {
+    // tables_f = supportiveness[H][4] | desirability[S][4];  tables_u = capacity[H][4] | residents[H]
+    MVB_CUDA(cudaMemcpyAsync(r.tables_f.p, t->supportiveness, sizeof(float) * 4 * r.H, cudaMemcpyHostToDevice, s->stream));
+    MVB_CUDA(cudaMemcpyAsync(r.tables_f.as<float>() + 4 * r.H, t->desirability, sizeof(float) * 4 * r.S,
+                             cudaMemcpyHostToDevice, s->stream));
+    MVB_CUDA(cudaMemcpyAsync(r.tables_u.p, t->capacity, sizeof(uint32_t) * 4 * r.H, cudaMemcpyHostToDevice, s->stream));
+    return MVB_OK;
+}
+
+int validate_population(const mvb_population* p, const mvb_tables* t) {
+    if (!p || p->n_agents == 0 || !p->subculture || !p->neighbourhood || !p->commute || !p->owns_car ||
+        !p->owns_bike || !p->weather_sensitivity || !p->habit || !p->current_mode || !p->norm ||
+        !p->social_rowptr || !p->neighbour_rowptr) {
+        set_error("population has null arrays or zero agents");
+        return MVB_ERR_ARG;
+    }
+    const uint32_t N = p->n_agents;
+    for (uint32_t i = 0; i < N; ++i) {
+        if (p->subculture[i] >= t->n_subcultures) { set_error("agent %u: subculture index %u out of range (\"Subculture not found\")", i, p->subculture[i]); return MVB_ERR_ARG; }
+        if (p->neighbourhood[i] >= t->n_neighbourhoods) { set_error("agent %u: neighbourhood index %u out of range", i, p->neighbourhood[i]); return MVB_ERR_ARG; }
+        if (p->commute[i] > 2 || p->current_mode[i] > 3 || p->norm[i] > 3) { set_error("agent %u: bad commute/mode/norm code", i); return MVB_ERR_ARG; }
+    }
+    for (int g = 0; g < 2; ++g) {
+        const uint64_t* rp = g ? p->neighbour_rowptr : p->social_rowptr;
+        const uint32_t* cl = g ? p->neighbour_col : p->social_col;
+        if (rp[0] != 0) { set_error("rowptr[0] must be 0"); return MVB_ERR_ARG; }
+        for (uint32_t i = 0; i < N; ++i)
+            if (rp[i + 1] < rp[i]) { set_error("rowptr not monotone at %u", i); return MVB_ERR_ARG; }
+        if (rp[N] && !cl) { set_error("null column array"); return MVB_ERR_ARG; }
+        for (uint64_t e = 0; e < rp[N]; ++e)
+            if (cl[e] >= N) { set_error("link target %u out of range", cl[e]); return MVB_ERR_ARG; }
+    }
+    return MVB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mvb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+uint32_t mvb_run_rows(uint32_t n_days) {
+    uint32_t r = 1;
+    for (uint32_t d = 1; d < n_days; ++d) r += (d % 7 < 5);
+    return r;
+}
+
+void mvb_destroy(mvb_sim* s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+int mvb_create_batch(uint32_t R, const mvb_population* const* pops, const mvb_tables* const* tabs,
+                     const mvb_params* prm, int device, mvb_sim** out) {
+    if (!out || !pops || !tabs || !prm || R == 0) { set_error("null argument or zero replicas"); return MVB_ERR_ARG; }
+    *out = nullptr;
+    int ndev = mvb_device_count();
+    if (ndev <= 0) { set_error("no CUDA device available (this library has no CPU path)"); return MVB_ERR_CUDA; }
+    if (device < 0 || device >= ndev) { set_error("device %d out of range (have %d)", device, ndev); return MVB_ERR_ARG; }
+    for (uint32_t r = 0; r < R; ++r) {
+        int rc = check_tables(tabs[r]);
+        if (rc) return rc;
+        rc = validate_population(pops[r], tabs[r]);
+        if (rc) return rc;
+    }
+    MVB_CUDA(cudaSetDevice(device));
+    std::unique_ptr<mvb_sim, void (*)(mvb_sim*)> sp(new (std::nothrow) mvb_sim(), mvb_destroy);
+    mvb_sim* s = sp.get();
+    if (!s) { set_error("out of memory"); return MVB_ERR_NOMEM; }
+    s->device = device;
+    s->prm = *prm;
+    MVB_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    MVB_CUDA(cudaEventCreate(&s->ev0));
+    MVB_CUDA(cudaEventCreate(&s->ev1));
+    s->reps.resize(R);
+    s->h_reps.resize(R);
+    std::vector<std::shared_ptr<Graph>> graphs;
+    uint32_t max_n = 0, max_sh = 0;
+    for (uint32_t r = 0; r < R; ++r) {
+        const mvb_population* p = pops[r];
+        const mvb_tables* t = tabs[r];
+        Replica& rp = s->reps[r];
+        const uint32_t N = p->n_agents;
+        rp.N = N; rp.S = t->n_subcultures; rp.H = t->n_neighbourhoods;
+        rp.rec_width = rec_width(rp.S, rp.H);
+        rp.rec_off = s->rec_stride;
+        s->rec_stride += rp.rec_width;
+        max_n = std::max(max_n, N);
+        max_sh = std::max<uint32_t>(max_sh, smem_words(rp.S, rp.H));
+        // graph (shared when the caller passes the same arrays)
+        const void* key[4] = {p->social_rowptr, p->social_col, p->neighbour_rowptr, p->neighbour_col};
+        for (auto& g : graphs)
+            if (g->N == N && !memcmp(g->key, key, sizeof key)) rp.graph = g;
+        if (!rp.graph) {
+            auto g = std::make_shared<Graph>();
+            g->N = N; memcpy(g->key, key, sizeof key);
+            g->Es = p->social_rowptr[N]; g->En = p->neighbour_rowptr[N];
+            MVB_CUDA(g->s_rowptr.alloc(8 * ((size_t)N + 1)));
+            MVB_CUDA(g->n_rowptr.alloc(8 * ((size_t)N + 1)));
+            MVB_CUDA(g->s_col.alloc(4 * g->Es));
+            MVB_CUDA(g->n_col.alloc(4 * g->En));
+            MVB_CUDA(cudaMemcpyAsync(g->s_rowptr.p, p->social_rowptr, 8 * ((size_t)N + 1), cudaMemcpyHostToDevice, s->stream));
+            MVB_CUDA(cudaMemcpyAsync(g->n_rowptr.p, p->neighbour_rowptr, 8 * ((size_t)N + 1), cudaMemcpyHostToDevice, s->stream));
+            if (g->Es) MVB_CUDA(cudaMemcpyAsync(g->s_col.p, p->social_col, 4 * g->Es, cudaMemcpyHostToDevice, s->stream));
+            if (g->En) MVB_CUDA(cudaMemcpyAsync(g->n_col.p, p->neighbour_col, 4 * g->En, cudaMemcpyHostToDevice, s->stream));
+            graphs.push_back(g);
+            rp.graph = g;
+        }
+        // per-agent state
+        rp.h_stat.resize(N);
+        for (uint32_t i = 0; i < N; ++i)
+            rp.h_stat[i] = pack_static(p->neighbourhood[i], p->subculture[i], p->commute[i], p->owns_car[i] != 0, p->owns_bike[i] != 0);
+        MVB_CUDA(rp.stat.alloc(4 * (size_t)N));
+        MVB_CUDA(rp.ws.alloc(4 * (size_t)N));
+        MVB_CUDA(rp.habit.alloc(16 * (size_t)N));
+        MVB_CUDA(rp.mode[0].alloc(N));
+        MVB_CUDA(rp.mode[1].alloc(N));
+        MVB_CUDA(rp.norm.alloc(N));
+        MVB_CUDA(cudaMemcpyAsync(rp.stat.p, rp.h_stat.data(), 4 * (size_t)N, cudaMemcpyHostToDevice, s->stream));
+        MVB_CUDA(cudaMemcpyAsync(rp.ws.p, p->weather_sensitivity, 4 * (size_t)N, cudaMemcpyHostToDevice, s->stream));
+        MVB_CUDA(cudaMemcpyAsync(rp.habit.p, p->habit, 16 * (size_t)N, cudaMemcpyHostToDevice, s->stream));
+        MVB_CUDA(cudaMemcpyAsync(rp.mode[0].p, p->current_mode, N, cudaMemcpyHostToDevice, s->stream));
+        MVB_CUDA(cudaMemcpyAsync(rp.mode[1].p, p->current_mode, N, cudaMemcpyHostToDevice, s->stream));
+        MVB_CUDA(cudaMemcpyAsync(rp.norm.p, p->norm, N, cudaMemcpyHostToDevice, s->stream));
+        const float* pa_src[5] = {p->consistency, p->social_connectivity, p->subculture_connectivity,
+                                  p->neighbourhood_connectivity, p->average_weight};
+        const float pa_def[5] = {prm->consistency, prm->social_connectivity, prm->subculture_connectivity,
+                                 prm->neighbourhood_connectivity, prm->average_weight};
+        rp.per_agent = false;
+        for (int k = 0; k < 5; ++k) rp.per_agent |= (pa_src[k] != nullptr);
+        if (rp.per_agent) {
+            s->any_per_agent = true;
+            std::vector<float> pa((size_t)5 * N);
+            for (int k = 0; k < 5; ++k)
+                for (uint32_t i = 0; i < N; ++i) pa[(size_t)k * N + i] = pa_src[k] ? pa_src[k][i] : pa_def[k];
+            MVB_CUDA(rp.pa.alloc(20 * (size_t)N));
+            MVB_CUDA(cudaMemcpy(rp.pa.p, pa.data(), 20 * (size_t)N, cudaMemcpyHostToDevice));
+        }
+        // tables + residents
+        MVB_CUDA(rp.tables_f.alloc(sizeof(float) * 4 * (rp.H + rp.S)));
+        MVB_CUDA(rp.tables_u.alloc(sizeof(uint32_t) * 5 * rp.H));
+        MVB_CUDA(rp.cong.alloc(sizeof(float) * 4 * rp.H));
+        int rc = upload_tables(s, rp, t);
+        if (rc) return rc;
+        std::vector<uint32_t> nres(rp.H, 0);
+        for (uint32_t i = 0; i < N; ++i) nres[p->neighbourhood[i]]++;
+        MVB_CUDA(cudaMemcpy(rp.tables_u.as<uint32_t>() + 4 * rp.H, nres.data(), 4 * rp.H, cudaMemcpyHostToDevice));
+        std::vector<float> ones(4 * rp.H, 1.0f);      // default_congestion_modifier, neighbourhood.rs:34-41
+        MVB_CUDA(cudaMemcpy(rp.cong.p, ones.data(), 16 * rp.H, cudaMemcpyHostToDevice));
+
+        RepDev& d = s->h_reps[r];
+        d.N = N; d.S = rp.S; d.H = rp.H; d.rec_off = rp.rec_off;
+        d.stat = rp.stat.as<uint32_t>(); d.ws = rp.ws.as<float>(); d.habit = rp.habit.as<float4>();
+        d.mode[0] = rp.mode[0].as<uint8_t>(); d.mode[1] = rp.mode[1].as<uint8_t>(); d.norm = rp.norm.as<uint8_t>();
+        d.pa = rp.per_agent ? rp.pa.as<float>() : nullptr;
+        d.s_rowptr = rp.graph->s_rowptr.as<uint64_t>(); d.s_col = rp.graph->s_col.as<uint32_t>();
+        d.n_rowptr = rp.graph->n_rowptr.as<uint64_t>(); d.n_col = rp.graph->n_col.as<uint32_t>();
+        d.supp = rp.tables_f.as<float>(); d.desir = rp.tables_f.as<float>() + 4 * rp.H;
+        d.cap = rp.tables_u.as<uint32_t>(); d.nres = rp.tables_u.as<uint32_t>() + 4 * rp.H;
+        d.cong = rp.cong.as<float>();
+    }
+    s->max_blocks_x = (max_n + kBlock - 1) / kBlock;
+    s->smem_bytes = sizeof(uint32_t) * max_sh;
+    if (s->smem_bytes > 200 * 1024) { set_error("too many neighbourhoods/subcultures for the shared-memory tables"); return MVB_ERR_ARG; }
+    if (s->smem_bytes > 48 * 1024) {
+        MVB_CUDA(cudaFuncSetAttribute(day_kernel_simple<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
+        MVB_CUDA(cudaFuncSetAttribute(day_kernel_simple<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
+        MVB_CUDA(cudaFuncSetAttribute(census_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
+    }
+    MVB_CUDA(s->d_reps.alloc(sizeof(RepDev) * R));
+    int rc = upload_reps(s);
+    if (rc) return rc;
+    rc = ensure_rows(s, 8);
+    if (rc) return rc;
+    s->cursor = 0;
+    s->row_days.assign(1, 0);
+    rc = launch_census(s, 0);
+    if (rc) return rc;
+    MVB_CUDA(cudaStreamSynchronize(s->stream));
+    *out = sp.release();
+    return MVB_OK;
+}
+
+int mvb_create(const mvb_population* pop, const mvb_tables* tab, const mvb_params* prm, int device, mvb_sim** out) {
+    return mvb_create_batch(1, &pop, &tab, prm, device, out);
+}
+
+uint32_t mvb_n_replicas(const mvb_sim* s) { return s ? (uint32_t)s->reps.size() : 0; }
+uint32_t mvb_stats_width(const mvb_sim* s, uint32_t r) {
+    return (s && r < s->reps.size()) ? MVB_STATS_FIXED + s->reps[r].S + s->reps[r].H : 0;
+}
+void* mvb_stream(mvb_sim* s) { return s ? (void*)s->stream : nullptr; }
+
+int mvb_sync(mvb_sim* s) {
+    if (!s) { set_error("null handle"); return MVB_ERR_ARG; }
+    MVB_CUDA(cudaSetDevice(s->device));
+    MVB_CUDA(cudaStreamSynchronize(s->stream));
+    return MVB_OK;
+}
+
+int mvb_step(mvb_sim* s, uint8_t weather_today, uint8_t weather_changed) {
+    if (!s) { set_error("null handle"); return MVB_ERR_ARG; }
+    if (weather_today > 1) { set_error("weather code must be 0 or 1"); return MVB_ERR_ARG; }
+    MVB_CUDA(cudaSetDevice(s->device));
+    int rc = launch_day(s, weather_today, weather_changed ? 1 : 0);
+    if (rc) return rc;
+    s->row_days.push_back(s->row_days.back() + 1);
+    s->prev_weather = weather_today;
+    return MVB_OK;
+}
+
+int mvb_set_tables(mvb_sim* s, uint32_t r, const mvb_tables* t) {
+    if (!s || r >= s->reps.size()) { set_error("bad handle/replica"); return MVB_ERR_ARG; }
+    int rc = check_tables(t);
+    if (rc) return rc;
+    Replica& rp = s->reps[r];
+    if (t->n_subcultures != rp.S || t->n_neighbourhoods != rp.H) { set_error("table shape differs from the replica's"); return MVB_ERR_ARG; }
+    MVB_CUDA(cudaSetDevice(s->device));
+    return upload_tables(s, rp, t);
+}
+
+int mvb_set_ownership(mvb_sim* s, uint32_t r, const uint8_t* car, const uint8_t* bike) {
+    if (!s || r >= s->reps.size()) { set_error("bad handle/replica"); return MVB_ERR_ARG; }
+    if (!car && !bike) return MVB_OK;
+    Replica& rp = s->reps[r];
+    for (uint32_t i = 0; i < rp.N; ++i) {
+        uint32_t w = rp.h_stat[i];
+        if (car)  w = (w & ~(1u << 26)) | ((car[i] ? 1u : 0u) << 26);
+        if (bike) w = (w & ~(1u << 27)) | ((bike[i] ? 1u : 0u) << 27);
+        rp.h_stat[i] = w;
+    }
+    MVB_CUDA(cudaSetDevice(s->device));
+    MVB_CUDA(cudaMemcpyAsync(rp.stat.p, rp.h_stat.data(), 4 * (size_t)rp.N, cudaMemcpyHostToDevice, s->stream));
+    MVB_CUDA(cudaStreamSynchronize(s->stream));   // h_stat may be edited again right after return
+    return MVB_OK;
+}
+
+int mvb_reset_rows(mvb_sim* s) {
+    if (!s) { set_error("null handle"); return MVB_ERR_ARG; }
+    MVB_CUDA(cudaSetDevice(s->device));
+    if (s->cursor != 0) {
+        // keep the current census as row 0, zero the rest
+        MVB_CUDA(cudaMemcpyAsync(s->rec.p, s->rec.as<uint32_t>() + (size_t)s->cursor * s->rec_stride,
+                                 sizeof(uint32_t) * s->rec_stride, cudaMemcpyDeviceToDevice, s->stream));
+        MVB_CUDA(cudaMemsetAsync(s->rec.as<uint32_t>() + s->rec_stride, 0,
+                                 sizeof(uint32_t) * (size_t)(s->rec_cap - 1) * s->rec_stride, s->stream));
+        s->cursor = 0;
+    }
+    const uint32_t d = s->row_days.back();
+    s->row_days.assign(1, d);
+    return MVB_OK;
+}
+
+int mvb_run_async(mvb_sim* s, const uint8_t* weather, uint32_t first_day, uint32_t end_day,
+                  const mvb_intervention* const* ivs) {
+    if (!s || !weather) { set_error("null argument"); return MVB_ERR_ARG; }
+    if (end_day <= first_day) { set_error("empty day range"); return MVB_ERR_ARG; }
+    MVB_CUDA(cudaSetDevice(s->device));
+    uint32_t d0 = first_day;
+    if (first_day == 0) {
+        // simulation.rs:95-98: prev = weather[0]; row for day 0 = census of the current state
+        int rc = mvb_reset_rows(s);
+        if (rc) return rc;
+        s->row_days.assign(1, 0);
+        s->prev_weather = weather[0];
+        d0 = 1;
+    }
+    uint32_t n_week = 0;
+    for (uint32_t d = d0; d < end_day; ++d) n_week += (d % 7 < 5);
+    int rc = ensure_rows(s, n_week);
+    if (rc) return rc;
+    s->last_launches = 0;
+    MVB_CUDA(cudaEventRecord(s->ev0, s->stream));
+    for (uint32_t day = d0; day < end_day; ++day) {
+        if (ivs)
+            for (uint32_t r = 0; r < s->reps.size(); ++r) {
+                const mvb_intervention* iv = ivs[r];
+                if (!iv || iv->day != day) continue;                        // simulation.rs:103-105
+                if (iv->tables && (rc = mvb_set_tables(s, r, iv->tables))) return rc;
+                if ((rc = mvb_set_ownership(s, r, iv->owns_car, iv->owns_bike))) return rc;
+            }
+        if (day % 7 < 5) {                                                  // simulation.rs:108, 297-299
+            const uint8_t w = weather[day];
+            if (w > 1) { set_error("weather[%u] = %u is not a weather code", day, w); return MVB_ERR_ARG; }
+            if ((rc = launch_day(s, w, (uint8_t)(s->prev_weather != w)))) return rc;   // :113-128
+            s->prev_weather = w;                                            // :131
+            s->row_days.push_back(day);
+        }
+    }
+    MVB_CUDA(cudaEventRecord(s->ev1, s->stream));
+    s->timing_valid = true;
+    return MVB_OK;
+}
+
+static void record_to_row(const Replica& rp, const uint32_t* rec, uint32_t* row) {
+    // rec: hist[H][4] | joint[4] (index active*2+active_norm) | commute[3] | sub[S]
+    const uint32_t H = rp.H, S = rp.S;
+    const uint32_t* j = rec + 4 * H;
+    row[0] = j[2] + j[3];                 // ActiveMode
+    row[1] = j[1] + j[3];                 // ActiveNorm
+    row[2] = j[2];                        // ActiveModeCounterToInactiveNorm
+    row[3] = j[1];                        // InactiveModeCounterToActiveNorm
+    for (uint32_t c = 0; c < 3; ++c) row[4 + c] = rec[4 * H + 4 + c];
+    for (uint32_t k = 0; k < S; ++k) row[7 + k] = rec[4 * H + 7 + k];
+    for (uint32_t h = 0; h < H; ++h) row[7 + S + h] = rec[4 * h + 2] + rec[4 * h + 3];
+}
+
+int mvb_fetch_rows(mvb_sim* s, uint32_t* n_rows, uint32_t* days_out, uint32_t* rows_out, size_t cap_u32) {
+    if (!s) { set_error("null handle"); return MVB_ERR_ARG; }
+    MVB_CUDA(cudaSetDevice(s->device));
+    MVB_CUDA(cudaStreamSynchronize(s->stream));
+    const uint32_t rows = s->cursor + 1;
+    if (n_rows) *n_rows = rows;
+    if (days_out) memcpy(days_out, s->row_days.data(), sizeof(uint32_t) * rows);
+    if (rows_out) {
+        size_t need = 0;
+        for (auto& rp : s->reps) need += (size_t)rows * (MVB_STATS_FIXED + rp.S + rp.H);
+        if (cap_u32 < need) { set_error("rows buffer too small: need %zu u32, have %zu", need, cap_u32); return MVB_ERR_ARG; }
+        std::vector<uint32_t> rec((size_t)rows * s->rec_stride);
+        MVB_CUDA(cudaMemcpy(rec.data(), s->rec.p, sizeof(uint32_t) * rec.size(), cudaMemcpyDeviceToHost));
+        uint32_t* o = rows_out;
+        for (auto& rp : s->reps) {
+            const uint32_t W = MVB_STATS_FIXED + rp.S + rp.H;
+            for (uint32_t k = 0; k < rows; ++k, o += W)
+                record_to_row(rp, rec.data() + (size_t)k * s->rec_stride + rp.rec_off, o);
+        }
+    }
+    return MVB_OK;
+}
+
+int mvb_run(mvb_sim* s, const uint8_t* weather, uint32_t n_days, const mvb_intervention* const* ivs,
+            uint32_t* days_out, uint32_t* rows_out) {
+    if (!s || !weather || n_days == 0) { set_error("null argument"); return MVB_ERR_ARG; }
+    int rc;
+    if (n_days == 1) {
+        if ((rc = mvb_reset_rows(s))) return rc;
+        s->row_days.assign(1, 0);
+        s->prev_weather = weather[0];
+    } else if ((rc = mvb_run_async(s, weather, 0, n_days, ivs))) return rc;
+    size_t cap = 0;
+    for (auto& rp : s->reps) cap += (size_t)mvb_run_rows(n_days) * (MVB_STATS_FIXED + rp.S + rp.H);
+    return mvb_fetch_rows(s, nullptr, days_out, rows_out, rows_out ? cap : 0);
+}
+
+int mvb_last_run_stats(mvb_sim* s, float* ms, uint64_t* launches) {
+    if (!s) { set_error("null handle"); return MVB_ERR_ARG; }
+    if (!s->timing_valid) { set_error("no mvb_run / mvb_run_async yet"); return MVB_ERR_STATE; }
+    MVB_CUDA(cudaSetDevice(s->device));
+    MVB_CUDA(cudaEventSynchronize(s->ev1));
+    MVB_CUDA(cudaEventElapsedTime(&s->last_ms, s->ev0, s->ev1));
+    if (ms) *ms = s->last_ms;
+    if (launches) *launches = s->last_launches;
+    return MVB_OK;
+}
+
+int mvb_stats_row(mvb_sim* s, uint32_t r, uint32_t* row) {
+    if (!s || r >= s->reps.size() || !row) { set_error("bad argument"); return MVB_ERR_ARG; }
+    MVB_CUDA(cudaSetDevice(s->device));
+    std::vector<uint32_t> rec(s->reps[r].rec_width);
+    MVB_CUDA(cudaStreamSynchronize(s->stream));
+    MVB_CUDA(cudaMemcpy(rec.data(), s->rec.as<uint32_t>() + (size_t)s->cursor * s->rec_stride + s->reps[r].rec_off,
+                        sizeof(uint32_t) * rec.size(), cudaMemcpyDeviceToHost));
+    record_to_row(s->reps[r], rec.data(), row);
+    return MVB_OK;
+}
+
+int mvb_get_state(mvb_sim* s, uint32_t r, float* habit, uint8_t* cur, uint8_t* last, uint8_t* norm,
+                  uint32_t* hist, float* cong) {
+    if (!s || r >= s->reps.size()) { set_error("bad handle/replica"); return MVB_ERR_ARG; }
+    MVB_CUDA(cudaSetDevice(s->device));
+    MVB_CUDA(cudaStreamSynchronize(s->stream));
+    Replica& rp = s->reps[r];
+    if (habit) MVB_CUDA(cudaMemcpy(habit, rp.habit.p, 16 * (size_t)rp.N, cudaMemcpyDeviceToHost));
+    if (cur)   MVB_CUDA(cudaMemcpy(cur, rp.mode[s->parity].p, rp.N, cudaMemcpyDeviceToHost));
+    if (last)  MVB_CUDA(cudaMemcpy(last, rp.mode[s->stepped ? (s->parity ^ 1u) : s->parity].p, rp.N, cudaMemcpyDeviceToHost));
+    if (norm)  MVB_CUDA(cudaMemcpy(norm, rp.norm.p, rp.N, cudaMemcpyDeviceToHost));
+    if (hist)  MVB_CUDA(cudaMemcpy(hist, s->rec.as<uint32_t>() + (size_t)s->cursor * s->rec_stride + rp.rec_off,
+                                   sizeof(uint32_t) * 4 * rp.H, cudaMemcpyDeviceToHost));
+    if (cong)  MVB_CUDA(cudaMemcpy(cong, rp.cong.p, sizeof(float) * 4 * rp.H, cudaMemcpyDeviceToHost));
+    return MVB_OK;
+}
+
+uint64_t mvb_algorithmic_bytes_per_day(const mvb_sim* s, uint32_t r) {
+    if (!s || r >= s->reps.size()) return 0;
+    const Replica& rp = s->reps[r];
+    return 4ull * (rp.graph->Es + rp.graph->En) + 51ull * rp.N;
+}
+
+}  // extern "C"

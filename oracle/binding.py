@@ -1,0 +1,121 @@
+"""ctypes binding of the CPU oracle (oracle/motivate_oracle.c).  TEST INFRASTRUCTURE ONLY:
+imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs — never by the product package."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+
+from motivate_b200 import _ffi
+from motivate_b200.api import InterventionData, PopulationData, TablesData, _ptr, run_rows
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmotivate_oracle.so")
+_libs = {}
+
+
+def build(native=False, out=None):
+    """Compile the oracle with gcc.  native=True adds -O3 -march=native (the README's intent for the
+    reference's release build, README.md:89-92) for CPU-baseline timing on the box it runs on."""
+    out = out or LIB_PATH
+    flags = ["-O3", "-march=native"] if native else ["-O2", "-march=x86-64-v2"]
+    cmd = ["gcc", *flags, "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-std=c11", "-shared",
+           "-o", out, os.path.join(_HERE, "motivate_oracle.c")]
+    subprocess.run(cmd, check=True)
+    return out
+
+
+def load(native=False):
+    key = "native" if native else "portable"
+    if key in _libs:
+        return _libs[key]
+    path = LIB_PATH
+    if native:
+        path = os.path.join(tempfile.gettempdir(), f"libmotivate_oracle_native_{os.getpid()}.so")
+        try:
+            build(native=True, out=path)
+        except Exception:
+            return load(False)
+    elif not os.path.exists(path):
+        build()
+    lib = C.CDLL(path, mode=C.RTLD_LOCAL)
+    P = C.c_void_p
+    sig = {
+        "mvo_create": (C.c_int, [_ffi.PopP, _ffi.TabP, _ffi.PrmP, C.POINTER(P)]),
+        "mvo_destroy": (None, [P]),
+        "mvo_step": (C.c_int, [P, C.c_uint8, C.c_uint8]),
+        "mvo_run": (C.c_int, [P, _ffi.u8p, C.c_uint32, _ffi.IvP, _ffi.u32p, _ffi.u32p]),
+        "mvo_run_rows": (C.c_uint32, [C.c_uint32]),
+        "mvo_set_tables": (C.c_int, [P, _ffi.TabP]),
+        "mvo_set_ownership": (C.c_int, [P, _ffi.u8p, _ffi.u8p]),
+        "mvo_stats_row": (C.c_int, [P, _ffi.u32p]),
+        "mvo_get_state": (C.c_int, [P, _ffi.f32p, _ffi.u8p, _ffi.u8p, _ffi.u8p, _ffi.u32p, _ffi.f32p]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    _libs[key] = lib
+    return lib
+
+
+class OracleSimulation:
+    """One replica on the CPU oracle; same method names as motivate_b200.Simulation."""
+
+    def __init__(self, pop: PopulationData, tab: TablesData, params, native=False):
+        self._lib = load(native)
+        self.pop, self.tab, self.params = pop, tab, params
+        self._h = C.c_void_p()
+        rc = self._lib.mvo_create(C.byref(pop.struct()), C.byref(tab.struct()), C.byref(params), C.byref(self._h))
+        if rc:
+            raise RuntimeError(f"mvo_create failed: {rc}")
+        self.width = 7 + tab.S + tab.H
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.mvo_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def step(self, weather_today, weather_changed):
+        self._lib.mvo_step(self._h, int(weather_today), int(bool(weather_changed)))
+
+    def run(self, weather, n_days=None, intervention: InterventionData | None = None):
+        weather = np.ascontiguousarray(weather, np.uint8)
+        n_days = len(weather) if n_days is None else n_days
+        rows = run_rows(n_days)
+        days = np.zeros(rows, np.uint32)
+        out = np.zeros((rows, self.width), np.uint32)
+        iv = C.byref(intervention.struct()) if intervention is not None else None
+        rc = self._lib.mvo_run(self._h, _ptr(weather, _ffi.u8p), n_days, iv, _ptr(days, _ffi.u32p), _ptr(out, _ffi.u32p))
+        if rc:
+            raise RuntimeError(f"mvo_run failed: {rc}")
+        return days, out
+
+    def set_tables(self, tab: TablesData):
+        self._lib.mvo_set_tables(self._h, C.byref(tab.struct()))
+        self.tab = tab
+
+    def set_ownership(self, owns_car=None, owns_bike=None):
+        car = None if owns_car is None else np.ascontiguousarray(owns_car, np.uint8)
+        bike = None if owns_bike is None else np.ascontiguousarray(owns_bike, np.uint8)
+        self._lib.mvo_set_ownership(self._h, _ptr(car, _ffi.u8p), _ptr(bike, _ffi.u8p))
+
+    def stats_row(self):
+        row = np.zeros(self.width, np.uint32)
+        self._lib.mvo_stats_row(self._h, _ptr(row, _ffi.u32p))
+        return row
+
+    def get_state(self):
+        N, H = self.pop.n_agents, self.tab.H
+        st = dict(habit=np.zeros((N, 4), np.float32), current_mode=np.zeros(N, np.uint8),
+                  last_mode=np.zeros(N, np.uint8), norm=np.zeros(N, np.uint8),
+                  hist=np.zeros((H, 4), np.uint32), congestion=np.zeros((H, 4), np.float32))
+        self._lib.mvo_get_state(self._h, _ptr(st["habit"], _ffi.f32p), _ptr(st["current_mode"], _ffi.u8p),
+                                _ptr(st["last_mode"], _ffi.u8p), _ptr(st["norm"], _ffi.u8p),
+                                _ptr(st["hist"], _ffi.u32p), _ptr(st["congestion"], _ffi.f32p))
+        return st
