@@ -4,12 +4,14 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <numeric>
 #include <cstring>
 #include <memory>
 #include <new>
 #include <vector>
 
 #include "day_kernels.cuh"
+#include "layout.h"
 #include "mvb_internal.h"
 
 using namespace mvb;
@@ -32,20 +34,20 @@ struct DevBuf {                       // owning device allocation
     template <class T> T* as() const { return (T*)p; }
 };
 
-// The graph of one population, shareable between replicas (scenario sweeps).
+// The link graph of one population in device layout (layout.h), shareable between replicas
+// (scenario sweeps over one population pass the same graph + neighbourhood arrays).
 struct Graph {
-    uint32_t N = 0;
-    uint64_t Es = 0, En = 0;
-    DevBuf s_rowptr, s_col, n_rowptr, n_col;
-    const void* key[4] = {nullptr, nullptr, nullptr, nullptr};   // caller pointers it was built from
+    GraphLayout L;                 // host copy: permutation, sizes (code arrays are released after upload)
+    DevBuf deg, ranges, hub_rowptr, hub_ds, hub_dn, hub_codes, sell_off, sell_K, sell_order, sell_codes;
+    const void* key[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // caller pointers it was built from
 };
 
 struct Replica {
     uint32_t N = 0, S = 0, H = 0;
     uint32_t rec_width = 0, rec_off = 0;
     std::shared_ptr<Graph> graph;
-    DevBuf stat, ws, habit, mode[2], norm, pa, tables_f, tables_u, cong;
-    std::vector<uint32_t> h_stat;       // host mirror of the packed static words (ownership edits)
+    DevBuf stat, ws, habit, vec[2], normvec, pa, tables_f, tables_u, cong;
+    std::vector<uint32_t> h_stat;       // host mirror of the packed static words, internal order (ownership edits)
     bool per_agent = false;
 };
 
@@ -60,8 +62,10 @@ struct mvb_sim {
     DevBuf d_reps;                       // RepDev[R]
     std::vector<RepDev> h_reps;
     uint32_t rec_stride = 0;             // u32 per record row (all replicas)
-    uint32_t max_blocks_x = 0;
-    size_t smem_bytes = 0;
+    uint32_t grid = 0, P = 1;            // persistent blocks, parts per replica
+    uint32_t max_npad = 0;
+    uint32_t vec_cap_words = 0;          // shared-memory words reserved for the staged mode vector
+    size_t smem_bytes = 0, census_smem = 0;
     bool any_per_agent = false;
     // record ring: rows [0, rec_cap); row `cursor` holds the census of the current state
     DevBuf rec;
@@ -105,8 +109,8 @@ int ensure_rows(mvb_sim* s, uint32_t n) {
 int launch_census(mvb_sim* s, uint32_t row) {
     uint32_t* rec = s->rec.as<uint32_t>() + (size_t)row * s->rec_stride;
     MVB_CUDA(cudaMemsetAsync(rec, 0, sizeof(uint32_t) * s->rec_stride, s->stream));
-    dim3 grid(s->max_blocks_x, (unsigned)s->reps.size());
-    census_kernel<<<grid, kBlock, s->smem_bytes, s->stream>>>(s->d_reps.as<RepDev>(), s->parity, rec);
+    dim3 grid((s->max_npad + kBlock - 1) / kBlock, (unsigned)s->reps.size());
+    census_kernel<<<grid, kBlock, s->census_smem, s->stream>>>(s->d_reps.as<RepDev>(), s->parity, rec);
     MVB_CUDA(cudaGetLastError());
     return MVB_OK;
 }
@@ -116,21 +120,48 @@ int launch_day(mvb_sim* s, uint8_t weather, uint8_t changed) {
     if (rc) return rc;
     const uint32_t* prev = s->rec.as<uint32_t>() + (size_t)s->cursor * s->rec_stride;
     uint32_t* next = s->rec.as<uint32_t>() + (size_t)(s->cursor + 1) * s->rec_stride;
-    dim3 grid(s->max_blocks_x, (unsigned)s->reps.size());
     AgentWeights uw{s->prm.consistency, s->prm.social_connectivity, s->prm.subculture_connectivity,
                     s->prm.neighbourhood_connectivity, s->prm.average_weight};
+    const uint32_t R = (uint32_t)s->reps.size();
     if (s->any_per_agent)
-        day_kernel_simple<true><<<grid, kBlock, s->smem_bytes, s->stream>>>(
-            s->d_reps.as<RepDev>(), s->parity, prev, next, weather, changed, uw);
+        day_kernel<true><<<s->grid, kThreads, s->smem_bytes, s->stream>>>(
+            s->d_reps.as<RepDev>(), R, s->P, s->parity, prev, next, weather, changed, uw, s->vec_cap_words);
     else
-        day_kernel_simple<false><<<grid, kBlock, s->smem_bytes, s->stream>>>(
-            s->d_reps.as<RepDev>(), s->parity, prev, next, weather, changed, uw);
+        day_kernel<false><<<s->grid, kThreads, s->smem_bytes, s->stream>>>(
+            s->d_reps.as<RepDev>(), R, s->P, s->parity, prev, next, weather, changed, uw, s->vec_cap_words);
     MVB_CUDA(cudaGetLastError());
     s->cursor++;
     s->parity ^= 1u;
     s->stepped = true;
     s->last_launches++;
     return MVB_OK;
+}
+
+template <class T>
+int upload(DevBuf& b, const std::vector<T>& v, cudaStream_t st) {
+    MVB_CUDA(b.alloc(sizeof(T) * v.size()));
+    if (!v.empty()) MVB_CUDA(cudaMemcpyAsync(b.p, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice, st));
+    return MVB_OK;
+}
+
+// 32 two-bit values -> the u64 of one slice (lanes 0-15 in .x, 16-31 in .y), as finish_slice packs them
+void pack_slices(const std::vector<uint32_t>& int2ext, const uint8_t* values, std::vector<uint2>& out) {
+    out.assign(int2ext.size() / 32, make_uint2(0, 0));
+    for (size_t i = 0; i < int2ext.size(); ++i) {
+        if (int2ext[i] == kInvalid) continue;
+        const uint32_t v = values[int2ext[i]] & 3u, l = (uint32_t)(i & 31);
+        uint2& w = out[i >> 5];
+        (l < 16 ? w.x : w.y) |= v << ((l & 15u) * 2u);
+    }
+}
+
+void unpack_slices(const std::vector<uint32_t>& int2ext, const std::vector<uint2>& in, uint8_t* values) {
+    for (size_t i = 0; i < int2ext.size(); ++i) {
+        if (int2ext[i] == kInvalid) continue;
+        const uint32_t l = (uint32_t)(i & 31);
+        const uint2 w = in[i >> 5];
+        values[int2ext[i]] = (uint8_t)(((l < 16 ? w.x : w.y) >> ((l & 15u) * 2u)) & 3u);
+    }
 }
 
 int check_tables(const mvb_tables* t) {
@@ -225,10 +256,32 @@ int mvb_create_batch(uint32_t R, const mvb_population* const* pops, const mvb_ta
     MVB_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     MVB_CUDA(cudaEventCreate(&s->ev0));
     MVB_CUDA(cudaEventCreate(&s->ev1));
+
+    // shared-memory budget: everything the device lets one block opt in to (227 KB on B200); what the
+    // tables do not need holds the staged mode vector
+    int sms = 0, smem_optin = 0;
+    MVB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    MVB_CUDA(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    uint32_t tail_max = 0, census_words = 0;
+    for (uint32_t r = 0; r < R; ++r) {
+        tail_max = std::max(tail_max, tail_words(tabs[r]->n_subcultures, tabs[r]->n_neighbourhoods));
+        census_words = std::max(census_words, rec_width(tabs[r]->n_subcultures, tabs[r]->n_neighbourhoods));
+    }
+    tail_max = (tail_max + 3u) & ~3u;
+    if ((uint64_t)tail_max * 4 + 4096 > (uint64_t)smem_optin) {
+        set_error("too many neighbourhoods/subcultures: the per-block tables need %u bytes of shared memory", tail_max * 4);
+        return MVB_ERR_ARG;
+    }
+    s->smem_bytes = (size_t)smem_optin;
+    s->vec_cap_words = ((uint32_t)smem_optin / 4 - tail_max) & ~3u;
+    s->census_smem = sizeof(uint32_t) * census_words;
+    const uint32_t capacity_agents = s->vec_cap_words * 16u / 64u * 64u;
+    s->grid = (uint32_t)sms;
+    s->P = s->grid / std::gcd(R, s->grid);              // R*P parts = lcm(R, grid): every block gets the same number
+
     s->reps.resize(R);
     s->h_reps.resize(R);
     std::vector<std::shared_ptr<Graph>> graphs;
-    uint32_t max_n = 0, max_sh = 0;
     for (uint32_t r = 0; r < R; ++r) {
         const mvb_population* p = pops[r];
         const mvb_tables* t = tabs[r];
@@ -238,88 +291,102 @@ int mvb_create_batch(uint32_t R, const mvb_population* const* pops, const mvb_ta
         rp.rec_width = rec_width(rp.S, rp.H);
         rp.rec_off = s->rec_stride;
         s->rec_stride += rp.rec_width;
-        max_n = std::max(max_n, N);
-        max_sh = std::max<uint32_t>(max_sh, smem_words(rp.S, rp.H));
-        // graph (shared when the caller passes the same arrays)
-        const void* key[4] = {p->social_rowptr, p->social_col, p->neighbour_rowptr, p->neighbour_col};
+        // graph layout (shared when the caller passes the same graph and neighbourhood arrays)
+        const void* key[5] = {p->social_rowptr, p->social_col, p->neighbour_rowptr, p->neighbour_col, p->neighbourhood};
         for (auto& g : graphs)
-            if (g->N == N && !memcmp(g->key, key, sizeof key)) rp.graph = g;
+            if (g->L.N == N && !memcmp(g->key, key, sizeof key)) rp.graph = g;
         if (!rp.graph) {
             auto g = std::make_shared<Graph>();
-            g->N = N; memcpy(g->key, key, sizeof key);
-            g->Es = p->social_rowptr[N]; g->En = p->neighbour_rowptr[N];
-            MVB_CUDA(g->s_rowptr.alloc(8 * ((size_t)N + 1)));
-            MVB_CUDA(g->n_rowptr.alloc(8 * ((size_t)N + 1)));
-            MVB_CUDA(g->s_col.alloc(4 * g->Es));
-            MVB_CUDA(g->n_col.alloc(4 * g->En));
-            MVB_CUDA(cudaMemcpyAsync(g->s_rowptr.p, p->social_rowptr, 8 * ((size_t)N + 1), cudaMemcpyHostToDevice, s->stream));
-            MVB_CUDA(cudaMemcpyAsync(g->n_rowptr.p, p->neighbour_rowptr, 8 * ((size_t)N + 1), cudaMemcpyHostToDevice, s->stream));
-            if (g->Es) MVB_CUDA(cudaMemcpyAsync(g->s_col.p, p->social_col, 4 * g->Es, cudaMemcpyHostToDevice, s->stream));
-            if (g->En) MVB_CUDA(cudaMemcpyAsync(g->n_col.p, p->neighbour_col, 4 * g->En, cudaMemcpyHostToDevice, s->stream));
+            memcpy(g->key, key, sizeof key);
+            int rc = build_graph_layout(*p, rp.H, capacity_agents, g->L);
+            if (rc) return rc;
+            GraphLayout& L = g->L;
+            if ((rc = upload(g->deg, L.deg, s->stream)) || (rc = upload(g->ranges, L.ranges, s->stream)) ||
+                (rc = upload(g->hub_rowptr, L.hub_rowptr, s->stream)) || (rc = upload(g->hub_ds, L.hub_ds, s->stream)) ||
+                (rc = upload(g->hub_dn, L.hub_dn, s->stream)) || (rc = upload(g->hub_codes, L.hub_codes, s->stream)) ||
+                (rc = upload(g->sell_off, L.sell_off, s->stream)) || (rc = upload(g->sell_K, L.sell_K, s->stream)) ||
+                (rc = upload(g->sell_order, L.sell_order, s->stream)) || (rc = upload(g->sell_codes, L.sell_codes, s->stream)))
+                return rc;
+            MVB_CUDA(cudaStreamSynchronize(s->stream));
+            std::vector<uint32_t>().swap(L.hub_codes);           // the big arrays now live on the device only
+            std::vector<uint32_t>().swap(L.sell_codes);
+            std::vector<uint32_t>().swap(L.deg);
             graphs.push_back(g);
             rp.graph = g;
         }
-        // per-agent state
-        rp.h_stat.resize(N);
-        for (uint32_t i = 0; i < N; ++i)
-            rp.h_stat[i] = pack_static(p->neighbourhood[i], p->subculture[i], p->commute[i], p->owns_car[i] != 0, p->owns_bike[i] != 0);
-        MVB_CUDA(rp.stat.alloc(4 * (size_t)N));
-        MVB_CUDA(rp.ws.alloc(4 * (size_t)N));
-        MVB_CUDA(rp.habit.alloc(16 * (size_t)N));
-        MVB_CUDA(rp.mode[0].alloc(N));
-        MVB_CUDA(rp.mode[1].alloc(N));
-        MVB_CUDA(rp.norm.alloc(N));
-        MVB_CUDA(cudaMemcpyAsync(rp.stat.p, rp.h_stat.data(), 4 * (size_t)N, cudaMemcpyHostToDevice, s->stream));
-        MVB_CUDA(cudaMemcpyAsync(rp.ws.p, p->weather_sensitivity, 4 * (size_t)N, cudaMemcpyHostToDevice, s->stream));
-        MVB_CUDA(cudaMemcpyAsync(rp.habit.p, p->habit, 16 * (size_t)N, cudaMemcpyHostToDevice, s->stream));
-        MVB_CUDA(cudaMemcpyAsync(rp.mode[0].p, p->current_mode, N, cudaMemcpyHostToDevice, s->stream));
-        MVB_CUDA(cudaMemcpyAsync(rp.mode[1].p, p->current_mode, N, cudaMemcpyHostToDevice, s->stream));
-        MVB_CUDA(cudaMemcpyAsync(rp.norm.p, p->norm, N, cudaMemcpyHostToDevice, s->stream));
+        const GraphLayout& L = rp.graph->L;
+        const uint32_t NP = L.N_pad;
+        s->max_npad = std::max(s->max_npad, NP);
+        // per-agent state in internal order
+        rp.h_stat.assign(NP, 0u);
+        std::vector<float> ws(NP, 0.f), habit((size_t)4 * NP, 0.f);
+        for (uint32_t i = 0; i < NP; ++i) {
+            const uint32_t e = L.int2ext[i];
+            if (e == kInvalid) continue;
+            rp.h_stat[i] = kStatValid | pack_static(p->neighbourhood[e], p->subculture[e], p->commute[e],
+                                                    p->owns_car[e] != 0, p->owns_bike[e] != 0);
+            ws[i] = p->weather_sensitivity[e];
+            memcpy(&habit[(size_t)4 * i], p->habit + (size_t)4 * e, 16);
+        }
+        std::vector<uint2> mv, nv;
+        pack_slices(L.int2ext, p->current_mode, mv);
+        pack_slices(L.int2ext, p->norm, nv);
+        int rc;
+        if ((rc = upload(rp.stat, rp.h_stat, s->stream)) || (rc = upload(rp.ws, ws, s->stream)) ||
+            (rc = upload(rp.habit, habit, s->stream)) || (rc = upload(rp.vec[0], mv, s->stream)) ||
+            (rc = upload(rp.vec[1], mv, s->stream)) || (rc = upload(rp.normvec, nv, s->stream)))
+            return rc;
         const float* pa_src[5] = {p->consistency, p->social_connectivity, p->subculture_connectivity,
                                   p->neighbourhood_connectivity, p->average_weight};
         const float pa_def[5] = {prm->consistency, prm->social_connectivity, prm->subculture_connectivity,
                                  prm->neighbourhood_connectivity, prm->average_weight};
         rp.per_agent = false;
         for (int k = 0; k < 5; ++k) rp.per_agent |= (pa_src[k] != nullptr);
+        std::vector<float> pa;
         if (rp.per_agent) {
             s->any_per_agent = true;
-            std::vector<float> pa((size_t)5 * N);
+            pa.assign((size_t)5 * NP, 0.f);
             for (int k = 0; k < 5; ++k)
-                for (uint32_t i = 0; i < N; ++i) pa[(size_t)k * N + i] = pa_src[k] ? pa_src[k][i] : pa_def[k];
-            MVB_CUDA(rp.pa.alloc(20 * (size_t)N));
-            MVB_CUDA(cudaMemcpy(rp.pa.p, pa.data(), 20 * (size_t)N, cudaMemcpyHostToDevice));
+                for (uint32_t i = 0; i < NP; ++i) {
+                    const uint32_t e = L.int2ext[i];
+                    pa[(size_t)k * NP + i] = e == kInvalid ? pa_def[k] : (pa_src[k] ? pa_src[k][e] : pa_def[k]);
+                }
+            if ((rc = upload(rp.pa, pa, s->stream))) return rc;
         }
         // tables + residents
         MVB_CUDA(rp.tables_f.alloc(sizeof(float) * 4 * (rp.H + rp.S)));
         MVB_CUDA(rp.tables_u.alloc(sizeof(uint32_t) * 5 * rp.H));
         MVB_CUDA(rp.cong.alloc(sizeof(float) * 4 * rp.H));
-        int rc = upload_tables(s, rp, t);
-        if (rc) return rc;
+        if ((rc = upload_tables(s, rp, t))) return rc;
         std::vector<uint32_t> nres(rp.H, 0);
         for (uint32_t i = 0; i < N; ++i) nres[p->neighbourhood[i]]++;
-        MVB_CUDA(cudaMemcpy(rp.tables_u.as<uint32_t>() + 4 * rp.H, nres.data(), 4 * rp.H, cudaMemcpyHostToDevice));
+        MVB_CUDA(cudaMemcpyAsync(rp.tables_u.as<uint32_t>() + 4 * rp.H, nres.data(), 4 * rp.H, cudaMemcpyHostToDevice, s->stream));
         std::vector<float> ones(4 * rp.H, 1.0f);      // default_congestion_modifier, neighbourhood.rs:34-41
-        MVB_CUDA(cudaMemcpy(rp.cong.p, ones.data(), 16 * rp.H, cudaMemcpyHostToDevice));
+        MVB_CUDA(cudaMemcpyAsync(rp.cong.p, ones.data(), 16 * rp.H, cudaMemcpyHostToDevice, s->stream));
+        MVB_CUDA(cudaStreamSynchronize(s->stream));   // the host staging vectors above go out of scope
 
+        Graph& g = *rp.graph;
         RepDev& d = s->h_reps[r];
-        d.N = N; d.S = rp.S; d.H = rp.H; d.rec_off = rp.rec_off;
+        d.N = N; d.N_pad = NP; d.S = rp.S; d.H = rp.H; d.rec_off = rp.rec_off;
+        d.n_hub_slices = L.n_hub_slices; d.n_sell_slices = L.n_sell_slices;
+        d.n_ranges = (uint32_t)L.ranges.size(); d.hot_words = L.hot_words;
         d.stat = rp.stat.as<uint32_t>(); d.ws = rp.ws.as<float>(); d.habit = rp.habit.as<float4>();
-        d.mode[0] = rp.mode[0].as<uint8_t>(); d.mode[1] = rp.mode[1].as<uint8_t>(); d.norm = rp.norm.as<uint8_t>();
         d.pa = rp.per_agent ? rp.pa.as<float>() : nullptr;
-        d.s_rowptr = rp.graph->s_rowptr.as<uint64_t>(); d.s_col = rp.graph->s_col.as<uint32_t>();
-        d.n_rowptr = rp.graph->n_rowptr.as<uint64_t>(); d.n_col = rp.graph->n_col.as<uint32_t>();
+        d.vec[0] = rp.vec[0].as<uint2>(); d.vec[1] = rp.vec[1].as<uint2>(); d.normvec = rp.normvec.as<uint2>();
+        d.deg = g.deg.as<uint32_t>(); d.ranges = g.ranges.as<StageRange>();
+        d.hub_rowptr = g.hub_rowptr.as<uint64_t>(); d.hub_ds = g.hub_ds.as<uint32_t>(); d.hub_dn = g.hub_dn.as<uint32_t>();
+        d.hub_codes = g.hub_codes.as<uint32_t>();
+        d.sell_off = g.sell_off.as<uint64_t>(); d.sell_K = g.sell_K.as<uint32_t>(); d.sell_order = g.sell_order.as<uint32_t>();
+        d.sell_codes = g.sell_codes.as<uint32_t>();
         d.supp = rp.tables_f.as<float>(); d.desir = rp.tables_f.as<float>() + 4 * rp.H;
         d.cap = rp.tables_u.as<uint32_t>(); d.nres = rp.tables_u.as<uint32_t>() + 4 * rp.H;
         d.cong = rp.cong.as<float>();
+        if (L.hot_words > s->vec_cap_words) { set_error("internal: staged vector larger than its shared-memory slot"); return MVB_ERR_STATE; }
     }
-    s->max_blocks_x = (max_n + kBlock - 1) / kBlock;
-    s->smem_bytes = sizeof(uint32_t) * max_sh;
-    if (s->smem_bytes > 200 * 1024) { set_error("too many neighbourhoods/subcultures for the shared-memory tables"); return MVB_ERR_ARG; }
-    if (s->smem_bytes > 48 * 1024) {
-        MVB_CUDA(cudaFuncSetAttribute(day_kernel_simple<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
-        MVB_CUDA(cudaFuncSetAttribute(day_kernel_simple<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
-        MVB_CUDA(cudaFuncSetAttribute(census_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
-    }
+    MVB_CUDA(cudaFuncSetAttribute(day_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
+    MVB_CUDA(cudaFuncSetAttribute(day_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
+    if (s->census_smem > 48 * 1024)
+        MVB_CUDA(cudaFuncSetAttribute(census_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->census_smem));
     MVB_CUDA(s->d_reps.alloc(sizeof(RepDev) * R));
     int rc = upload_reps(s);
     if (rc) return rc;
@@ -376,14 +443,17 @@ int mvb_set_ownership(mvb_sim* s, uint32_t r, const uint8_t* car, const uint8_t*
     if (!s || r >= s->reps.size()) { set_error("bad handle/replica"); return MVB_ERR_ARG; }
     if (!car && !bike) return MVB_OK;
     Replica& rp = s->reps[r];
-    for (uint32_t i = 0; i < rp.N; ++i) {
+    const std::vector<uint32_t>& int2ext = rp.graph->L.int2ext;
+    for (size_t i = 0; i < int2ext.size(); ++i) {
+        const uint32_t e = int2ext[i];
+        if (e == kInvalid) continue;
         uint32_t w = rp.h_stat[i];
-        if (car)  w = (w & ~(1u << 26)) | ((car[i] ? 1u : 0u) << 26);
-        if (bike) w = (w & ~(1u << 27)) | ((bike[i] ? 1u : 0u) << 27);
+        if (car)  w = (w & ~(1u << 26)) | ((car[e] ? 1u : 0u) << 26);
+        if (bike) w = (w & ~(1u << 27)) | ((bike[e] ? 1u : 0u) << 27);
         rp.h_stat[i] = w;
     }
     MVB_CUDA(cudaSetDevice(s->device));
-    MVB_CUDA(cudaMemcpyAsync(rp.stat.p, rp.h_stat.data(), 4 * (size_t)rp.N, cudaMemcpyHostToDevice, s->stream));
+    MVB_CUDA(cudaMemcpyAsync(rp.stat.p, rp.h_stat.data(), 4 * rp.h_stat.size(), cudaMemcpyHostToDevice, s->stream));
     MVB_CUDA(cudaStreamSynchronize(s->stream));   // h_stat may be edited again right after return
     return MVB_OK;
 }
@@ -523,10 +593,27 @@ int mvb_get_state(mvb_sim* s, uint32_t r, float* habit, uint8_t* cur, uint8_t* l
     MVB_CUDA(cudaSetDevice(s->device));
     MVB_CUDA(cudaStreamSynchronize(s->stream));
     Replica& rp = s->reps[r];
-    if (habit) MVB_CUDA(cudaMemcpy(habit, rp.habit.p, 16 * (size_t)rp.N, cudaMemcpyDeviceToHost));
-    if (cur)   MVB_CUDA(cudaMemcpy(cur, rp.mode[s->parity].p, rp.N, cudaMemcpyDeviceToHost));
-    if (last)  MVB_CUDA(cudaMemcpy(last, rp.mode[s->stepped ? (s->parity ^ 1u) : s->parity].p, rp.N, cudaMemcpyDeviceToHost));
-    if (norm)  MVB_CUDA(cudaMemcpy(norm, rp.norm.p, rp.N, cudaMemcpyDeviceToHost));
+    const std::vector<uint32_t>& int2ext = rp.graph->L.int2ext;
+    const size_t NP = int2ext.size();
+    if (habit) {
+        std::vector<float> h(4 * NP);
+        MVB_CUDA(cudaMemcpy(h.data(), rp.habit.p, 16 * NP, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < NP; ++i)
+            if (int2ext[i] != kInvalid) memcpy(habit + (size_t)4 * int2ext[i], &h[4 * i], 16);
+    }
+    std::vector<uint2> v(NP / 32);
+    if (cur) {
+        MVB_CUDA(cudaMemcpy(v.data(), rp.vec[s->parity].p, 8 * v.size(), cudaMemcpyDeviceToHost));
+        unpack_slices(int2ext, v, cur);
+    }
+    if (last) {
+        MVB_CUDA(cudaMemcpy(v.data(), rp.vec[s->stepped ? (s->parity ^ 1u) : s->parity].p, 8 * v.size(), cudaMemcpyDeviceToHost));
+        unpack_slices(int2ext, v, last);
+    }
+    if (norm) {
+        MVB_CUDA(cudaMemcpy(v.data(), rp.normvec.p, 8 * v.size(), cudaMemcpyDeviceToHost));
+        unpack_slices(int2ext, v, norm);
+    }
     if (hist)  MVB_CUDA(cudaMemcpy(hist, s->rec.as<uint32_t>() + (size_t)s->cursor * s->rec_stride + rp.rec_off,
                                    sizeof(uint32_t) * 4 * rp.H, cudaMemcpyDeviceToHost));
     if (cong)  MVB_CUDA(cudaMemcpy(cong, rp.cong.p, sizeof(float) * 4 * rp.H, cudaMemcpyDeviceToHost));
@@ -536,7 +623,7 @@ int mvb_get_state(mvb_sim* s, uint32_t r, float* habit, uint8_t* cur, uint8_t* l
 uint64_t mvb_algorithmic_bytes_per_day(const mvb_sim* s, uint32_t r) {
     if (!s || r >= s->reps.size()) return 0;
     const Replica& rp = s->reps[r];
-    return 4ull * (rp.graph->Es + rp.graph->En) + 51ull * rp.N;
+    return 4ull * (rp.graph->L.Es + rp.graph->L.En) + 51ull * rp.N;
 }
 
 }  // extern "C"

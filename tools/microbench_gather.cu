@@ -24,14 +24,14 @@ __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
     return v;
 }
 
-template <int V>
+template <int V, int U>
 __global__ void __launch_bounds__(1024, 1)
 gather_kernel(const uint4* __restrict__ idx, size_t n_vec, const uint8_t* __restrict__ mode8,
               const uint32_t* __restrict__ mode2, uint32_t n_agents, uint32_t n_smem_words, unsigned long long* out) {
     extern __shared__ uint32_t s_mode[];
     uint32_t* remote = nullptr;
     uint32_t half_words = 0, my_rank = 0;
-    if (V == 3) {
+    if (V == 3 || V == 5) {
         for (uint32_t k = threadIdx.x; k < n_smem_words; k += blockDim.x) s_mode[k] = mode2[k];
         __syncthreads();
     }
@@ -45,26 +45,36 @@ gather_kernel(const uint4* __restrict__ idx, size_t n_vec, const uint8_t* __rest
     }
     uint32_t acc = 0;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
-        const uint4 v = ldg_stream(idx + i);
-        const uint32_t j[4] = {v.x, v.y, v.z, v.w};
+    for (size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n_vec; i0 += stride * U) {
+        uint4 vv[U];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            uint32_t m;
-            if (V == 0) m = j[k] & 3u;
-            if (V == 1) m = __ldg(mode8 + j[k]);
-            if (V == 2) m = (__ldg(mode2 + (j[k] >> 4)) >> ((j[k] & 15u) * 2u)) & 3u;
-            if (V == 3) {
-                const uint32_t jj = j[k] < n_smem_words * 16u ? j[k] : j[k] - n_smem_words * 16u;   // fold the tail
-                m = (s_mode[jj >> 4] >> ((jj & 15u) * 2u)) & 3u;
+        for (int u = 0; u < U; ++u) vv[u] = (i0 + u * stride < n_vec) ? ldg_stream(idx + i0 + u * stride) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t j[4] = {vv[u].x, vv[u].y, vv[u].z, vv[u].w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                uint32_t m;
+                if (V == 0) m = j[k] & 3u;
+                if (V == 1) m = __ldg(mode8 + j[k]);
+                if (V == 2) m = (__ldg(mode2 + (j[k] >> 4)) >> ((j[k] & 15u) * 2u)) & 3u;
+                if (V == 3) {
+                    const uint32_t jj = j[k] < n_smem_words * 16u ? j[k] : j[k] - n_smem_words * 16u;   // fold the tail
+                    m = (s_mode[jj >> 4] >> ((jj & 15u) * 2u)) & 3u;
+                }
+                if (V == 4) {
+                    const uint32_t wd = j[k] >> 4;
+                    const uint32_t owner = wd >= half_words;
+                    const uint32_t* base = owner == my_rank ? s_mode : remote;
+                    m = (base[wd - owner * half_words] >> ((j[k] & 15u) * 2u)) & 3u;
+                }
+                if (V == 5) {      // hybrid: hot part in shared memory, cold tail from global (L2)
+                    const uint32_t wd = j[k] >> 4;
+                    const uint32_t w = wd < n_smem_words ? s_mode[wd] : __ldg(mode2 + wd);
+                    m = (w >> ((j[k] & 15u) * 2u)) & 3u;
+                }
+                acc += 1u << (8u * m);
             }
-            if (V == 4) {
-                const uint32_t wd = j[k] >> 4;
-                const uint32_t owner = wd >= half_words;
-                const uint32_t* base = owner == my_rank ? s_mode : remote;
-                m = (base[wd - owner * half_words] >> ((j[k] & 15u) * 2u)) & 3u;
-            }
-            acc += 1u << (8u * m);
         }
     }
     if (V == 4) cg::this_cluster().sync();
@@ -72,10 +82,10 @@ gather_kernel(const uint4* __restrict__ idx, size_t n_vec, const uint8_t* __rest
     atomicAdd(out + 1, (unsigned long long)(acc & 0xFF));
 }
 
-template <int V>
+template <int V, int U>
 float run(const char* name, int grid, size_t smem, const uint4* idx, size_t n_vec, const uint8_t* m8, const uint32_t* m2,
           uint32_t n_agents, uint32_t words, unsigned long long* out, int cluster) {
-    CK(cudaFuncSetAttribute(gather_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(gather_kernel<V, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     float best = 1e30f;
@@ -87,9 +97,9 @@ float run(const char* name, int grid, size_t smem, const uint4* idx, size_t n_ve
             cudaLaunchAttribute at[1];
             at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
             cfg.attrs = at; cfg.numAttrs = 1;
-            CK(cudaLaunchKernelEx(&cfg, gather_kernel<V>, idx, n_vec, m8, m2, n_agents, words, out));
+            CK(cudaLaunchKernelEx(&cfg, gather_kernel<V, U>, idx, n_vec, m8, m2, n_agents, words, out));
         } else {
-            gather_kernel<V><<<grid, 1024, smem>>>(idx, n_vec, m8, m2, n_agents, words, out);
+            gather_kernel<V, U><<<grid, 1024, smem>>>(idx, n_vec, m8, m2, n_agents, words, out);
         }
         CK(cudaEventRecord(e1));
         CK(cudaEventSynchronize(e1));
@@ -116,15 +126,16 @@ int main() {
     int dev_sms = 0; CK(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, 0));
     printf("SMs %d, links %zu (%.0f MB)\n", dev_sms, E, E * 4 / 1e6);
     const uint4* idx = (const uint4*)d_idx;
-    run<0>("V0 stream only", dev_sms, 0, idx, n_vec, d_m8, d_m2, N, 0, d_out, 1);
-    run<1>("V1 global u8", dev_sms, 0, idx, n_vec, d_m8, d_m2, N, 0, d_out, 1);
-    run<2>("V2 global 2-bit", dev_sms, 0, idx, n_vec, d_m8, d_m2, N, 0, d_out, 1);
-    const uint32_t words3 = 57000;                        // 228000 B: 912k agents resident, tail folded
-    run<3>("V3 smem 2-bit", dev_sms, words3 * 4, idx, n_vec, d_m8, d_m2, N, words3, d_out, 1);
+    const uint32_t words3 = 57000;                        // 228000 B: 912k agents resident
     const uint32_t words4 = N / 16 / 2;                   // 31250 words = 125 KB per CTA
-    run<4>("V4 cluster2 DSMEM", dev_sms, words4 * 4, idx, n_vec, d_m8, d_m2, N, words4, d_out, 2);
-    // more resident warps for the global variants (2 CTAs/SM is impossible at 1024 threads; try 2x grid anyway)
-    run<1>("V1 global u8 grid x2", dev_sms * 2, 0, idx, n_vec, d_m8, d_m2, N, 0, d_out, 1);
-    run<2>("V2 global 2-bit x2", dev_sms * 2, 0, idx, n_vec, d_m8, d_m2, N, 0, d_out, 1);
+#define ROW(U) \
+    printf("--- %d uint4 loads in flight per thread\n", U); \
+    run<0, U>("V0 stream only", dev_sms, 0, idx, n_vec, d_m8, d_m2, N, 0, d_out, 1); \
+    run<1, U>("V1 global u8", dev_sms, 0, idx, n_vec, d_m8, d_m2, N, 0, d_out, 1); \
+    run<2, U>("V2 global 2-bit", dev_sms, 0, idx, n_vec, d_m8, d_m2, N, 0, d_out, 1); \
+    run<3, U>("V3 smem 2-bit (fold)", dev_sms, words3 * 4, idx, n_vec, d_m8, d_m2, N, words3, d_out, 1); \
+    run<5, U>("V5 hot smem+cold L2", dev_sms, words3 * 4, idx, n_vec, d_m8, d_m2, N, words3, d_out, 1);
+    ROW(1) ROW(2) ROW(4) ROW(8)
+    run<4, 4>("V4 cluster2 DSMEM", dev_sms, words4 * 4, idx, n_vec, d_m8, d_m2, N, words4, d_out, 2);
     return 0;
 }
