@@ -6,12 +6,14 @@
 //   1. stages the hot part of yesterday's 2-bit mode vector of replica r in shared memory with
 //      TMA bulk copies (cp.async.bulk + mbarrier) and builds the per-replica tables
 //      (congestion from yesterday's histogram, pre-weather cost, desirability);
-//   2. hub slices p, p+P, ... : one WARP per hub agent streams that agent's link codes
-//      (uint4 per lane, coalesced), gathers the targets' modes from shared memory, and leaves 8
-//      counts per hub in shared memory; warp 0 then finishes the 32 hubs lane-per-agent;
+//   2. hub slices p, p+P, ... : one WARP per hub agent; the hub's link list is cut into 32
+//      contiguous chunks, one per lane, and goes through the same routine as a SELL slice
+//      (accumulate_block); the warp then adds its lanes up and leaves 8 counts per hub in shared
+//      memory; warp 0 finishes the 32 hubs lane-per-agent;
 //   3. SELL slices (taken from a block-wide counter, longest first): one LANE per agent, link
-//      codes read k-major (uint4 body + u32 tail, next row prefetched while the current one is
-//      gathered), modes collected 2 bits at a time and counted with popc;
+//      codes read k-major (uint4 body + u32 tail, two rows prefetched ahead of the one being
+//      gathered), each target's 2 bits pulled to the top of its word and pushed into a 32-bit
+//      collector by two funnel shifts, 16 links at a time counted with popc;
 //   4. per agent (agent.rs:244-316): habit EMA, shares, norm, budget/cost ranks, choice; the
 //      warp packs its 32 new modes into one u64 of tomorrow's vector; statistics are reduced
 //      with warp REDUX and a handful of shared-memory atomics, flushed once per part.
@@ -48,9 +50,9 @@ struct RepDev {                     // device-side descriptor of one replica
     const float* pa;                // per-agent weights [5][N_pad] or nullptr (uniform)
     uint2* vec[2];                  // [N_pad/32] packed current_mode per slice, double buffered by day parity
     uint2* normvec;                 // [N_pad/32] packed norm per slice
-    const uint32_t* deg;            // [N_pad] SELL agents: ds | dn << 16
+    const uint32_t* deg;            // [N_pad] SELL agents: ds_hot | dn_hot<<8 | ds_cold<<16 | dn_cold<<24
     const StageRange* ranges;
-    const uint64_t* hub_rowptr; const uint32_t* hub_ds; const uint32_t* hub_dn; const uint32_t* hub_codes;
+    const uint64_t* hub_off; const uint4* hub_deg; const uint32_t* hub_codes;   // per hub: block offset, (ds_hot, dn_hot, ds_cold, dn_cold)
     const uint64_t* sell_off; const uint32_t* sell_K; const uint32_t* sell_order; const uint32_t* sell_codes;
     const float* supp; const float* desir;       // [H][4], [S][4]
     const uint32_t* cap; const uint32_t* nres;   // [H][4], [H]
@@ -99,31 +101,92 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 }
 
 // ---- gathering yesterday's modes ---------------------------------------------------------------
-// Link code (layout.h): bits 31-27 = 2*position in the word, bits 26-2 = word index, bit 1 = cold.
-__device__ __forceinline__ uint32_t gather_hot(const uint32_t* s_vec, uint32_t code) {
-    const uint32_t w = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(s_vec) + (code & kCodeAddrMask));
-    return (w >> (code >> 27)) & 3u;
+// Link code (layout.h): code >> 5 = byte offset of the target's word, low 5 bits = left shift that brings the
+// target's 2 bits to bits 31:30.  __funnelshift_l wraps the shift amount, so the code is used as it is.
+__device__ __forceinline__ uint32_t top2_hot(const uint32_t* s_vec, uint32_t code) {
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(s_vec) + (code >> 5));
+    return __funnelshift_l(0u, w, code);                       // w << (code & 31)
 }
-__device__ __forceinline__ uint32_t gather_any(const uint32_t* s_vec, const uint32_t* g_vec, uint32_t code) {
-    uint32_t w;
-    if (code & 2u) w = __ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(g_vec) + (code & kCodeAddrMask)));
-    else w = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(s_vec) + (code & kCodeAddrMask));
-    return (w >> (code >> 27)) & 3u;
+__device__ __forceinline__ uint32_t top2_cold(const uint32_t* g_vec, uint32_t code) {
+    const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(g_vec) + (code >> 5)));
+    return __funnelshift_l(0u, w, code);
+}
+__device__ __forceinline__ uint32_t push2(uint32_t bits, uint32_t top) {      // (bits << 2) | (top >> 30)
+    return __funnelshift_l(top, bits, 2u);
+}
+__device__ __forceinline__ uint32_t push_row(const uint32_t* s_vec, uint32_t bits, const uint4& c) {
+    bits = push2(bits, top2_hot(s_vec, c.x));
+    bits = push2(bits, top2_hot(s_vec, c.y));
+    bits = push2(bits, top2_hot(s_vec, c.z));
+    return push2(bits, top2_hot(s_vec, c.w));
+}
+__device__ __forceinline__ uint32_t top_fields(int n) {      // mask of the low bit of the n highest 2-bit fields
+    return ~__funnelshift_rc(0xFFFFFFFFu, 0u, 2u * (uint32_t)n) & 0x55555555u;
 }
 
-// `bits` holds up to 16 gathered modes, field f (bits 2f+1..2f) = link number base+f of a list whose first `ds`
-// links are social and the following are neighbour links, `d` in total (fields at or past d are padding).  Adds the per-mode counts to the packed
-// 8-bit accumulators (social, neighbour).  count_in_subgroup's grouping, agent.rs:325-329.
-template <int NF>   // NF = fields of `bits` that were filled (16 for a SELL group, 4 for one uint4 of a hub row)
+// `bits` holds 16 gathered modes, link number base+e in field 15-e (the first link pushed ends up highest), of a
+// list whose first `ds` links are social and the following neighbour links, `d` in total (fields at or past d are
+// padding).  Adds the per-mode counts to the packed 8-bit accumulators.  count_in_subgroup's grouping, agent.rs:325-329.
 __device__ __forceinline__ void count_fields(uint32_t bits, int base, int ds, int d, uint32_t& acc_s, uint32_t& acc_n) {
-    const int nv = min(max(d - base, 0), NF), ns = min(max(ds - base, 0), NF);
-    const uint32_t vmask = (nv >= 16 ? 0xFFFFFFFFu : ((1u << (2 * nv)) - 1u)) & 0x55555555u;
-    const uint32_t smask = (ns >= 16 ? 0xFFFFFFFFu : ((1u << (2 * ns)) - 1u)) & 0x55555555u;
+    const uint32_t vmask = top_fields(min(max(d - base, 0), 16)), smask = top_fields(min(max(ds - base, 0), 16));
     const uint32_t nmask = vmask & ~smask;
     const uint32_t lo = bits & 0x55555555u, hi = (bits >> 1) & 0x55555555u;
     const uint32_t m3 = hi & lo, m2 = hi & ~lo, m1 = ~hi & lo, m0 = ~(hi | lo);
     acc_s += __popc(m0 & smask) | __popc(m1 & smask) << 8 | __popc(m2 & smask) << 16 | __popc(m3 & smask) << 24;
     acc_n += __popc(m0 & nmask) | __popc(m1 & nmask) << 8 | __popc(m2 & nmask) << 16 | __popc(m3 & nmask) << 24;
+}
+
+// One lane's part of a block of link codes laid out k-major for the warp (layout.h): K hot codes per lane
+// (floor(K/4) uint4 rows, then K%4 u32 rows) followed by Kc cold codes per lane.  The lane's hot list has d_h
+// links of which the first ds_h are social; likewise d_c / ds_c for the cold list.  Per-mode counts are added to
+// acc_s / acc_n (8 bits per mode: the caller keeps every list below 256 links).
+__device__ __forceinline__ void accumulate_block(const uint32_t* __restrict__ blk, uint32_t K, uint32_t Kc, uint32_t lane,
+                                                 int ds_h, int d_h, int ds_c, int d_c, const uint32_t* s_vec,
+                                                 const uint32_t* __restrict__ g_vec, uint32_t& acc_s, uint32_t& acc_n) {
+    const uint32_t K4 = K >> 2, Kt = K & 3u;
+    const uint4* body = reinterpret_cast<const uint4*>(blk) + lane;
+    const uint32_t* tail = blk + (size_t)K4 * 128 + lane;
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+    uint4 r0 = zero, r1 = zero, r2 = zero, r3 = zero;
+    uint32_t t0 = 0, t1 = 0, t2 = 0;
+    if (K4 > 0) r0 = ld_stream_v4(body);
+    if (K4 > 1) r1 = ld_stream_v4(body + 32);
+    if (Kt > 0) t0 = ld_stream_u32(tail);                       // the short tail goes out with the first rows
+    if (Kt > 1) t1 = ld_stream_u32(tail + 32);
+    if (Kt > 2) t2 = ld_stream_u32(tail + 64);
+    uint32_t q = 0, bits = 0;
+    for (; q + 4 <= K4; q += 4) {                               // 16 links per lane, two rows kept in flight
+        r2 = ld_stream_v4(body + (size_t)(q + 2) * 32);
+        bits = push_row(s_vec, bits, r0);
+        r3 = ld_stream_v4(body + (size_t)(q + 3) * 32);
+        bits = push_row(s_vec, bits, r1);
+        if (q + 4 < K4) r0 = ld_stream_v4(body + (size_t)(q + 4) * 32);
+        bits = push_row(s_vec, bits, r2);
+        if (q + 5 < K4) r1 = ld_stream_v4(body + (size_t)(q + 5) * 32);
+        bits = push_row(s_vec, bits, r3);
+        count_fields(bits, (int)(q * 4), ds_h, d_h, acc_s, acc_n);
+        bits = 0;
+    }
+    const uint32_t rem = K4 - q;                                // 0..3 rows left, then the tail
+    if (rem + Kt) {
+        if (rem > 2) r2 = ld_stream_v4(body + (size_t)(q + 2) * 32);
+        if (rem > 0) bits = push_row(s_vec, bits, r0);
+        if (rem > 1) bits = push_row(s_vec, bits, r1);
+        if (rem > 2) bits = push_row(s_vec, bits, r2);
+        if (Kt > 0) bits = push2(bits, top2_hot(s_vec, t0));
+        if (Kt > 1) bits = push2(bits, top2_hot(s_vec, t1));
+        if (Kt > 2) bits = push2(bits, top2_hot(s_vec, t2));
+        bits <<= 2u * (16u - (rem * 4u + Kt));                  // first link of the group back to field 15
+        count_fields(bits, (int)(q * 4), ds_h, d_h, acc_s, acc_n);
+    }
+    const uint32_t* cold = blk + (size_t)K * 32 + lane;        // cold list: targets outside shared memory, from L2
+    for (uint32_t k = 0; k < Kc; ++k) {
+        const uint32_t code = ld_stream_u32(cold + (size_t)k * 32);
+        if ((int)k < d_c) {
+            const uint32_t inc = 1u << ((top2_cold(g_vec, code) >> 30) * 8u);
+            if ((int)k < ds_c) acc_s += inc; else acc_n += inc;
+        }
+    }
 }
 
 // ---- per-warp statistics -------------------------------------------------------------------------
@@ -263,37 +326,32 @@ day_kernel(const RepDev* __restrict__ reps, uint32_t R, uint32_t P, uint32_t par
 
         WarpStats st{0, 0, 0, 0, 0, 0, 0};
 
-        // 2. hub slices: one warp per hub agent
+        // 2. hub slices: one warp per hub agent, the hub's lists cut into 32 chunks (one per lane)
         uint32_t hbuf = 0;
         for (uint32_t hs = p; hs < r.n_hub_slices; hs += P, hbuf ^= 1u) {
             const uint32_t hub = hs * 32 + warp;
-            const uint64_t b = r.hub_rowptr[hub], e = r.hub_rowptr[hub + 1];
-            const int ds = (int)r.hub_ds[hub], d = ds + (int)r.hub_dn[hub];
+            const uint4 hd = r.hub_deg[hub];                    // ds_hot, dn_hot, ds_cold, dn_cold
+            const uint32_t n_hot = hd.x + hd.y, n_cold = hd.z + hd.w;
             uint32_t cs[4] = {0, 0, 0, 0}, cn[4] = {0, 0, 0, 0};
-            uint32_t acc_s = 0, acc_n = 0, rows = 0;
-            const uint4* codes = reinterpret_cast<const uint4*>(r.hub_codes + b);
-            const uint32_t n4 = (uint32_t)((e - b) >> 2);
-            for (uint32_t q0 = 0; q0 < n4; q0 += 64) {                     // two rows of 32 uint4 per iteration
-                const uint32_t qa = q0 + lane, qb = q0 + 32 + lane;
-                uint4 va = make_uint4(0, 0, 0, 0), vb = va;
-                if (qa < n4) va = ld_stream_v4(codes + qa);
-                if (qb < n4) vb = ld_stream_v4(codes + qb);
-                uint32_t bits = gather_any(s_vec, g_vec, va.x) | gather_any(s_vec, g_vec, va.y) << 2 |
-                                gather_any(s_vec, g_vec, va.z) << 4 | gather_any(s_vec, g_vec, va.w) << 6;
-                count_fields<4>(bits, (int)(qa * 4), ds, d, acc_s, acc_n);
-                bits = gather_any(s_vec, g_vec, vb.x) | gather_any(s_vec, g_vec, vb.y) << 2 |
-                       gather_any(s_vec, g_vec, vb.z) << 4 | gather_any(s_vec, g_vec, vb.w) << 6;
-                count_fields<4>(bits, (int)(qb * 4), ds, d, acc_s, acc_n);
-                if (++rows == 30) {                                        // 8 links per iteration: < 256 per field
+            const uint32_t* blk = r.hub_codes + r.hub_off[hub];
+            // blocks of at most 252 links per lane keep the 8-bit accumulators exact (hub_segment, layout.h)
+            for (uint32_t done_h = 0, done_c = 0; done_h < n_hot || done_c < n_cold;) {
+                uint32_t K, Kc;
+                hub_segment(n_hot - min(done_h, n_hot), n_cold - min(done_c, n_cold), K, Kc);
+                const int oh = (int)(done_h + lane * K), oc = (int)(done_c + lane * Kc);
+                uint32_t acc_s = 0, acc_n = 0;
+                accumulate_block(blk, K, Kc, lane, min(max((int)hd.x - oh, 0), (int)K), min(max((int)n_hot - oh, 0), (int)K),
+                                 min(max((int)hd.z - oc, 0), (int)Kc), min(max((int)n_cold - oc, 0), (int)Kc),
+                                 s_vec, g_vec, acc_s, acc_n);
 #pragma unroll
-                    for (int m = 0; m < 4; ++m) { cs[m] += (acc_s >> (8 * m)) & 0xFFu; cn[m] += (acc_n >> (8 * m)) & 0xFFu; }
-                    acc_s = acc_n = 0; rows = 0;
-                }
+                for (int m = 0; m < 4; ++m) { cs[m] += (acc_s >> (8 * m)) & 0xFFu; cn[m] += (acc_n >> (8 * m)) & 0xFFu; }
+                blk += (size_t)32 * (K + Kc);
+                done_h += 32u * K; done_c += 32u * Kc;
             }
 #pragma unroll
             for (int m = 0; m < 4; ++m) {
-                cs[m] = __reduce_add_sync(0xFFFFFFFFu, cs[m] + ((acc_s >> (8 * m)) & 0xFFu));
-                cn[m] = __reduce_add_sync(0xFFFFFFFFu, cn[m] + ((acc_n >> (8 * m)) & 0xFFu));
+                cs[m] = __reduce_add_sync(0xFFFFFFFFu, cs[m]);
+                cn[m] = __reduce_add_sync(0xFFFFFFFFu, cn[m]);
             }
             if (lane < 8) {
                 const uint32_t v = lane == 0 ? cs[0] : lane == 1 ? cs[1] : lane == 2 ? cs[2] : lane == 3 ? cs[3]
@@ -307,9 +365,10 @@ day_kernel(const RepDev* __restrict__ reps, uint32_t R, uint32_t P, uint32_t par
 #pragma unroll
                 for (int m = 0; m < 4; ++m) { hcs[m] = s_hub[hbuf * 256 + lane * 8 + m]; hcn[m] = s_hub[hbuf * 256 + lane * 8 + 4 + m]; }
                 const uint32_t stat = r.stat[agent];
+                const uint4 ad = r.hub_deg[agent];
                 const uint2 own = r.vec[parity][hs];
                 const uint32_t last = ((lane < 16 ? own.x : own.y) >> ((lane & 15u) * 2u)) & 3u;
-                finish_slice<PER_AGENT>(r, hs, lane, false, hcs, r.hub_ds[agent], hcn, r.hub_dn[agent], stat, r.ws[agent],
+                finish_slice<PER_AGENT>(r, hs, lane, false, hcs, ad.x + ad.z, hcn, ad.y + ad.w, stat, r.ws[agent],
                                         r.habit[agent], last, uw, s_cong, s_cost, s_des, s_rec, weather, changed, parity, st);
             }
         }
@@ -323,46 +382,23 @@ day_kernel(const RepDev* __restrict__ reps, uint32_t R, uint32_t P, uint32_t par
             if (idx >= r.n_sell_slices) break;
             const uint32_t s = r.sell_order[idx];
             const uint32_t slice = r.n_hub_slices + s, agent = slice * 32 + lane;
-            const uint32_t K = r.sell_K[s], K4 = K >> 2;
-            const uint4* body = reinterpret_cast<const uint4*>(r.sell_codes + r.sell_off[s]) + lane;
-            // the first rows of link codes and the agent's own state go out together
-            uint4 cur = make_uint4(0, 0, 0, 0), nxt = cur;
-            if (K4 > 0) cur = ld_stream_v4(body);
-            if (K4 > 1) nxt = ld_stream_v4(body + 32);
+            const uint32_t KK = r.sell_K[s];
+            const uint32_t* blk = r.sell_codes + r.sell_off[s];
+            // the agent's own state goes out with the first rows of link codes
             const uint32_t stat = r.stat[agent];
             const uint32_t dg = r.deg[agent];
             const float wsv = r.ws[agent];
             const float4 hv = r.habit[agent];
             const uint2 own = r.vec[parity][slice];
-            const int ds = (int)(dg & 0xFFFFu), d = ds + (int)(dg >> 16);
-            uint32_t acc_s = 0, acc_n = 0, bits = 0;
-            for (uint32_t q4 = 0; q4 < K4; ++q4) {
-                uint4 pre = make_uint4(0, 0, 0, 0);
-                if (q4 + 2 < K4) pre = ld_stream_v4(body + (size_t)(q4 + 2) * 32);       // keep two rows in flight
-                const uint32_t f = (q4 & 3u) * 8u;
-                if (__builtin_expect(((cur.x | cur.y | cur.z | cur.w) & 2u) == 0u, 1)) {
-                    bits |= (gather_hot(s_vec, cur.x) | gather_hot(s_vec, cur.y) << 2 | gather_hot(s_vec, cur.z) << 4 |
-                             gather_hot(s_vec, cur.w) << 6) << f;
-                } else {
-                    bits |= (gather_any(s_vec, g_vec, cur.x) | gather_any(s_vec, g_vec, cur.y) << 2 |
-                             gather_any(s_vec, g_vec, cur.z) << 4 | gather_any(s_vec, g_vec, cur.w) << 6) << f;
-                }
-                if ((q4 & 3u) == 3u) { count_fields<16>(bits, (int)(q4 >> 2) * 16, ds, d, acc_s, acc_n); bits = 0; }
-                cur = nxt; nxt = pre;
-            }
-            {   // tail: K % 4 single codes per lane, after the last complete group of the body
-                const uint32_t* tail = r.sell_codes + r.sell_off[s] + (size_t)K4 * 128 + lane;
-                const uint32_t Kt = K & 3u;
-                uint32_t f = (K4 & 3u) * 8u;
-                for (uint32_t t = 0; t < Kt; ++t, f += 2u) bits |= gather_any(s_vec, g_vec, ld_stream_u32(tail + t * 32)) << f;
-                if ((K4 & 3u) != 0u || Kt != 0u) count_fields<16>(bits, (int)(K4 >> 2) * 16, ds, d, acc_s, acc_n);
-            }
+            const int ds_h = (int)(dg & 0xFFu), dn_h = (int)((dg >> 8) & 0xFFu), ds_c = (int)((dg >> 16) & 0xFFu), dn_c = (int)(dg >> 24);
+            uint32_t acc_s = 0, acc_n = 0;
+            accumulate_block(blk, KK & 0xFFFFu, KK >> 16, lane, ds_h, ds_h + dn_h, ds_c, ds_c + dn_c, s_vec, g_vec, acc_s, acc_n);
             uint32_t cs[4], cn[4];
 #pragma unroll
             for (int m = 0; m < 4; ++m) { cs[m] = (acc_s >> (8 * m)) & 0xFFu; cn[m] = (acc_n >> (8 * m)) & 0xFFu; }
             const uint32_t last = ((lane < 16 ? own.x : own.y) >> ((lane & 15u) * 2u)) & 3u;
-            finish_slice<PER_AGENT>(r, slice, lane, true, cs, (uint32_t)ds, cn, (uint32_t)(d - ds), stat, wsv, hv, last, uw,
-                                    s_cong, s_cost, s_des, s_rec, weather, changed, parity, st);
+            finish_slice<PER_AGENT>(r, slice, lane, true, cs, (uint32_t)(ds_h + ds_c), cn, (uint32_t)(dn_h + dn_c), stat, wsv, hv,
+                                    last, uw, s_cong, s_cost, s_des, s_rec, weather, changed, parity, st);
             if (st.slices >= 1024) flush_warp_stats(r, lane, s_rec, st);
         }
         flush_warp_stats(r, lane, s_rec, st);

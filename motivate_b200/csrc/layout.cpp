@@ -39,17 +39,74 @@ int build_graph_layout(const mvb_population& pop, uint32_t H, uint32_t capacity_
     std::sort(hubs.begin(), hubs.end(), by_degree);
     for (auto& g : groups) std::sort(g.begin(), g.end(), by_degree);
 
-    // ---- internal order ----------------------------------------------------------------------
+    // ---- hot set: all hubs + the highest-degree agents of every group, as many as fit ---------
     const uint32_t hub_pad = round_up((uint32_t)hubs.size(), 64);
+    std::vector<uint32_t> take(H, 0);                    // hot agents of group h (a prefix in degree order)
+    std::vector<uint32_t> gpad(H);
     uint64_t total = hub_pad;
-    std::vector<uint32_t> gstart(H), gpad(H);
-    for (uint32_t h = 0; h < H; ++h) {
-        gstart[h] = (uint32_t)total;
-        gpad[h] = round_up((uint32_t)groups[h].size(), 64);
-        total += gpad[h];
-    }
-    if (total >= (1ull << 29)) { set_error("too many agents for the 25-bit word index of a link code"); return MVB_ERR_ARG; }
+    for (uint32_t h = 0; h < H; ++h) { gpad[h] = round_up((uint32_t)groups[h].size(), 64); total += gpad[h]; }
+    if (total >= (1ull << 29)) { set_error("too many agents for the word index of a link code"); return MVB_ERR_ARG; }
     L.N_pad = (uint32_t)total;
+    const bool all_hot = L.N_pad <= capacity_agents;
+    if (all_hot) {
+        for (uint32_t h = 0; h < H; ++h) take[h] = (uint32_t)groups[h].size();
+    } else {
+        // largest degree threshold theta such that {hubs} U {d >= theta} (rounded to 64 per group) fits
+        const uint32_t budget = capacity_agents > hub_pad ? capacity_agents - hub_pad : 0;
+        auto count_for = [&](uint64_t theta, std::vector<uint32_t>& out) {
+            uint64_t sum = 0;
+            for (uint32_t h = 0; h < H; ++h) {
+                const auto& g = groups[h];
+                const uint32_t c = (uint32_t)(std::partition_point(g.begin(), g.end(), [&](uint32_t a) { return d[a] >= theta; }) - g.begin());
+                out[h] = std::min(round_up(c, 64), (uint32_t)g.size() / 64 * 64);
+                sum += out[h];
+            }
+            return sum;
+        };
+        std::vector<uint32_t> tmp(H);
+        uint64_t lo = 0, hi = kHubDegree + 1;            // theta in (lo, hi]; hi always fits (nothing taken)
+        while (hi - lo > 1) {
+            const uint64_t mid = (lo + hi) / 2;
+            if (count_for(mid, tmp) <= budget) hi = mid; else lo = mid;
+        }
+        uint64_t used = count_for(hi, take);
+        for (uint32_t h = 0; h < H && used + 64 <= budget; ++h) {   // spend the rest on the next degree class
+            const uint32_t room = (uint32_t)groups[h].size() / 64 * 64 - take[h];
+            const uint32_t extra = (uint32_t)std::min<uint64_t>(room, (budget - used) / 64 * 64);
+            take[h] += extra; used += extra;
+        }
+    }
+    std::vector<uint8_t> is_hot(N, 0);
+    if (all_hot || hub_pad <= capacity_agents) for (uint32_t e : hubs) is_hot[e] = 1;
+    else for (uint32_t k = 0; k < std::min<size_t>(hubs.size(), capacity_agents); ++k) is_hot[hubs[k]] = 1;
+    for (uint32_t h = 0; h < H; ++h)
+        for (uint32_t k = 0; k < take[h]; ++k) is_hot[groups[h][k]] = 1;
+
+    // hot / cold link counts per agent; order each group's hot part and cold part by (hot, cold) length
+    std::vector<uint32_t> nsh(N, 0), nnh(N, 0);          // social / neighbour links whose target is hot
+    for (uint32_t i = 0; i < N; ++i) {
+        uint32_t a = 0, b = 0;
+        for (uint64_t x = srp[i]; x < srp[i + 1]; ++x) a += is_hot[pop.social_col[x]];
+        for (uint64_t x = nrp[i]; x < nrp[i + 1]; ++x) b += is_hot[pop.neighbour_col[x]];
+        nsh[i] = a; nnh[i] = b;
+    }
+    auto by_lists = [&](uint32_t a, uint32_t b) {
+        const uint64_t ha = nsh[a] + nnh[a], hb = nsh[b] + nnh[b];
+        if (ha != hb) return ha > hb;
+        if (d[a] != d[b]) return d[a] > d[b];
+        return a < b;
+    };
+    for (uint32_t h = 0; h < H; ++h) {
+        std::sort(groups[h].begin(), groups[h].begin() + take[h], by_lists);
+        std::sort(groups[h].begin() + take[h], groups[h].end(), by_lists);
+    }
+
+    // ---- internal order ----------------------------------------------------------------------
+    std::vector<uint32_t> gstart(H);
+    {
+        uint64_t at = hub_pad;
+        for (uint32_t h = 0; h < H; ++h) { gstart[h] = (uint32_t)at; at += gpad[h]; }
+    }
     L.n_hub_slices = hub_pad / 32;
     L.n_sell_slices = (L.N_pad - hub_pad) / 32;
     L.int2ext.assign(L.N_pad, kInvalid);
@@ -60,8 +117,7 @@ int build_graph_layout(const mvb_population& pop, uint32_t H, uint32_t capacity_
     for (uint32_t s = 0; s < L.N_pad; ++s)
         if (L.int2ext[s] != kInvalid) L.ext2int[L.int2ext[s]] = s;
 
-    // ---- hot set: hub region + a degree-descending prefix of every group ---------------------
-    // position of an internal slot in the staged vector, or kInvalid if cold
+    // ---- staged ranges: position of an internal slot in the shared-memory vector, or kInvalid if cold
     std::vector<uint32_t> hot_pos(L.N_pad, kInvalid);
     uint32_t staged = 0;
     auto add_range = [&](uint32_t start, uint32_t count) {       // both multiples of 64
@@ -70,69 +126,77 @@ int build_graph_layout(const mvb_population& pop, uint32_t H, uint32_t capacity_
         for (uint32_t k = 0; k < count; ++k) hot_pos[start + k] = staged + k;
         staged += count;
     };
-    if (L.N_pad <= capacity_agents) {
+    if (all_hot) {
         add_range(0, L.N_pad);
     } else {
-        // largest degree threshold theta such that {hubs} ∪ {d >= theta} (rounded per group) fits
-        uint32_t budget = capacity_agents > hub_pad ? capacity_agents - hub_pad : 0;
-        uint32_t hub_take = std::min(hub_pad, capacity_agents);
-        std::vector<uint32_t> take(H, 0);
-        uint64_t lo = 0, hi = kHubDegree + 1;                    // theta in (lo, hi]: hi always fits
-        auto count_for = [&](uint64_t theta, std::vector<uint32_t>& out) {
-            uint64_t sum = 0;
-            for (uint32_t h = 0; h < H; ++h) {
-                const auto& g = groups[h];
-                // g sorted by degree descending: first index with d < theta
-                uint32_t c = (uint32_t)(std::partition_point(g.begin(), g.end(), [&](uint32_t a) { return d[a] >= theta; }) - g.begin());
-                out[h] = std::min(round_up(c, 64), gpad[h]);
-                sum += out[h];
-            }
-            return sum;
-        };
-        std::vector<uint32_t> tmp(H);
-        while (hi - lo > 1) {
-            const uint64_t mid = (lo + hi) / 2;
-            if (count_for(mid, tmp) <= budget) hi = mid; else lo = mid;
-        }
-        uint64_t used = count_for(hi, take);
-        // spend what is left on the next-lower degree class, group by group
-        for (uint32_t h = 0; h < H && used < budget; ++h) {
-            const uint32_t extra = std::min<uint64_t>(gpad[h] - take[h], (budget - used) / 64 * 64);
-            take[h] += extra; used += extra;
-        }
-        add_range(0, hub_take);
-        for (uint32_t h = 0; h < H; ++h) add_range(gstart[h], take[h]);
+        add_range(0, std::min(hub_pad, capacity_agents));
+        for (uint32_t h = 0; h < H; ++h) add_range(gstart[h], take[h]);     // take[h] is a multiple of 64 here
     }
     L.hot_words = staged / 16;
 
     // ---- link codes ---------------------------------------------------------------------------
-    auto code_of = [&](uint32_t ext_target) -> uint32_t {
+    auto code_of = [&](uint32_t ext_target, bool& hot) -> uint32_t {
         const uint32_t t = L.ext2int[ext_target];
         const uint32_t hp = hot_pos[t];
-        const uint32_t pos = hp != kInvalid ? hp : t;
-        return ((pos & 15u) * 2u) << 27 | (pos >> 4) << 2 | (hp != kInvalid ? 0u : 2u);
+        hot = hp != kInvalid;
+        const uint32_t pos = hot ? hp : t;
+        return (pos >> 4) << 7 | (30u - 2u * (pos & 15u));
     };
-    // hub rows: [social codes | neighbour codes | pad to 4]
+    // one agent's four lists
+    std::vector<uint32_t> lh, lc;
+    uint32_t c_sh, c_nh, c_sc, c_nc;
+    auto build_lists = [&](uint32_t e) {
+        lh.clear(); lc.clear();
+        c_sh = c_nh = c_sc = c_nc = 0;
+        bool hot;
+        for (uint64_t x = srp[e]; x < srp[e + 1]; ++x) { const uint32_t c = code_of(pop.social_col[x], hot); if (hot) { lh.push_back(c); ++c_sh; } }
+        for (uint64_t x = nrp[e]; x < nrp[e + 1]; ++x) { const uint32_t c = code_of(pop.neighbour_col[x], hot); if (hot) { lh.push_back(c); ++c_nh; } }
+        for (uint64_t x = srp[e]; x < srp[e + 1]; ++x) { const uint32_t c = code_of(pop.social_col[x], hot); if (!hot) { lc.push_back(c); ++c_sc; } }
+        for (uint64_t x = nrp[e]; x < nrp[e + 1]; ++x) { const uint32_t c = code_of(pop.neighbour_col[x], hot); if (!hot) { lc.push_back(c); ++c_nc; } }
+    };
+    // write code number k of a lane's hot (or cold) chunk into a block of the k-major SELL format
+    auto put_hot = [](uint32_t* blk, uint32_t K, uint32_t lane, uint32_t k, uint32_t code) {
+        const uint32_t K4 = K / 4;
+        if (k < 4 * K4) blk[(size_t)(k / 4) * 128 + lane * 4 + (k & 3)] = code;
+        else blk[(size_t)K4 * 128 + (size_t)(k - 4 * K4) * 32 + lane] = code;
+    };
+    auto put_cold = [](uint32_t* blk, uint32_t K, uint32_t lane, uint32_t k, uint32_t code) {
+        blk[(size_t)K * 32 + (size_t)k * 32 + lane] = code;
+    };
+    // hub blocks: lane l of a block holds links [l*K, (l+1)*K) of what is left of the list
     const uint32_t n_hub_rows = L.n_hub_slices * 32;
-    L.hub_rowptr.assign((size_t)n_hub_rows + 1, 0);
-    L.hub_ds.assign(n_hub_rows, 0);
-    L.hub_dn.assign(n_hub_rows, 0);
+    L.hub_off.assign(n_hub_rows, 0);
+    L.hub_deg.assign((size_t)4 * n_hub_rows, 0);
+    uint64_t hoff = 0;
     for (uint32_t k = 0; k < n_hub_rows; ++k) {
-        uint64_t len = 0;
-        if (k < hubs.size()) {
-            const uint32_t e = hubs[k];
-            L.hub_ds[k] = (uint32_t)(srp[e + 1] - srp[e]);
-            L.hub_dn[k] = (uint32_t)(nrp[e + 1] - nrp[e]);
-            len = (d[e] + 3) / 4 * 4;
-        }
-        L.hub_rowptr[k + 1] = L.hub_rowptr[k] + len;
-    }
-    L.hub_codes.assign(L.hub_rowptr[n_hub_rows], 0);
-    for (uint32_t k = 0; k < hubs.size(); ++k) {
+        L.hub_off[k] = hoff;
+        if (k >= hubs.size()) continue;
         const uint32_t e = hubs[k];
-        uint32_t* o = L.hub_codes.data() + L.hub_rowptr[k];
-        for (uint64_t x = srp[e]; x < srp[e + 1]; ++x) *o++ = code_of(pop.social_col[x]);
-        for (uint64_t x = nrp[e]; x < nrp[e + 1]; ++x) *o++ = code_of(pop.neighbour_col[x]);
+        const uint32_t nh = nsh[e] + nnh[e], nc = (uint32_t)d[e] - nh;
+        for (uint32_t dh = 0, dc = 0; dh < nh || dc < nc;) {
+            uint32_t K, Kc;
+            hub_segment(nh - std::min(dh, nh), nc - std::min(dc, nc), K, Kc);
+            hoff += (uint64_t)32 * (K + Kc);
+            dh += 32 * K; dc += 32 * Kc;
+        }
+    }
+    L.hub_codes.assign(hoff + 256, 0);                   // + slack for the row prefetch
+    for (uint32_t k = 0; k < hubs.size(); ++k) {
+        build_lists(hubs[k]);
+        uint32_t* dg = &L.hub_deg[(size_t)4 * k];
+        dg[0] = c_sh; dg[1] = c_nh; dg[2] = c_sc; dg[3] = c_nc;
+        const uint32_t nh = (uint32_t)lh.size(), nc = (uint32_t)lc.size();
+        uint32_t* blk = L.hub_codes.data() + L.hub_off[k];
+        for (uint32_t dh = 0, dc = 0; dh < nh || dc < nc;) {
+            uint32_t K, Kc;
+            hub_segment(nh - std::min(dh, nh), nc - std::min(dc, nc), K, Kc);
+            for (uint32_t l = 0; l < 32; ++l) {
+                for (uint32_t j = 0; j < K && dh + l * K + j < nh; ++j) put_hot(blk, K, l, j, lh[dh + l * K + j]);
+                for (uint32_t j = 0; j < Kc && dc + l * Kc + j < nc; ++j) put_cold(blk, K, l, j, lc[dc + l * Kc + j]);
+            }
+            blk += (size_t)32 * (K + Kc);
+            dh += 32 * K; dc += 32 * Kc;
+        }
     }
     // SELL slices
     L.deg.assign(L.N_pad, 0);
@@ -141,39 +205,35 @@ int build_graph_layout(const mvb_population& pop, uint32_t H, uint32_t capacity_
     uint64_t off = 0;
     for (uint32_t s = 0; s < L.n_sell_slices; ++s) {
         const uint32_t base = hub_pad + s * 32;
-        uint32_t K = 0;
-        for (uint32_t l = 0; l < 32; ++l) {
-            const uint32_t e = L.int2ext[base + l];
-            if (e != kInvalid) K = std::max<uint32_t>(K, (uint32_t)d[e]);
-        }
-        L.sell_off[s] = off;
-        L.sell_K[s] = K;
-        off += (uint64_t)32 * K;
-    }
-    L.sell_codes.assign(off, 0);
-    std::vector<uint32_t> row;
-    for (uint32_t s = 0; s < L.n_sell_slices; ++s) {
-        const uint32_t base = hub_pad + s * 32, K = L.sell_K[s], K4 = K / 4;
-        uint32_t* body = L.sell_codes.data() + L.sell_off[s];
-        uint32_t* tail = body + (size_t)K4 * 128;
+        uint32_t K = 0, Kc = 0;
         for (uint32_t l = 0; l < 32; ++l) {
             const uint32_t e = L.int2ext[base + l];
             if (e == kInvalid) continue;
-            const uint32_t ds = (uint32_t)(srp[e + 1] - srp[e]), dn = (uint32_t)(nrp[e + 1] - nrp[e]);
-            L.deg[base + l] = ds | dn << 16;
-            row.clear();
-            for (uint64_t x = srp[e]; x < srp[e + 1]; ++x) row.push_back(code_of(pop.social_col[x]));
-            for (uint64_t x = nrp[e]; x < nrp[e + 1]; ++x) row.push_back(code_of(pop.neighbour_col[x]));
-            for (uint32_t k = 0; k < row.size(); ++k) {
-                if (k < 4 * K4) body[(size_t)(k / 4) * 128 + l * 4 + (k & 3)] = row[k];
-                else tail[(size_t)(k - 4 * K4) * 32 + l] = row[k];
-            }
+            const uint32_t nh = nsh[e] + nnh[e];
+            K = std::max(K, nh);
+            Kc = std::max<uint32_t>(Kc, (uint32_t)d[e] - nh);
+        }
+        L.sell_off[s] = off;
+        L.sell_K[s] = K | Kc << 16;
+        off += (uint64_t)32 * (K + Kc);
+    }
+    L.sell_codes.assign(off + 256, 0);                   // + slack: the kernel's row prefetch may run 2 rows past a slice
+    for (uint32_t s = 0; s < L.n_sell_slices; ++s) {
+        const uint32_t base = hub_pad + s * 32, K = L.sell_K[s] & 0xFFFFu;
+        uint32_t* blk = L.sell_codes.data() + L.sell_off[s];
+        for (uint32_t l = 0; l < 32; ++l) {
+            const uint32_t e = L.int2ext[base + l];
+            if (e == kInvalid) continue;
+            build_lists(e);
+            L.deg[base + l] = c_sh | c_nh << 8 | c_sc << 16 | c_nc << 24;
+            for (uint32_t k = 0; k < lh.size(); ++k) put_hot(blk, K, l, k, lh[k]);
+            for (uint32_t k = 0; k < lc.size(); ++k) put_cold(blk, K, l, k, lc[k]);
         }
     }
     L.sell_order.resize(L.n_sell_slices);
     std::iota(L.sell_order.begin(), L.sell_order.end(), 0u);
-    std::stable_sort(L.sell_order.begin(), L.sell_order.end(),
-                     [&](uint32_t a, uint32_t b) { return L.sell_K[a] > L.sell_K[b]; });
+    auto work = [&](uint32_t s) { return (L.sell_K[s] & 0xFFFFu) + 2u * (L.sell_K[s] >> 16); };
+    std::stable_sort(L.sell_order.begin(), L.sell_order.end(), [&](uint32_t a, uint32_t b) { return work(a) > work(b); });
     return MVB_OK;
 }
 

@@ -16,17 +16,22 @@
 //   group, as many agents as fit (everything if N <= capacity).  The rest is "cold"
 //   and gathered from L2.
 //
-// Link codes (u32 per link): bit 31 = neighbour link (else social link)
-//                            bit 30 = cold target: bits 0-29 = internal id (global vector)
-//                            else    bits 0-29 = position in the staged shared-memory vector
-//   kDummyCode = a social link to a reserved shared-memory slot that always reads mode 0;
-//   used as padding and subtracted from the Car count afterwards.
+// Link codes (u32 per link).  Every agent's links are split into a HOT list (targets staged in shared
+// memory) and a COLD list (targets read from the global vector); inside each list social links come
+// first, then neighbour links, so "which list" is a position test, not a flag:
+//     hot  code = (byte offset of the target's word in the staged vector) << 5 | (30 - 2*position in word)
+//     cold code = (byte offset of the target's word in the global vector) << 5 | (30 - 2*position in word)
+//   The low 5 bits are the left-shift that brings the target's 2 bits to bits 31:30 of the word
+//   (a wrapping funnel shift uses them directly); code >> 5 is the byte address.
 //
-// Hub slices  (32 hubs, one WARP per hub): CSR rows, each padded to a multiple of 4 codes.
-// SELL slices (32 agents, one LANE per agent): K = longest list of the slice; codes stored
-//   k-major so that a warp's loads are contiguous: a "body" of floor(K/4) uint4 per lane
-//   (lane's links 4q..4q+3) followed by a "tail" of K%4 u32 per lane; lists shorter than K
-//   are padded with kDummyCode (degree-sorted slices make this padding ~0).
+// Hub slices  (32 hubs, one WARP per hub): the hub's hot and cold lists are cut into 32 contiguous chunks, one
+//   per lane, and stored as blocks of the SELL format below (lane = chunk); a list too long for one block
+//   (more than 252 links per lane, the 8-bit counters' limit) continues in further blocks, see hub_segment().
+// SELL slices (32 agents, one LANE per agent): K = longest hot list, Kc = longest cold list of the slice;
+//   codes stored k-major so that a warp's loads are contiguous: a "body" of floor(K/4) uint4 per lane
+//   (lane's hot links 4q..4q+3), a "tail" of K%4 u32 per lane, then Kc u32 per lane of cold links.
+//   Lists shorter than K / Kc are padded with code 0.  Agents are ordered by (hot length, cold length)
+//   inside their region, so slices are uniform and the padding is ~0.
 #pragma once
 #include <cstdint>
 #include <vector>
@@ -36,10 +41,19 @@
 namespace mvb {
 
 constexpr uint32_t kHubDegree = 128;        // total links above which an agent is a hub (must be <= 255)
-constexpr uint32_t kCodeNbr = 0x80000000u;
-constexpr uint32_t kCodeCold = 0x40000000u;
-constexpr uint32_t kCodeMask = 0x3FFFFFFFu;
 constexpr uint32_t kInvalid = 0xFFFFFFFFu;
+
+// Lengths (per lane) of the next block of a hub whose lists still have rem_hot / rem_cold links to go.
+// Host (layout.cpp) and device (day_kernels.cuh) walk a hub's blocks with this same rule.
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline void hub_segment(uint32_t rem_hot, uint32_t rem_cold, uint32_t& K, uint32_t& Kc) {
+    K = (rem_hot + 31u) / 32u;
+    if (K > 252u) K = 252u;
+    Kc = (rem_cold + 31u) / 32u;
+    if (Kc > 252u - K) Kc = 252u - K;
+}
 
 struct StageRange {                // one contiguous piece of the mode vector staged in shared memory
     uint32_t src_word;             // first u32 word in the global packed vector (16 agents per word)
@@ -53,20 +67,19 @@ struct GraphLayout {
     uint32_t N_pad = 0;            // internal slots (multiple of 64)
     uint32_t n_hub_slices = 0;     // slices [0, n_hub_slices) are hub slices
     uint32_t n_sell_slices = 0;    // the rest
-    uint32_t hot_words = 0;        // staged vector size in u32 words, including the dummy word (last)
-    uint32_t dummy_code = 0;
+    uint32_t hot_words = 0;        // staged vector size in u32 words
     uint64_t Es = 0, En = 0;       // link counts of the source graph
     std::vector<uint32_t> int2ext; // [N_pad] internal slot -> caller's agent id, kInvalid for padding
     std::vector<uint32_t> ext2int; // [N]
-    std::vector<uint32_t> deg;     // [N_pad] SELL agents: ds | dn << 16 (hub entries unused)
+    std::vector<uint32_t> deg;     // [N_pad] SELL agents: ds_hot | dn_hot<<8 | ds_cold<<16 | dn_cold<<24
     std::vector<StageRange> ranges;
     // hubs
-    std::vector<uint64_t> hub_rowptr;      // [n_hub_slices*32 + 1] in u32 units, rows padded to 4
-    std::vector<uint32_t> hub_ds, hub_dn;  // [n_hub_slices*32]
+    std::vector<uint64_t> hub_off;         // [n_hub_slices*32] offset of the hub's first block in hub_codes (u32 units)
+    std::vector<uint32_t> hub_deg;         // [n_hub_slices*32][4] ds_hot, dn_hot, ds_cold, dn_cold
     std::vector<uint32_t> hub_codes;
     // SELL
     std::vector<uint64_t> sell_off;        // [n_sell_slices] offset of the slice in sell_codes (u32 units)
-    std::vector<uint32_t> sell_K;          // [n_sell_slices]
+    std::vector<uint32_t> sell_K;          // [n_sell_slices] K | Kc << 16
     std::vector<uint32_t> sell_order;      // [n_sell_slices] processing order, longest lists first
     std::vector<uint32_t> sell_codes;
 };

@@ -38,7 +38,7 @@ struct DevBuf {                       // owning device allocation
 // (scenario sweeps over one population pass the same graph + neighbourhood arrays).
 struct Graph {
     GraphLayout L;                 // host copy: permutation, sizes (code arrays are released after upload)
-    DevBuf deg, ranges, hub_rowptr, hub_ds, hub_dn, hub_codes, sell_off, sell_K, sell_order, sell_codes;
+    DevBuf deg, ranges, hub_off, hub_deg, hub_codes, sell_off, sell_K, sell_order, sell_codes;
     const void* key[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // caller pointers it was built from
 };
 
@@ -302,8 +302,8 @@ int mvb_create_batch(uint32_t R, const mvb_population* const* pops, const mvb_ta
             if (rc) return rc;
             GraphLayout& L = g->L;
             if ((rc = upload(g->deg, L.deg, s->stream)) || (rc = upload(g->ranges, L.ranges, s->stream)) ||
-                (rc = upload(g->hub_rowptr, L.hub_rowptr, s->stream)) || (rc = upload(g->hub_ds, L.hub_ds, s->stream)) ||
-                (rc = upload(g->hub_dn, L.hub_dn, s->stream)) || (rc = upload(g->hub_codes, L.hub_codes, s->stream)) ||
+                (rc = upload(g->hub_off, L.hub_off, s->stream)) || (rc = upload(g->hub_deg, L.hub_deg, s->stream)) ||
+                (rc = upload(g->hub_codes, L.hub_codes, s->stream)) ||
                 (rc = upload(g->sell_off, L.sell_off, s->stream)) || (rc = upload(g->sell_K, L.sell_K, s->stream)) ||
                 (rc = upload(g->sell_order, L.sell_order, s->stream)) || (rc = upload(g->sell_codes, L.sell_codes, s->stream)))
                 return rc;
@@ -374,7 +374,7 @@ int mvb_create_batch(uint32_t R, const mvb_population* const* pops, const mvb_ta
         d.pa = rp.per_agent ? rp.pa.as<float>() : nullptr;
         d.vec[0] = rp.vec[0].as<uint2>(); d.vec[1] = rp.vec[1].as<uint2>(); d.normvec = rp.normvec.as<uint2>();
         d.deg = g.deg.as<uint32_t>(); d.ranges = g.ranges.as<StageRange>();
-        d.hub_rowptr = g.hub_rowptr.as<uint64_t>(); d.hub_ds = g.hub_ds.as<uint32_t>(); d.hub_dn = g.hub_dn.as<uint32_t>();
+        d.hub_off = g.hub_off.as<uint64_t>(); d.hub_deg = g.hub_deg.as<uint4>();
         d.hub_codes = g.hub_codes.as<uint32_t>();
         d.sell_off = g.sell_off.as<uint64_t>(); d.sell_K = g.sell_K.as<uint32_t>(); d.sell_order = g.sell_order.as<uint32_t>();
         d.sell_codes = g.sell_codes.as<uint32_t>();

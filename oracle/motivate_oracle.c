@@ -227,18 +227,17 @@ static void choose(mvo_sim* s, uint32_t i, uint8_t weather, uint8_t changed) {
         c[2] = c[2] * mod;  c[3] = c[3] * mod;
     }
 
-    /* ranks: budget descending stable over all 4 (agent.rs:168-176), cost ascending
-     * stable over K (agent.rs:224-232) */
-    unsigned brank[4], crank[4];
-    for (int m = 0; m < 4; ++m) {
-        unsigned rb = 0, rc = 0;
-        for (int o = 0; o < 4; ++o) {
-            if (o == m) continue;
-            if (b[o] > b[m] || (b[o] == b[m] && o < m)) rb++;
-            if (((K >> o) & 1u) && (c[o] < c[m] || (c[o] == c[m] && o < m))) rc++;
+    /* ranks: budget descending stable over all 4 (agent.rs:168-176), cost ascending stable over K
+     * (agent.rs:224-232).  A stable sort over the canonical order puts m before o (o < m) only if m is strictly
+     * better; partial_cmp(..).unwrap_or(Equal) makes an unordered (NaN) pair a tie, so o stays first. */
+    unsigned brank[4] = {0, 0, 0, 0}, crank[4] = {0, 0, 0, 0};
+    for (int o = 0; o < 3; ++o)
+        for (int m = o + 1; m < 4; ++m) {
+            if (b[m] > b[o]) brank[o]++; else brank[m]++;
+            if (((K >> o) & 1u) && ((K >> m) & 1u)) {
+                if (c[m] < c[o]) crank[o]++; else crank[m]++;
+            }
         }
-        brank[m] = rb; crank[m] = rc;
-    }
 
     /* allowed set and pick (agent.rs:274-315): min sum, tie -> min budget rank */
     unsigned A = K;
