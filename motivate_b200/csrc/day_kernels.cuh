@@ -36,8 +36,6 @@
 
 namespace mvb {
 
-constexpr uint32_t kThreads = 1024;
-constexpr uint32_t kWarps = kThreads / 32;
 constexpr uint32_t kCodeAddrMask = 0x07FFFFFCu;     // byte offset of the vector word (shared or global)
 constexpr uint32_t kStatValid = 0x80000000u;        // bit 31 of the packed static word: a real agent
 
@@ -53,7 +51,7 @@ struct RepDev {                     // device-side descriptor of one replica
     const uint32_t* deg;            // [N_pad] SELL agents: ds_hot | dn_hot<<8 | ds_cold<<16 | dn_cold<<24
     const StageRange* ranges;
     const uint64_t* hub_off; const uint4* hub_deg; const uint32_t* hub_codes;   // per hub: block offset, (ds_hot, dn_hot, ds_cold, dn_cold)
-    const uint64_t* sell_off; const uint32_t* sell_K; const uint32_t* sell_order; const uint32_t* sell_codes;
+    const uint4* sell_meta; const uint32_t* sell_codes;       // per slice {off_lo, off_hi, K | Kc << 16, 0}
     const float* supp; const float* desir;       // [H][4], [S][4]
     const uint32_t* cap; const uint32_t* nres;   // [H][4], [H]
     float* cong;                    // [H][4] modifier used by the last step (for mvb_get_state)
@@ -61,11 +59,14 @@ struct RepDev {                     // device-side descriptor of one replica
 
 __host__ __device__ inline uint32_t rec_width(uint32_t S, uint32_t H) { return 4 * H + 7 + S; }
 // words of shared memory a block needs besides the staged vector:
-// mbarrier(2) + counter(2) + hub counts [2][32][8] + replica descriptor + cong[H][4] + cost_base[H][3][4] + desir[S][4] + record
-constexpr uint32_t kRepWords = 64;                   // sizeof(RepDev) rounded up, in u32
-static_assert(sizeof(RepDev) <= kRepWords * 4, "RepDev outgrew its shared-memory slot");
+// mbarrier(2) + spare(2) + hub counts [2][32][8] + cong[H][4] + cost_base[H][3][4] + desir[S][4] + record
+// The day kernel receives the replica descriptors BY VALUE (constant bank, uniform registers): up to
+// kMaxRepsPerLaunch per launch; more replicas take several launches per weekday.
+constexpr uint32_t kMaxRepsPerLaunch = 64;
+struct RepArray { RepDev r[kMaxRepsPerLaunch]; };
+static_assert(sizeof(RepArray) <= 24 * 1024, "kernel parameter space");
 __host__ __device__ inline uint32_t tail_words(uint32_t S, uint32_t H) {
-    return 4 + 512 + kRepWords + 4 * H + 12 * H + 4 * S + rec_width(S, H);
+    return 4 + 512 + 4 * H + 12 * H + 4 * S + rec_width(S, H);
 }
 
 // ---- small PTX helpers ----------------------------------------------------------------------
@@ -94,6 +95,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
     while (!ok)
         asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
                      : "=r"(ok) : "r"(a), "r"(phase) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* p, uint32_t bytes) {     // TMA prefetch of a byte range into L2
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -215,7 +219,7 @@ __device__ __forceinline__ void finish_slice(const RepDev& r, uint32_t slice, ui
     float h[4] = {hv.x, hv.y, hv.z, hv.w};
     habit_update(h, last, w.average_weight);
     uint32_t mode, norm;
-    decide(cs, ds, cn, dn, w, h, s_des + 4 * st_sub(stat), s_cong + 4 * st_nbhd(stat),
+    decide<!PER_AGENT>(cs, ds, cn, dn, w, h, s_des + 4 * st_sub(stat), s_cong + 4 * st_nbhd(stat),
            s_cost + 12 * st_nbhd(stat) + 4 * st_commute(stat), st_commute(stat), st_car(stat), st_bike(stat), wsv,
            last, weather, changed, mode, norm);
     if (!valid) { mode = 0; norm = 0; }
@@ -267,18 +271,16 @@ __device__ __forceinline__ void flush_warp_stats(const RepDev& r, uint32_t lane,
 }
 
 // ---- the weekday kernel ----------------------------------------------------------------------------
-template <bool PER_AGENT>
-__global__ void __launch_bounds__(kThreads, 1)
-day_kernel(const RepDev* __restrict__ reps, uint32_t R, uint32_t P, uint32_t parity,
+template <bool PER_AGENT, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
+day_kernel(const __grid_constant__ RepArray reps, uint32_t R, uint32_t P, uint32_t parity,
            const uint32_t* __restrict__ rec_prev, uint32_t* __restrict__ rec_next, uint32_t weather,
            uint32_t changed, AgentWeights uw, uint32_t vec_cap_words) {
     extern __shared__ __align__(128) uint32_t smem[];
     uint32_t* s_vec = smem;
     uint32_t* s_tail = smem + vec_cap_words;
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_tail);
-    uint32_t* s_next = s_tail + 2;
     uint32_t* s_hub = s_tail + 4;                     // [2][32][8]
-    uint32_t* s_rep = s_hub + 512;                    // RepDev of the current part
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 
     if (tid == 0) mbar_init(s_bar, 1);
@@ -286,12 +288,10 @@ day_kernel(const RepDev* __restrict__ reps, uint32_t R, uint32_t P, uint32_t par
 
     for (uint32_t part = blockIdx.x; part < R * P; part += gridDim.x) {
         const uint32_t p = part % P;
-        __syncthreads();                              // previous part is done with shared memory
-        if (tid < sizeof(RepDev) / 4) s_rep[tid] = reinterpret_cast<const uint32_t*>(reps + part / P)[tid];
-        __syncthreads();
-        const RepDev& r = *reinterpret_cast<const RepDev*>(s_rep);
+        const RepDev& r = reps.r[part / P];
         const uint32_t H = r.H, S = r.S;
-        float* s_cong = reinterpret_cast<float*>(s_rep + kRepWords);
+        float* s_cong = reinterpret_cast<float*>(s_hub + 512);
+        __syncthreads();                              // previous part is done with shared memory
         float* s_cost = s_cong + 4 * H;
         float* s_des = s_cost + 12 * H;
         uint32_t* s_rec = reinterpret_cast<uint32_t*>(s_des + 4 * S);
@@ -307,19 +307,18 @@ day_kernel(const RepDev* __restrict__ reps, uint32_t R, uint32_t P, uint32_t par
                     bulk_g2s(s_vec + g.dst_word + o, g_vec + g.src_word + o, n * 4u, s_bar);
                 }
             }
-            *s_next = 0;
         }
-        for (uint32_t k = tid; k < 4 * H; k += kThreads) {                 // neighbourhood.rs:57-89
+        for (uint32_t k = tid; k < 4 * H; k += THREADS) {                 // neighbourhood.rs:57-89
             const float c = congestion_entry(rec_prev[r.rec_off + k], r.cap[k], r.nres[k >> 2]);
             s_cong[k] = c;
             if (p == 0) r.cong[k] = c;
         }
-        for (uint32_t k = tid; k < 12 * H; k += kThreads) {                // agent.rs:185-196
+        for (uint32_t k = tid; k < 12 * H; k += THREADS) {                // agent.rs:185-196
             const uint32_t hh = k / 12, c = (k >> 2) % 3, m = k & 3;
             s_cost[k] = cost_base_entry(r.supp[4 * hh + m], c, m);
         }
-        for (uint32_t k = tid; k < 4 * S; k += kThreads) s_des[k] = r.desir[k];
-        for (uint32_t k = tid; k < rec_width(S, H); k += kThreads) s_rec[k] = 0;
+        for (uint32_t k = tid; k < 4 * S; k += THREADS) s_des[k] = r.desir[k];
+        for (uint32_t k = tid; k < rec_width(S, H); k += THREADS) s_rec[k] = 0;
         __syncthreads();
         mbar_wait(s_bar, phase);
         phase ^= 1u;
@@ -329,7 +328,8 @@ day_kernel(const RepDev* __restrict__ reps, uint32_t R, uint32_t P, uint32_t par
         // 2. hub slices: one warp per hub agent, the hub's lists cut into 32 chunks (one per lane)
         uint32_t hbuf = 0;
         for (uint32_t hs = p; hs < r.n_hub_slices; hs += P, hbuf ^= 1u) {
-            const uint32_t hub = hs * 32 + warp;
+          for (uint32_t hh = warp; hh < 32; hh += THREADS / 32) {
+            const uint32_t hub = hs * 32 + hh;
             const uint4 hd = r.hub_deg[hub];                    // ds_hot, dn_hot, ds_cold, dn_cold
             const uint32_t n_hot = hd.x + hd.y, n_cold = hd.z + hd.w;
             uint32_t cs[4] = {0, 0, 0, 0}, cn[4] = {0, 0, 0, 0};
@@ -356,8 +356,9 @@ day_kernel(const RepDev* __restrict__ reps, uint32_t R, uint32_t P, uint32_t par
             if (lane < 8) {
                 const uint32_t v = lane == 0 ? cs[0] : lane == 1 ? cs[1] : lane == 2 ? cs[2] : lane == 3 ? cs[3]
                                  : lane == 4 ? cn[0] : lane == 5 ? cn[1] : lane == 6 ? cn[2] : cn[3];
-                s_hub[hbuf * 256 + warp * 8 + lane] = v;
+                s_hub[hbuf * 256 + hh * 8 + lane] = v;
             }
+          }
             __syncthreads();
             if (warp == 0) {
                 const uint32_t agent = hs * 32 + lane;
@@ -373,17 +374,32 @@ day_kernel(const RepDev* __restrict__ reps, uint32_t R, uint32_t P, uint32_t par
             }
         }
 
-        // 3. SELL slices: one lane per agent, slices handed out longest-first from a block-wide counter
-        for (;;) {
-            uint32_t q = 0;
-            if (lane == 0) q = atomicAdd(s_next, 1u);
-            q = __shfl_sync(0xFFFFFFFFu, q, 0);
-            const uint64_t idx = (uint64_t)p + (uint64_t)P * q;
-            if (idx >= r.n_sell_slices) break;
-            const uint32_t s = r.sell_order[idx];
+        // 3. SELL slices: one lane per agent; warp w of this part takes slices p + P*(w + nwarps*i).  The slice
+        // record is read two slices ahead, and the slice after this one is pulled into L2 (its link codes and its
+        // agents' state) by TMA prefetches while this one is being processed.
+        const uint32_t n_sell = r.n_sell_slices;
+        const uint64_t stride = (uint64_t)P * (THREADS / 32);
+        uint64_t idx = (uint64_t)p + (uint64_t)P * warp;
+        uint4 meta = make_uint4(0, 0, 0, 0), meta1 = meta;
+        if (idx < n_sell) meta = r.sell_meta[idx];
+        if (idx + stride < n_sell) meta1 = r.sell_meta[idx + stride];
+        for (; idx < n_sell; idx += stride) {
+            const uint32_t s = (uint32_t)idx;
+            uint4 meta2 = make_uint4(0, 0, 0, 0);
+            if (idx + 2 * stride < n_sell) meta2 = r.sell_meta[idx + 2 * stride];
+            if (idx + stride < n_sell) {
+                const uint32_t s1 = (uint32_t)(idx + stride), a1 = (r.n_hub_slices + s1) * 32;
+                const uint32_t nrow = (meta1.z & 0xFFFFu) + (meta1.z >> 16);
+                if (lane == 0 && nrow) prefetch_l2(r.sell_codes + (((uint64_t)meta1.y << 32) | meta1.x), nrow * 128u);
+                if (lane == 1) prefetch_l2(r.stat + a1, 128u);
+                if (lane == 2) prefetch_l2(r.deg + a1, 128u);
+                if (lane == 3) prefetch_l2(r.ws + a1, 128u);
+                if (lane == 4) prefetch_l2(r.habit + a1, 512u);
+            }
             const uint32_t slice = r.n_hub_slices + s, agent = slice * 32 + lane;
-            const uint32_t KK = r.sell_K[s];
-            const uint32_t* blk = r.sell_codes + r.sell_off[s];
+            const uint32_t KK = meta.z;
+            const uint32_t* blk = r.sell_codes + (((uint64_t)meta.y << 32) | meta.x);
+            meta = meta1; meta1 = meta2;
             // the agent's own state goes out with the first rows of link codes
             const uint32_t stat = r.stat[agent];
             const uint32_t dg = r.deg[agent];
@@ -403,7 +419,7 @@ day_kernel(const RepDev* __restrict__ reps, uint32_t R, uint32_t P, uint32_t par
         }
         flush_warp_stats(r, lane, s_rec, st);
         __syncthreads();
-        for (uint32_t k = tid; k < rec_width(S, H); k += kThreads)
+        for (uint32_t k = tid; k < rec_width(S, H); k += THREADS)
             if (s_rec[k]) atomicAdd(&rec_next[r.rec_off + k], s_rec[k]);
     }
 }

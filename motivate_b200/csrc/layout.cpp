@@ -230,10 +230,10 @@ int build_graph_layout(const mvb_population& pop, uint32_t H, uint32_t capacity_
             for (uint32_t k = 0; k < lc.size(); ++k) put_cold(blk, K, l, k, lc[k]);
         }
     }
-    L.sell_order.resize(L.n_sell_slices);
-    std::iota(L.sell_order.begin(), L.sell_order.end(), 0u);
-    auto work = [&](uint32_t s) { return (L.sell_K[s] & 0xFFFFu) + 2u * (L.sell_K[s] >> 16); };
-    std::stable_sort(L.sell_order.begin(), L.sell_order.end(), [&](uint32_t a, uint32_t b) { return work(a) > work(b); });
+    // one 16-byte record per slice; 64 zero records of slack let the kernel prefetch past the end
+    L.sell_meta.assign((size_t)L.n_sell_slices + 64, uint4x{0, 0, 0, 0});
+    for (uint32_t s = 0; s < L.n_sell_slices; ++s)
+        L.sell_meta[s] = uint4x{(uint32_t)L.sell_off[s], (uint32_t)(L.sell_off[s] >> 32), L.sell_K[s], 0};
     return MVB_OK;
 }
 

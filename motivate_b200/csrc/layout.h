@@ -55,6 +55,8 @@ inline void hub_segment(uint32_t rem_hot, uint32_t rem_cold, uint32_t& K, uint32
     if (Kc > 252u - K) Kc = 252u - K;
 }
 
+struct uint4x { uint32_t x, y, z, w; };   // host-side mirror of CUDA's uint4 (16 bytes)
+
 struct StageRange {                // one contiguous piece of the mode vector staged in shared memory
     uint32_t src_word;             // first u32 word in the global packed vector (16 agents per word)
     uint32_t n_words;              // multiple of 4 (16 bytes)
@@ -80,7 +82,7 @@ struct GraphLayout {
     // SELL
     std::vector<uint64_t> sell_off;        // [n_sell_slices] offset of the slice in sell_codes (u32 units)
     std::vector<uint32_t> sell_K;          // [n_sell_slices] K | Kc << 16
-    std::vector<uint32_t> sell_order;      // [n_sell_slices] processing order, longest lists first
+    std::vector<uint4x> sell_meta;         // [n_sell_slices + 64] {off_lo, off_hi, K | Kc << 16, 0}: what the kernel reads
     std::vector<uint32_t> sell_codes;
 };
 

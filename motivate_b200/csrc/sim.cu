@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <numeric>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <new>
@@ -38,7 +39,7 @@ struct DevBuf {                       // owning device allocation
 // (scenario sweeps over one population pass the same graph + neighbourhood arrays).
 struct Graph {
     GraphLayout L;                 // host copy: permutation, sizes (code arrays are released after upload)
-    DevBuf deg, ranges, hub_off, hub_deg, hub_codes, sell_off, sell_K, sell_order, sell_codes;
+    DevBuf deg, ranges, hub_off, hub_deg, hub_codes, sell_meta, sell_codes;
     const void* key[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // caller pointers it was built from
 };
 
@@ -61,8 +62,10 @@ struct mvb_sim {
     std::vector<Replica> reps;
     DevBuf d_reps;                       // RepDev[R]
     std::vector<RepDev> h_reps;
+    std::vector<RepArray> rep_args;      // h_reps cut into kernel-parameter sized pieces
     uint32_t rec_stride = 0;             // u32 per record row (all replicas)
-    uint32_t grid = 0, P = 1;            // persistent blocks, parts per replica
+    uint32_t grid = 0;                   // persistent blocks (one per SM)
+    uint32_t threads = 1024;             // block size of the day kernel (MVB_THREADS=512 selects the 128-register variant)
     uint32_t max_npad = 0;
     uint32_t vec_cap_words = 0;          // shared-memory words reserved for the staged mode vector
     size_t smem_bytes = 0, census_smem = 0;
@@ -122,18 +125,21 @@ int launch_day(mvb_sim* s, uint8_t weather, uint8_t changed) {
     uint32_t* next = s->rec.as<uint32_t>() + (size_t)(s->cursor + 1) * s->rec_stride;
     AgentWeights uw{s->prm.consistency, s->prm.social_connectivity, s->prm.subculture_connectivity,
                     s->prm.neighbourhood_connectivity, s->prm.average_weight};
-    const uint32_t R = (uint32_t)s->reps.size();
-    if (s->any_per_agent)
-        day_kernel<true><<<s->grid, kThreads, s->smem_bytes, s->stream>>>(
-            s->d_reps.as<RepDev>(), R, s->P, s->parity, prev, next, weather, changed, uw, s->vec_cap_words);
-    else
-        day_kernel<false><<<s->grid, kThreads, s->smem_bytes, s->stream>>>(
-            s->d_reps.as<RepDev>(), R, s->P, s->parity, prev, next, weather, changed, uw, s->vec_cap_words);
-    MVB_CUDA(cudaGetLastError());
+    // replica descriptors travel as kernel parameters, kMaxRepsPerLaunch at a time
+#define MVB_LAUNCH(PA, T) day_kernel<PA, T><<<s->grid, T, s->smem_bytes, s->stream>>>( \
+        s->rep_args[c], R, P, s->parity, prev, next, weather, changed, uw, s->vec_cap_words)
+    for (size_t c = 0; c < s->rep_args.size(); ++c) {
+        const uint32_t R = std::min<uint32_t>(kMaxRepsPerLaunch, (uint32_t)s->reps.size() - (uint32_t)c * kMaxRepsPerLaunch);
+        const uint32_t P = s->grid / std::gcd(R, s->grid);      // R*P parts = lcm(R, grid): every block gets the same number
+        if (s->threads == 512) { if (s->any_per_agent) MVB_LAUNCH(true, 512); else MVB_LAUNCH(false, 512); }
+        else                   { if (s->any_per_agent) MVB_LAUNCH(true, 1024); else MVB_LAUNCH(false, 1024); }
+        MVB_CUDA(cudaGetLastError());
+        s->last_launches++;
+    }
+#undef MVB_LAUNCH
     s->cursor++;
     s->parity ^= 1u;
     s->stepped = true;
-    s->last_launches++;
     return MVB_OK;
 }
 
@@ -253,6 +259,11 @@ int mvb_create_batch(uint32_t R, const mvb_population* const* pops, const mvb_ta
     if (!s) { set_error("out of memory"); return MVB_ERR_NOMEM; }
     s->device = device;
     s->prm = *prm;
+    {   // the uniform-weight kernel's division shortcut (decide.cuh FAST_SHARES) needs tame connectivities;
+        // anything else goes through the general kernel, which divides with plain IEEE `/`
+        auto tame = [](float w) { return w >= 0x1p-60f && w <= 0x1p60f; };
+        if (!tame(prm->social_connectivity) || !tame(prm->neighbourhood_connectivity)) s->any_per_agent = true;
+    }
     MVB_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     MVB_CUDA(cudaEventCreate(&s->ev0));
     MVB_CUDA(cudaEventCreate(&s->ev1));
@@ -277,7 +288,6 @@ int mvb_create_batch(uint32_t R, const mvb_population* const* pops, const mvb_ta
     s->census_smem = sizeof(uint32_t) * census_words;
     const uint32_t capacity_agents = s->vec_cap_words * 16u / 64u * 64u;
     s->grid = (uint32_t)sms;
-    s->P = s->grid / std::gcd(R, s->grid);              // R*P parts = lcm(R, grid): every block gets the same number
 
     s->reps.resize(R);
     s->h_reps.resize(R);
@@ -304,8 +314,7 @@ int mvb_create_batch(uint32_t R, const mvb_population* const* pops, const mvb_ta
             if ((rc = upload(g->deg, L.deg, s->stream)) || (rc = upload(g->ranges, L.ranges, s->stream)) ||
                 (rc = upload(g->hub_off, L.hub_off, s->stream)) || (rc = upload(g->hub_deg, L.hub_deg, s->stream)) ||
                 (rc = upload(g->hub_codes, L.hub_codes, s->stream)) ||
-                (rc = upload(g->sell_off, L.sell_off, s->stream)) || (rc = upload(g->sell_K, L.sell_K, s->stream)) ||
-                (rc = upload(g->sell_order, L.sell_order, s->stream)) || (rc = upload(g->sell_codes, L.sell_codes, s->stream)))
+                (rc = upload(g->sell_meta, L.sell_meta, s->stream)) || (rc = upload(g->sell_codes, L.sell_codes, s->stream)))
                 return rc;
             MVB_CUDA(cudaStreamSynchronize(s->stream));
             std::vector<uint32_t>().swap(L.hub_codes);           // the big arrays now live on the device only
@@ -376,17 +385,21 @@ int mvb_create_batch(uint32_t R, const mvb_population* const* pops, const mvb_ta
         d.deg = g.deg.as<uint32_t>(); d.ranges = g.ranges.as<StageRange>();
         d.hub_off = g.hub_off.as<uint64_t>(); d.hub_deg = g.hub_deg.as<uint4>();
         d.hub_codes = g.hub_codes.as<uint32_t>();
-        d.sell_off = g.sell_off.as<uint64_t>(); d.sell_K = g.sell_K.as<uint32_t>(); d.sell_order = g.sell_order.as<uint32_t>();
-        d.sell_codes = g.sell_codes.as<uint32_t>();
+        d.sell_meta = g.sell_meta.as<uint4>(); d.sell_codes = g.sell_codes.as<uint32_t>();
         d.supp = rp.tables_f.as<float>(); d.desir = rp.tables_f.as<float>() + 4 * rp.H;
         d.cap = rp.tables_u.as<uint32_t>(); d.nres = rp.tables_u.as<uint32_t>() + 4 * rp.H;
         d.cong = rp.cong.as<float>();
         if (L.hot_words > s->vec_cap_words) { set_error("internal: staged vector larger than its shared-memory slot"); return MVB_ERR_STATE; }
     }
-    MVB_CUDA(cudaFuncSetAttribute(day_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
-    MVB_CUDA(cudaFuncSetAttribute(day_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
+    if (const char* t = getenv("MVB_THREADS")) s->threads = atoi(t) == 512 ? 512 : 1024;
+    MVB_CUDA(cudaFuncSetAttribute(day_kernel<true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
+    MVB_CUDA(cudaFuncSetAttribute(day_kernel<false, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
+    MVB_CUDA(cudaFuncSetAttribute(day_kernel<true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
+    MVB_CUDA(cudaFuncSetAttribute(day_kernel<false, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
     if (s->census_smem > 48 * 1024)
         MVB_CUDA(cudaFuncSetAttribute(census_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->census_smem));
+    s->rep_args.assign((R + kMaxRepsPerLaunch - 1) / kMaxRepsPerLaunch, RepArray{});
+    for (uint32_t r = 0; r < R; ++r) s->rep_args[r / kMaxRepsPerLaunch].r[r % kMaxRepsPerLaunch] = s->h_reps[r];
     MVB_CUDA(s->d_reps.alloc(sizeof(RepDev) * R));
     int rc = upload_reps(s);
     if (rc) return rc;
