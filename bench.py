@@ -222,10 +222,9 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    if args.replicas % world:
-        raise SystemExit("--replicas must be divisible by the number of ranks")
-    per = args.replicas // world
-    my_ids = list(range(rank * per, (rank + 1) * per))
+    from motivate_b200.sharding import replicas_of_rank
+    my_ids = replicas_of_rank(args.replicas, rank, world)        # contiguous share, no communication
+    per = len(my_ids)
     pops, tabs = make_inputs(args, my_ids)
     prm = mb.make_params()
     n_days = weekdays_calendar(args.warmup + args.steps)
