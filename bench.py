@@ -103,10 +103,14 @@ class ClockSampler:
 
 
 def make_inputs(args, replica_ids, pinned=False):
+    """Synthetic populations (master seed 0, replica r -> seed r), generated on all host cores; with pinned=True the
+    arrays live in page-locked host memory so mvb_create_batch's H2D copies run at full PCIe speed."""
+    from concurrent.futures import ThreadPoolExecutor
+
     import motivate_b200 as mb
-    pops, tabs = [], []
-    for r in replica_ids:
-        p = mb.synth_population(args.agents, 4, 10, 5, 10, seed=r)        # master seed 0, replica r -> seed r
+
+    def one(r):
+        p = mb.synth_population(args.agents, 4, 10, 5, 10, seed=r)        # ctypes call: releases the GIL
         if pinned:
             import torch
             p._pins = []
@@ -119,9 +123,11 @@ def make_inputs(args, replica_ids, pinned=False):
                 p.arrays[k] = a
                 p._pins.append(t)
             p._struct = None
-        pops.append(p)
-        tabs.append(mb.synth_tables(4, 10, args.agents, seed=r))
-    return pops, tabs
+        return p, mb.synth_tables(4, 10, args.agents, seed=r)
+
+    with ThreadPoolExecutor(max_workers=min(len(replica_ids), os.cpu_count() or 1)) as ex:
+        res = list(ex.map(one, replica_ids))
+    return [p for p, _ in res], [t for _, t in res]
 
 
 def cpu_reference_throughput(args, n_threads, n_days, warm_days=1):
@@ -225,7 +231,7 @@ def main():
     from motivate_b200.sharding import replicas_of_rank
     my_ids = replicas_of_rank(args.replicas, rank, world)        # contiguous share, no communication
     per = len(my_ids)
-    pops, tabs = make_inputs(args, my_ids)
+    pops, tabs = make_inputs(args, my_ids, pinned=not args.no_e2e)
     prm = mb.make_params()
     n_days = weekdays_calendar(args.warmup + args.steps)
     w = mb.weather_pattern(n_days, seed=0)
@@ -275,7 +281,7 @@ def main():
     }
 
     if not args.no_e2e:
-        out["e2e"] = e2e(args, my_ids, prm, w, n_days, local_rank, world, dist if world > 1 else None, torch)
+        out["e2e"] = e2e(args, pops, tabs, prm, w, n_days, local_rank, world, dist if world > 1 else None, torch)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         v, dt = cpu_reference_throughput(args, cores, args.cpu_baseline_days)
@@ -299,11 +305,10 @@ def profile_traffic():
     return None
 
 
-def e2e(args, my_ids, prm, w, n_days, local_rank, world, dist, torch):
+def e2e(args, pops, tabs, prm, w, n_days, local_rank, world, dist, torch):
     """Same metric through the public call a host makes, with HOST buffers: mvb_create_batch (population H2D from
     pinned memory) + mvb_run over the same calendar (weather in, statistics rows D2H) + mvb_destroy."""
     import motivate_b200 as mb
-    pops, tabs = make_inputs(args, my_ids, pinned=True)
     h2d = sum(sum(v.nbytes for v in p.arrays.values() if v is not None) for p in pops) + n_days
     if dist:
         dist.barrier()

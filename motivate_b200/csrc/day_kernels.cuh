@@ -51,6 +51,7 @@ struct RepDev {                     // device-side descriptor of one replica
     const uint32_t* deg;            // [N_pad] SELL agents: ds_hot | dn_hot<<8 | ds_cold<<16 | dn_cold<<24
     const StageRange* ranges;
     const uint64_t* hub_off; const uint4* hub_deg; const uint32_t* hub_codes;   // per hub: block offset, (ds_hot, dn_hot, ds_cold, dn_cold)
+    uint32_t* hub_cnt;              // [n_hub_slices*32][8] scratch: a hub's 4 social + 4 neighbour counts of the day
     const uint4* sell_meta; const uint32_t* sell_codes;       // per slice {off_lo, off_hi, K | Kc << 16, 0}
     const float* supp; const float* desir;       // [H][4], [S][4]
     const uint32_t* cap; const uint32_t* nres;   // [H][4], [H]
@@ -59,14 +60,14 @@ struct RepDev {                     // device-side descriptor of one replica
 
 __host__ __device__ inline uint32_t rec_width(uint32_t S, uint32_t H) { return 4 * H + 7 + S; }
 // words of shared memory a block needs besides the staged vector:
-// mbarrier(2) + spare(2) + hub counts [2][32][8] + cong[H][4] + cost_base[H][3][4] + desir[S][4] + record
+// mbarrier(2) + work counter(2) + cong[H][4] + cost_base[H][3][4] + desir[S][4] + record
 // The day kernel receives the replica descriptors BY VALUE (constant bank, uniform registers): up to
 // kMaxRepsPerLaunch per launch; more replicas take several launches per weekday.
 constexpr uint32_t kMaxRepsPerLaunch = 64;
 struct RepArray { RepDev r[kMaxRepsPerLaunch]; };
 static_assert(sizeof(RepArray) <= 24 * 1024, "kernel parameter space");
 __host__ __device__ inline uint32_t tail_words(uint32_t S, uint32_t H) {
-    return 4 + 512 + 4 * H + 12 * H + 4 * S + rec_width(S, H);
+    return 4 + 4 * H + 12 * H + 4 * S + rec_width(S, H);
 }
 
 // ---- small PTX helpers ----------------------------------------------------------------------
@@ -80,6 +81,12 @@ __device__ __forceinline__ uint4 ld_stream_v4(const uint4* p) {       // read-on
 __device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t* p) {
     uint32_t v;
     asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ld_stream_f32(const float* p) { return __uint_as_float(ld_stream_u32(reinterpret_cast<const uint32_t*>(p))); }
+__device__ __forceinline__ uint2 ld_stream_v2(const uint2* p) {
+    uint2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
     return v;
 }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -158,6 +165,14 @@ __device__ __forceinline__ void accumulate_block(const uint32_t* __restrict__ bl
     if (Kt > 0) t0 = ld_stream_u32(tail);                       // the short tail goes out with the first rows
     if (Kt > 1) t1 = ld_stream_u32(tail + 32);
     if (Kt > 2) t2 = ld_stream_u32(tail + 64);
+    // cold list (targets outside shared memory, gathered from L2): its first two links go out with the first rows
+    // and their gathers are issued before the hot loop, so both round trips overlap the shared-memory work
+    const uint32_t* cold = blk + (size_t)K * 32 + lane;
+    uint32_t c0 = 0, c1 = 0, w0 = 0, w1 = 0;
+    if (Kc > 0) c0 = ld_stream_u32(cold);
+    if (Kc > 1) c1 = ld_stream_u32(cold + 32);
+    if (Kc > 0) w0 = __ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(g_vec) + (c0 >> 5)));
+    if (Kc > 1) w1 = __ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(g_vec) + (c1 >> 5)));
     uint32_t q = 0, bits = 0;
     for (; q + 4 <= K4; q += 4) {                               // 16 links per lane, two rows kept in flight
         r2 = ld_stream_v4(body + (size_t)(q + 2) * 32);
@@ -183,8 +198,15 @@ __device__ __forceinline__ void accumulate_block(const uint32_t* __restrict__ bl
         bits <<= 2u * (16u - (rem * 4u + Kt));                  // first link of the group back to field 15
         count_fields(bits, (int)(q * 4), ds_h, d_h, acc_s, acc_n);
     }
-    const uint32_t* cold = blk + (size_t)K * 32 + lane;        // cold list: targets outside shared memory, from L2
-    for (uint32_t k = 0; k < Kc; ++k) {
+    if (0 < d_c) {
+        const uint32_t inc = 1u << ((__funnelshift_l(0u, w0, c0) >> 30) * 8u);
+        if (0 < ds_c) acc_s += inc; else acc_n += inc;
+    }
+    if (1 < d_c) {
+        const uint32_t inc = 1u << ((__funnelshift_l(0u, w1, c1) >> 30) * 8u);
+        if (1 < ds_c) acc_s += inc; else acc_n += inc;
+    }
+    for (uint32_t k = 2; k < Kc; ++k) {
         const uint32_t code = ld_stream_u32(cold + (size_t)k * 32);
         if ((int)k < d_c) {
             const uint32_t inc = 1u << ((top2_cold(g_vec, code) >> 30) * 8u);
@@ -280,7 +302,7 @@ day_kernel(const __grid_constant__ RepArray reps, uint32_t R, uint32_t P, uint32
     uint32_t* s_vec = smem;
     uint32_t* s_tail = smem + vec_cap_words;
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_tail);
-    uint32_t* s_hub = s_tail + 4;                     // [2][32][8]
+    uint32_t* s_next = s_tail + 2;                    // work-item counter of the current part
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 
     if (tid == 0) mbar_init(s_bar, 1);
@@ -290,7 +312,7 @@ day_kernel(const __grid_constant__ RepArray reps, uint32_t R, uint32_t P, uint32
         const uint32_t p = part % P;
         const RepDev& r = reps.r[part / P];
         const uint32_t H = r.H, S = r.S;
-        float* s_cong = reinterpret_cast<float*>(s_hub + 512);
+        float* s_cong = reinterpret_cast<float*>(s_tail + 4);
         __syncthreads();                              // previous part is done with shared memory
         float* s_cost = s_cong + 4 * H;
         float* s_des = s_cost + 12 * H;
@@ -307,6 +329,7 @@ day_kernel(const __grid_constant__ RepArray reps, uint32_t R, uint32_t P, uint32
                     bulk_g2s(s_vec + g.dst_word + o, g_vec + g.src_word + o, n * 4u, s_bar);
                 }
             }
+            *s_next = 0;
         }
         for (uint32_t k = tid; k < 4 * H; k += THREADS) {                 // neighbourhood.rs:57-89
             const float c = congestion_entry(rec_prev[r.rec_off + k], r.cap[k], r.nres[k >> 2]);
@@ -325,12 +348,13 @@ day_kernel(const __grid_constant__ RepArray reps, uint32_t R, uint32_t P, uint32
 
         WarpStats st{0, 0, 0, 0, 0, 0, 0};
 
-        // 2. hub slices: one warp per hub agent, the hub's lists cut into 32 chunks (one per lane)
-        uint32_t hbuf = 0;
-        for (uint32_t hs = p; hs < r.n_hub_slices; hs += P, hbuf ^= 1u) {
-          for (uint32_t hh = warp; hh < 32; hh += THREADS / 32) {
-            const uint32_t hub = hs * 32 + hh;
-            const uint4 hd = r.hub_deg[hub];                    // ds_hot, dn_hot, ds_cold, dn_cold
+        // 2. hubs of this part's hub slices (p, p+P, ...): one warp per hub agent, the hub's lists cut into 32 chunks
+        // (one per lane).  The 8 counts of a hub go to a small global scratch; the hub slices are finished below
+        // like any other slice, so no warp waits for another here.
+        const uint32_t n_my_hub_slices = r.n_hub_slices > p ? (r.n_hub_slices - p + P - 1) / P : 0;
+        for (uint32_t j = warp; j < n_my_hub_slices * 32; j += THREADS / 32) {
+            const uint32_t hub = (p + P * (j >> 5)) * 32 + (j & 31u);
+            const uint4 hd = ld_stream_v4(reinterpret_cast<const uint4*>(r.hub_deg) + hub);   // ds_hot, dn_hot, ds_cold, dn_cold
             const uint32_t n_hot = hd.x + hd.y, n_cold = hd.z + hd.w;
             uint32_t cs[4] = {0, 0, 0, 0}, cn[4] = {0, 0, 0, 0};
             const uint32_t* blk = r.hub_codes + r.hub_off[hub];
@@ -356,39 +380,33 @@ day_kernel(const __grid_constant__ RepArray reps, uint32_t R, uint32_t P, uint32
             if (lane < 8) {
                 const uint32_t v = lane == 0 ? cs[0] : lane == 1 ? cs[1] : lane == 2 ? cs[2] : lane == 3 ? cs[3]
                                  : lane == 4 ? cn[0] : lane == 5 ? cn[1] : lane == 6 ? cn[2] : cn[3];
-                s_hub[hbuf * 256 + hh * 8 + lane] = v;
-            }
-          }
-            __syncthreads();
-            if (warp == 0) {
-                const uint32_t agent = hs * 32 + lane;
-                uint32_t hcs[4], hcn[4];
-#pragma unroll
-                for (int m = 0; m < 4; ++m) { hcs[m] = s_hub[hbuf * 256 + lane * 8 + m]; hcn[m] = s_hub[hbuf * 256 + lane * 8 + 4 + m]; }
-                const uint32_t stat = r.stat[agent];
-                const uint4 ad = r.hub_deg[agent];
-                const uint2 own = r.vec[parity][hs];
-                const uint32_t last = ((lane < 16 ? own.x : own.y) >> ((lane & 15u) * 2u)) & 3u;
-                finish_slice<PER_AGENT>(r, hs, lane, false, hcs, ad.x + ad.z, hcn, ad.y + ad.w, stat, r.ws[agent],
-                                        r.habit[agent], last, uw, s_cong, s_cost, s_des, s_rec, weather, changed, parity, st);
+                r.hub_cnt[(size_t)hub * 8 + lane] = v;
             }
         }
+        __syncthreads();                              // the hub counts written above are read by other warps below
 
-        // 3. SELL slices: one lane per agent; warp w of this part takes slices p + P*(w + nwarps*i).  The slice
-        // record is read two slices ahead, and the slice after this one is pulled into L2 (its link codes and its
-        // agents' state) by TMA prefetches while this one is being processed.
+        // 3. work items handed out by a block-wide counter: first this part's hub slices (finish only), then its
+        // SELL slices p + P*k: one lane per agent.  The slice record is read two items ahead, and the next slice is
+        // pulled into L2 (its link codes and its agents' state) by TMA prefetches while this one is processed.
         const uint32_t n_sell = r.n_sell_slices;
-        const uint64_t stride = (uint64_t)P * (THREADS / 32);
-        uint64_t idx = (uint64_t)p + (uint64_t)P * warp;
-        uint4 meta = make_uint4(0, 0, 0, 0), meta1 = meta;
-        if (idx < n_sell) meta = r.sell_meta[idx];
-        if (idx + stride < n_sell) meta1 = r.sell_meta[idx + stride];
-        for (; idx < n_sell; idx += stride) {
-            const uint32_t s = (uint32_t)idx;
-            uint4 meta2 = make_uint4(0, 0, 0, 0);
-            if (idx + 2 * stride < n_sell) meta2 = r.sell_meta[idx + 2 * stride];
-            if (idx + stride < n_sell) {
-                const uint32_t s1 = (uint32_t)(idx + stride), a1 = (r.n_hub_slices + s1) * 32;
+        const uint32_t n_my_sell = n_sell > p ? (n_sell - p + P - 1) / P : 0;
+        const uint32_t n_items = n_my_hub_slices + n_my_sell;
+        auto next_item = [&]() -> uint32_t {
+            uint32_t q = 0;
+            if (lane == 0) q = atomicAdd(s_next, 1u);
+            return __shfl_sync(0xFFFFFFFFu, q, 0);
+        };
+        auto meta_of = [&](uint32_t item) -> uint4 {   // SELL items only; zero for hub items / past the end
+            if (item < n_my_hub_slices || item >= n_items) return make_uint4(0, 0, 0, 0);
+            return ld_stream_v4(r.sell_meta + (p + (uint64_t)P * (item - n_my_hub_slices)));
+        };
+        uint32_t it0 = next_item(), it1 = next_item();
+        uint4 meta = meta_of(it0), meta1 = meta_of(it1);
+        while (it0 < n_items) {
+            const uint32_t it2 = next_item();
+            const uint4 meta2 = meta_of(it2);
+            if (it1 < n_items && it1 >= n_my_hub_slices) {
+                const uint32_t s1 = p + P * (it1 - n_my_hub_slices), a1 = (r.n_hub_slices + s1) * 32;
                 const uint32_t nrow = (meta1.z & 0xFFFFu) + (meta1.z >> 16);
                 if (lane == 0 && nrow) prefetch_l2(r.sell_codes + (((uint64_t)meta1.y << 32) | meta1.x), nrow * 128u);
                 if (lane == 1) prefetch_l2(r.stat + a1, 128u);
@@ -396,16 +414,30 @@ day_kernel(const __grid_constant__ RepArray reps, uint32_t R, uint32_t P, uint32
                 if (lane == 3) prefetch_l2(r.ws + a1, 128u);
                 if (lane == 4) prefetch_l2(r.habit + a1, 512u);
             }
+            if (it0 < n_my_hub_slices) {              // finish one hub slice: counts come from the scratch
+                const uint32_t hs = p + P * it0, agent = hs * 32 + lane;
+                const uint4 ca = *reinterpret_cast<const uint4*>(r.hub_cnt + (size_t)agent * 8);
+                const uint4 cb = *reinterpret_cast<const uint4*>(r.hub_cnt + (size_t)agent * 8 + 4);
+                const uint32_t hcs[4] = {ca.x, ca.y, ca.z, ca.w}, hcn[4] = {cb.x, cb.y, cb.z, cb.w};
+                const uint32_t stat = r.stat[agent];
+                const uint4 ad = r.hub_deg[agent];
+                const uint2 own = r.vec[parity][hs];
+                const uint32_t last = ((lane < 16 ? own.x : own.y) >> ((lane & 15u) * 2u)) & 3u;
+                finish_slice<PER_AGENT>(r, hs, lane, false, hcs, ad.x + ad.z, hcn, ad.y + ad.w, stat, r.ws[agent],
+                                        r.habit[agent], last, uw, s_cong, s_cost, s_des, s_rec, weather, changed, parity, st);
+            } else {
+            const uint32_t s = p + P * (it0 - n_my_hub_slices);
             const uint32_t slice = r.n_hub_slices + s, agent = slice * 32 + lane;
             const uint32_t KK = meta.z;
             const uint32_t* blk = r.sell_codes + (((uint64_t)meta.y << 32) | meta.x);
-            meta = meta1; meta1 = meta2;
             // the agent's own state goes out with the first rows of link codes
-            const uint32_t stat = r.stat[agent];
-            const uint32_t dg = r.deg[agent];
-            const float wsv = r.ws[agent];
-            const float4 hv = r.habit[agent];
-            const uint2 own = r.vec[parity][slice];
+            // (all streaming loads bypass L1, which is left to the cold part of the mode vector)
+            const uint32_t stat = ld_stream_u32(r.stat + agent);
+            const uint32_t dg = ld_stream_u32(r.deg + agent);
+            const float wsv = ld_stream_f32(r.ws + agent);
+            const uint4 hraw = ld_stream_v4(reinterpret_cast<const uint4*>(r.habit + agent));
+            const float4 hv = make_float4(__uint_as_float(hraw.x), __uint_as_float(hraw.y), __uint_as_float(hraw.z), __uint_as_float(hraw.w));
+            const uint2 own = ld_stream_v2(r.vec[parity] + slice);
             const int ds_h = (int)(dg & 0xFFu), dn_h = (int)((dg >> 8) & 0xFFu), ds_c = (int)((dg >> 16) & 0xFFu), dn_c = (int)(dg >> 24);
             uint32_t acc_s = 0, acc_n = 0;
             accumulate_block(blk, KK & 0xFFFFu, KK >> 16, lane, ds_h, ds_h + dn_h, ds_c, ds_c + dn_c, s_vec, g_vec, acc_s, acc_n);
@@ -415,7 +447,9 @@ day_kernel(const __grid_constant__ RepArray reps, uint32_t R, uint32_t P, uint32
             const uint32_t last = ((lane < 16 ? own.x : own.y) >> ((lane & 15u) * 2u)) & 3u;
             finish_slice<PER_AGENT>(r, slice, lane, true, cs, (uint32_t)(ds_h + ds_c), cn, (uint32_t)(dn_h + dn_c), stat, wsv, hv,
                                     last, uw, s_cong, s_cost, s_des, s_rec, weather, changed, parity, st);
+            }
             if (st.slices >= 1024) flush_warp_stats(r, lane, s_rec, st);
+            it0 = it1; it1 = it2; meta = meta1; meta1 = meta2;
         }
         flush_warp_stats(r, lane, s_rec, st);
         __syncthreads();

@@ -135,25 +135,13 @@ int build_graph_layout(const mvb_population& pop, uint32_t H, uint32_t capacity_
     L.hot_words = staged / 16;
 
     // ---- link codes ---------------------------------------------------------------------------
-    auto code_of = [&](uint32_t ext_target, bool& hot) -> uint32_t {
-        const uint32_t t = L.ext2int[ext_target];
-        const uint32_t hp = hot_pos[t];
-        hot = hp != kInvalid;
-        const uint32_t pos = hot ? hp : t;
-        return (pos >> 4) << 7 | (30u - 2u * (pos & 15u));
-    };
-    // one agent's four lists
-    std::vector<uint32_t> lh, lc;
-    uint32_t c_sh, c_nh, c_sc, c_nc;
-    auto build_lists = [&](uint32_t e) {
-        lh.clear(); lc.clear();
-        c_sh = c_nh = c_sc = c_nc = 0;
-        bool hot;
-        for (uint64_t x = srp[e]; x < srp[e + 1]; ++x) { const uint32_t c = code_of(pop.social_col[x], hot); if (hot) { lh.push_back(c); ++c_sh; } }
-        for (uint64_t x = nrp[e]; x < nrp[e + 1]; ++x) { const uint32_t c = code_of(pop.neighbour_col[x], hot); if (hot) { lh.push_back(c); ++c_nh; } }
-        for (uint64_t x = srp[e]; x < srp[e + 1]; ++x) { const uint32_t c = code_of(pop.social_col[x], hot); if (!hot) { lc.push_back(c); ++c_sc; } }
-        for (uint64_t x = nrp[e]; x < nrp[e + 1]; ++x) { const uint32_t c = code_of(pop.neighbour_col[x], hot); if (!hot) { lc.push_back(c); ++c_nc; } }
-    };
+    // code of every possible target, computed once
+    std::vector<uint32_t> tcode(N);
+    for (uint32_t e = 0; e < N; ++e) {
+        const uint32_t t = L.ext2int[e];
+        const uint32_t pos = is_hot[e] ? hot_pos[t] : t;
+        tcode[e] = (pos >> 4) << 7 | (30u - 2u * (pos & 15u));
+    }
     // write code number k of a lane's hot (or cold) chunk into a block of the k-major SELL format
     auto put_hot = [](uint32_t* blk, uint32_t K, uint32_t lane, uint32_t k, uint32_t code) {
         const uint32_t K4 = K / 4;
@@ -181,10 +169,15 @@ int build_graph_layout(const mvb_population& pop, uint32_t H, uint32_t capacity_
         }
     }
     L.hub_codes.assign(hoff + 256, 0);                   // + slack for the row prefetch
+    std::vector<uint32_t> lh, lc;
     for (uint32_t k = 0; k < hubs.size(); ++k) {
-        build_lists(hubs[k]);
+        const uint32_t e = hubs[k];
+        lh.clear(); lc.clear();
+        for (uint64_t x = srp[e]; x < srp[e + 1]; ++x) { const uint32_t t = pop.social_col[x]; (is_hot[t] ? lh : lc).push_back(tcode[t]); }
+        const uint32_t c_sh = (uint32_t)lh.size(), c_sc = (uint32_t)lc.size();
+        for (uint64_t x = nrp[e]; x < nrp[e + 1]; ++x) { const uint32_t t = pop.neighbour_col[x]; (is_hot[t] ? lh : lc).push_back(tcode[t]); }
         uint32_t* dg = &L.hub_deg[(size_t)4 * k];
-        dg[0] = c_sh; dg[1] = c_nh; dg[2] = c_sc; dg[3] = c_nc;
+        dg[0] = c_sh; dg[1] = (uint32_t)lh.size() - c_sh; dg[2] = c_sc; dg[3] = (uint32_t)lc.size() - c_sc;
         const uint32_t nh = (uint32_t)lh.size(), nc = (uint32_t)lc.size();
         uint32_t* blk = L.hub_codes.data() + L.hub_off[k];
         for (uint32_t dh = 0, dc = 0; dh < nh || dc < nc;) {
@@ -224,10 +217,17 @@ int build_graph_layout(const mvb_population& pop, uint32_t H, uint32_t capacity_
         for (uint32_t l = 0; l < 32; ++l) {
             const uint32_t e = L.int2ext[base + l];
             if (e == kInvalid) continue;
-            build_lists(e);
-            L.deg[base + l] = c_sh | c_nh << 8 | c_sc << 16 | c_nc << 24;
-            for (uint32_t k = 0; k < lh.size(); ++k) put_hot(blk, K, l, k, lh[k]);
-            for (uint32_t k = 0; k < lc.size(); ++k) put_cold(blk, K, l, k, lc[k]);
+            uint32_t kh = 0, kc = 0;
+            for (uint64_t x = srp[e]; x < srp[e + 1]; ++x) {
+                const uint32_t t = pop.social_col[x];
+                if (is_hot[t]) put_hot(blk, K, l, kh++, tcode[t]); else put_cold(blk, K, l, kc++, tcode[t]);
+            }
+            const uint32_t c_sh = kh, c_sc = kc;
+            for (uint64_t x = nrp[e]; x < nrp[e + 1]; ++x) {
+                const uint32_t t = pop.neighbour_col[x];
+                if (is_hot[t]) put_hot(blk, K, l, kh++, tcode[t]); else put_cold(blk, K, l, kc++, tcode[t]);
+            }
+            L.deg[base + l] = c_sh | (kh - c_sh) << 8 | c_sc << 16 | (kc - c_sc) << 24;
         }
     }
     // one 16-byte record per slice; 64 zero records of slack let the kernel prefetch past the end

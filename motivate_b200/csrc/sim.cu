@@ -5,6 +5,8 @@
 
 #include <algorithm>
 #include <numeric>
+#include <thread>
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
@@ -40,6 +42,7 @@ struct DevBuf {                       // owning device allocation
 struct Graph {
     GraphLayout L;                 // host copy: permutation, sizes (code arrays are released after upload)
     DevBuf deg, ranges, hub_off, hub_deg, hub_codes, sell_meta, sell_codes;
+    uint32_t n_hub_rows = 0;
     const void* key[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // caller pointers it was built from
 };
 
@@ -47,7 +50,7 @@ struct Replica {
     uint32_t N = 0, S = 0, H = 0;
     uint32_t rec_width = 0, rec_off = 0;
     std::shared_ptr<Graph> graph;
-    DevBuf stat, ws, habit, vec[2], normvec, pa, tables_f, tables_u, cong;
+    DevBuf stat, ws, habit, vec[2], normvec, pa, tables_f, tables_u, cong, hub_cnt;
     std::vector<uint32_t> h_stat;       // host mirror of the packed static words, internal order (ownership edits)
     bool per_agent = false;
 };
@@ -170,6 +173,18 @@ void unpack_slices(const std::vector<uint32_t>& int2ext, const std::vector<uint2
     }
 }
 
+// Run f(0..n-1) on up to hardware_concurrency host threads (setup only: validation, layout builds).
+template <class F>
+void parallel_for(uint32_t n, F f) {
+    const uint32_t nt = std::max(1u, std::min(n, std::thread::hardware_concurrency()));
+    if (nt <= 1) { for (uint32_t i = 0; i < n; ++i) f(i); return; }
+    std::atomic<uint32_t> next{0};
+    std::vector<std::thread> th;
+    for (uint32_t t = 0; t < nt; ++t)
+        th.emplace_back([&] { for (uint32_t i; (i = next.fetch_add(1)) < n;) f(i); });
+    for (auto& t : th) t.join();
+}
+
 int check_tables(const mvb_tables* t) {
     if (!t || !t->supportiveness || !t->capacity || !t->desirability || t->n_subcultures == 0 ||
         t->n_subcultures > 256 || t->n_neighbourhoods == 0 || t->n_neighbourhoods > 65536) {
@@ -250,8 +265,16 @@ int mvb_create_batch(uint32_t R, const mvb_population* const* pops, const mvb_ta
     for (uint32_t r = 0; r < R; ++r) {
         int rc = check_tables(tabs[r]);
         if (rc) return rc;
-        rc = validate_population(pops[r], tabs[r]);
-        if (rc) return rc;
+    }
+    {   // validate the populations on all host cores (each walks every link once)
+        std::vector<int> rcs(R, MVB_OK);
+        std::vector<std::string> msgs(R);
+        parallel_for(R, [&](uint32_t r) {
+            rcs[r] = validate_population(pops[r], tabs[r]);
+            if (rcs[r]) msgs[r] = mvb_last_error();
+        });
+        for (uint32_t r = 0; r < R; ++r)
+            if (rcs[r]) { set_error("replica %u: %s", r, msgs[r].c_str()); return rcs[r]; }
     }
     MVB_CUDA(cudaSetDevice(device));
     std::unique_ptr<mvb_sim, void (*)(mvb_sim*)> sp(new (std::nothrow) mvb_sim(), mvb_destroy);
@@ -291,7 +314,34 @@ int mvb_create_batch(uint32_t R, const mvb_population* const* pops, const mvb_ta
 
     s->reps.resize(R);
     s->h_reps.resize(R);
+    // distinct link graphs (replicas that pass the same graph + neighbourhood arrays share one), laid out in parallel
     std::vector<std::shared_ptr<Graph>> graphs;
+    std::vector<uint32_t> graph_of(R), first_rep;
+    for (uint32_t r = 0; r < R; ++r) {
+        const mvb_population* p = pops[r];
+        const void* key[5] = {p->social_rowptr, p->social_col, p->neighbour_rowptr, p->neighbour_col, p->neighbourhood};
+        uint32_t g = 0;
+        for (; g < graphs.size(); ++g)
+            if (pops[first_rep[g]]->n_agents == p->n_agents && !memcmp(graphs[g]->key, key, sizeof key) &&
+                tabs[first_rep[g]]->n_neighbourhoods == tabs[r]->n_neighbourhoods) break;
+        if (g == graphs.size()) {
+            graphs.push_back(std::make_shared<Graph>());
+            memcpy(graphs.back()->key, key, sizeof key);
+            first_rep.push_back(r);
+        }
+        graph_of[r] = g;
+    }
+    {
+        std::vector<int> rcs(graphs.size(), MVB_OK);
+        std::vector<std::string> msgs(graphs.size());
+        parallel_for((uint32_t)graphs.size(), [&](uint32_t g) {
+            rcs[g] = build_graph_layout(*pops[first_rep[g]], tabs[first_rep[g]]->n_neighbourhoods, capacity_agents, graphs[g]->L);
+            if (rcs[g]) msgs[g] = mvb_last_error();
+        });
+        for (size_t g = 0; g < graphs.size(); ++g)
+            if (rcs[g]) { set_error("%s", msgs[g].c_str()); return rcs[g]; }
+    }
+    std::vector<char> uploaded(graphs.size(), 0);
     for (uint32_t r = 0; r < R; ++r) {
         const mvb_population* p = pops[r];
         const mvb_tables* t = tabs[r];
@@ -301,16 +351,12 @@ int mvb_create_batch(uint32_t R, const mvb_population* const* pops, const mvb_ta
         rp.rec_width = rec_width(rp.S, rp.H);
         rp.rec_off = s->rec_stride;
         s->rec_stride += rp.rec_width;
-        // graph layout (shared when the caller passes the same graph and neighbourhood arrays)
-        const void* key[5] = {p->social_rowptr, p->social_col, p->neighbour_rowptr, p->neighbour_col, p->neighbourhood};
-        for (auto& g : graphs)
-            if (g->L.N == N && !memcmp(g->key, key, sizeof key)) rp.graph = g;
-        if (!rp.graph) {
-            auto g = std::make_shared<Graph>();
-            memcpy(g->key, key, sizeof key);
-            int rc = build_graph_layout(*p, rp.H, capacity_agents, g->L);
-            if (rc) return rc;
+        rp.graph = graphs[graph_of[r]];
+        if (!uploaded[graph_of[r]]) {
+            uploaded[graph_of[r]] = 1;
+            Graph* g = rp.graph.get();
             GraphLayout& L = g->L;
+            int rc;
             if ((rc = upload(g->deg, L.deg, s->stream)) || (rc = upload(g->ranges, L.ranges, s->stream)) ||
                 (rc = upload(g->hub_off, L.hub_off, s->stream)) || (rc = upload(g->hub_deg, L.hub_deg, s->stream)) ||
                 (rc = upload(g->hub_codes, L.hub_codes, s->stream)) ||
@@ -320,8 +366,7 @@ int mvb_create_batch(uint32_t R, const mvb_population* const* pops, const mvb_ta
             std::vector<uint32_t>().swap(L.hub_codes);           // the big arrays now live on the device only
             std::vector<uint32_t>().swap(L.sell_codes);
             std::vector<uint32_t>().swap(L.deg);
-            graphs.push_back(g);
-            rp.graph = g;
+            std::vector<uint4x>().swap(L.sell_meta);
         }
         const GraphLayout& L = rp.graph->L;
         const uint32_t NP = L.N_pad;
@@ -383,7 +428,8 @@ int mvb_create_batch(uint32_t R, const mvb_population* const* pops, const mvb_ta
         d.pa = rp.per_agent ? rp.pa.as<float>() : nullptr;
         d.vec[0] = rp.vec[0].as<uint2>(); d.vec[1] = rp.vec[1].as<uint2>(); d.normvec = rp.normvec.as<uint2>();
         d.deg = g.deg.as<uint32_t>(); d.ranges = g.ranges.as<StageRange>();
-        d.hub_off = g.hub_off.as<uint64_t>(); d.hub_deg = g.hub_deg.as<uint4>();
+        MVB_CUDA(rp.hub_cnt.alloc(sizeof(uint32_t) * 8 * 32 * (size_t)L.n_hub_slices));
+        d.hub_off = g.hub_off.as<uint64_t>(); d.hub_deg = g.hub_deg.as<uint4>(); d.hub_cnt = rp.hub_cnt.as<uint32_t>();
         d.hub_codes = g.hub_codes.as<uint32_t>();
         d.sell_meta = g.sell_meta.as<uint4>(); d.sell_codes = g.sell_codes.as<uint32_t>();
         d.supp = rp.tables_f.as<float>(); d.desir = rp.tables_f.as<float>() + 4 * rp.H;
