@@ -60,14 +60,14 @@ struct RepDev {                     // device-side descriptor of one replica
 
 __host__ __device__ inline uint32_t rec_width(uint32_t S, uint32_t H) { return 4 * H + 7 + S; }
 // words of shared memory a block needs besides the staged vector:
-// mbarrier(2) + work counter(2) + cong[H][4] + cost_base[H][3][4] + desir[S][4] + record
+// mbarrier(2) + work counter(2) + good-weather cost ranks[H][3] + cong[H][4] + cost_base[H][3][4] + desir[S][4] + record
 // The day kernel receives the replica descriptors BY VALUE (constant bank, uniform registers): up to
 // kMaxRepsPerLaunch per launch; more replicas take several launches per weekday.
 constexpr uint32_t kMaxRepsPerLaunch = 64;
 struct RepArray { RepDev r[kMaxRepsPerLaunch]; };
 static_assert(sizeof(RepArray) <= 24 * 1024, "kernel parameter space");
 __host__ __device__ inline uint32_t tail_words(uint32_t S, uint32_t H) {
-    return 4 + 4 * H + 12 * H + 4 * S + rec_width(S, H);
+    return 4 + 4 * H + 12 * H + 3 * H + 4 * S + rec_width(S, H);
 }
 
 // ---- small PTX helpers ----------------------------------------------------------------------
@@ -137,14 +137,19 @@ __device__ __forceinline__ uint32_t top_fields(int n) {      // mask of the low 
 
 // `bits` holds 16 gathered modes, link number base+e in field 15-e (the first link pushed ends up highest), of a
 // list whose first `ds` links are social and the following neighbour links, `d` in total (fields at or past d are
-// padding).  Adds the per-mode counts to the packed 8-bit accumulators.  count_in_subgroup's grouping, agent.rs:325-329.
+// padding).  Adds the counts of modes 1..3 to bits 8-31 of the packed 8-bit accumulators; the Car count (mode 0) is
+// what is left of the list length (car_counts).  count_in_subgroup's grouping, agent.rs:325-329.
 __device__ __forceinline__ void count_fields(uint32_t bits, int base, int ds, int d, uint32_t& acc_s, uint32_t& acc_n) {
     const uint32_t vmask = top_fields(min(max(d - base, 0), 16)), smask = top_fields(min(max(ds - base, 0), 16));
-    const uint32_t nmask = vmask & ~smask;
-    const uint32_t lo = bits & 0x55555555u, hi = (bits >> 1) & 0x55555555u;
-    const uint32_t m3 = hi & lo, m2 = hi & ~lo, m1 = ~hi & lo, m0 = ~(hi | lo);
-    acc_s += __popc(m0 & smask) | __popc(m1 & smask) << 8 | __popc(m2 & smask) << 16 | __popc(m3 & smask) << 24;
-    acc_n += __popc(m0 & nmask) | __popc(m1 & nmask) << 8 | __popc(m2 & nmask) << 16 | __popc(m3 & nmask) << 24;
+    const uint32_t lo = bits & vmask, hi = (bits >> 1) & vmask;          // padding fields drop out here
+    const uint32_t m3 = hi & lo, m2 = hi & ~lo, m1 = ~hi & lo;
+    const uint32_t s1 = __popc(m1 & smask), s2 = __popc(m2 & smask), s3 = __popc(m3 & smask);
+    acc_s += s1 << 8 | s2 << 16 | s3 << 24;
+    acc_n += (__popc(m1) - s1) << 8 | (__popc(m2) - s2) << 16 | (__popc(m3) - s3) << 24;
+}
+// Fill in the Car count of a list of n links whose other three counts sit in bits 8-31 of acc.
+__device__ __forceinline__ uint32_t car_counts(uint32_t acc, uint32_t n) {
+    return acc | (n - ((acc >> 8) & 0xFFu) - ((acc >> 16) & 0xFFu) - (acc >> 24));
 }
 
 // One lane's part of a block of link codes laid out k-major for the warp (layout.h): K hot codes per lane
@@ -199,27 +204,54 @@ __device__ __forceinline__ void accumulate_block(const uint32_t* __restrict__ bl
         count_fields(bits, (int)(q * 4), ds_h, d_h, acc_s, acc_n);
     }
     if (0 < d_c) {
-        const uint32_t inc = 1u << ((__funnelshift_l(0u, w0, c0) >> 30) * 8u);
+        const uint32_t inc = (1u << ((__funnelshift_l(0u, w0, c0) >> 30) * 8u)) & ~0xFFu;      // Car is derived, see count_fields
         if (0 < ds_c) acc_s += inc; else acc_n += inc;
     }
     if (1 < d_c) {
-        const uint32_t inc = 1u << ((__funnelshift_l(0u, w1, c1) >> 30) * 8u);
+        const uint32_t inc = (1u << ((__funnelshift_l(0u, w1, c1) >> 30) * 8u)) & ~0xFFu;
         if (1 < ds_c) acc_s += inc; else acc_n += inc;
     }
     for (uint32_t k = 2; k < Kc; ++k) {
         const uint32_t code = ld_stream_u32(cold + (size_t)k * 32);
         if ((int)k < d_c) {
-            const uint32_t inc = 1u << ((top2_cold(g_vec, code) >> 30) * 8u);
+            const uint32_t inc = (1u << ((top2_cold(g_vec, code) >> 30) * 8u)) & ~0xFFu;
             if ((int)k < ds_c) acc_s += inc; else acc_n += inc;
         }
     }
 }
 
-// ---- per-warp statistics -------------------------------------------------------------------------
-struct WarpStats {                  // 16-bit packed running sums (two u32 per class group), flushed per part
-    uint32_t joint_lo, joint_hi, commute_lo, commute_hi, sub_lo, sub_hi;
-    uint32_t slices;
+// Per-lane statistics of the agents a lane has finished since the last flush: four 8-bit counters per word.
+struct LaneStats {
+    uint32_t hist;      // by mode, for neighbourhood `nbhd` (SELL slices are neighbourhood-uniform)
+    uint32_t joint;     // by active*2 + active_norm     (statistics.rs:14-57)
+    uint32_t commute;   // active by commute length      (statistics.rs:62-70)
+    uint32_t sub;       // active by subculture, S <= 4  (statistics.rs:75-83)
+    uint32_t nbhd, n;   // neighbourhood of `hist`, agents counted since the last flush
 };
+__device__ __forceinline__ void flush_hist(uint32_t lane, uint32_t* s_rec, LaneStats& st) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t c = __reduce_add_sync(0xFFFFFFFFu, (st.hist >> (8 * k)) & 0xFFu);
+        if (lane == 0 && c) atomicAdd(&s_rec[4 * st.nbhd + k], c);
+    }
+    st.hist = 0;
+}
+__device__ __forceinline__ void flush_stats(uint32_t lane, uint32_t H, uint32_t S, uint32_t* s_rec, LaneStats& st) {
+    flush_hist(lane, s_rec, st);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t j = __reduce_add_sync(0xFFFFFFFFu, (st.joint >> (8 * k)) & 0xFFu);
+        const uint32_t c = __reduce_add_sync(0xFFFFFFFFu, (st.commute >> (8 * k)) & 0xFFu);
+        const uint32_t u = __reduce_add_sync(0xFFFFFFFFu, (st.sub >> (8 * k)) & 0xFFu);
+        if (lane == 0) {
+            if (j) atomicAdd(&s_rec[4 * H + k], j);
+            if (c && k < 3) atomicAdd(&s_rec[4 * H + 4 + k], c);
+            if (u && (uint32_t)k < S) atomicAdd(&s_rec[4 * H + 7 + k], u);
+        }
+    }
+    st.joint = st.commute = st.sub = 0;
+    st.n = 0;
+}
 
 // Everything that happens once the link counts of 32 agents (one per lane) are known.
 template <bool PER_AGENT>
@@ -227,8 +259,8 @@ __device__ __forceinline__ void finish_slice(const RepDev& r, uint32_t slice, ui
                                              const uint32_t cs[4], uint32_t ds, const uint32_t cn[4], uint32_t dn,
                                              uint32_t stat, float wsv, float4 hv, uint32_t last,
                                              const AgentWeights& uw, const float* s_cong, const float* s_cost,
-                                             const float* s_des, uint32_t* s_rec, uint32_t weather, uint32_t changed,
-                                             uint32_t parity, WarpStats& st) {
+                                             const uint32_t* s_crank, const float* s_des, uint32_t* s_rec,
+                                             uint32_t weather, uint32_t changed, uint32_t parity, LaneStats& st) {
     const uint32_t agent = slice * 32 + lane;
     const bool valid = (stat & kStatValid) != 0;
     AgentWeights w = uw;
@@ -241,9 +273,9 @@ __device__ __forceinline__ void finish_slice(const RepDev& r, uint32_t slice, ui
     float h[4] = {hv.x, hv.y, hv.z, hv.w};
     habit_update(h, last, w.average_weight);
     uint32_t mode, norm;
-    decide<!PER_AGENT>(cs, ds, cn, dn, w, h, s_des + 4 * st_sub(stat), s_cong + 4 * st_nbhd(stat),
-           s_cost + 12 * st_nbhd(stat) + 4 * st_commute(stat), st_commute(stat), st_car(stat), st_bike(stat), wsv,
-           last, weather, changed, mode, norm);
+    const uint32_t nb = st_nbhd(stat), cm = st_commute(stat);
+    decide<!PER_AGENT>(cs, ds, cn, dn, w, h, s_des + 4 * st_sub(stat), s_cong + 4 * nb, s_cost + 12 * nb + 4 * cm,
+                       s_crank[3 * nb + cm], cm, st_car(stat), st_bike(stat), wsv, last, weather, changed, mode, norm);
     if (!valid) { mode = 0; norm = 0; }
     if (valid) r.habit[agent] = make_float4(h[0], h[1], h[2], h[3]);
     // 32 agents x 2 bits -> one u64 (lanes 0-15 in .x, 16-31 in .y)
@@ -254,42 +286,20 @@ __device__ __forceinline__ void finish_slice(const RepDev& r, uint32_t slice, ui
     const uint32_t nhi = __reduce_or_sync(0xFFFFFFFFu, lane < 16 ? 0u : norm << sh);
     if (lane == 0) r.vec[parity ^ 1u][slice] = make_uint2(mlo, mhi);
     if (lane == 1) r.normvec[slice] = make_uint2(nlo, nhi);
-    // statistics (statistics.rs:14-93)
+    // statistics (statistics.rs:14-93): every lane counts its own agent; the warp adds its lanes up at a flush
     const uint32_t a = valid && mode >= 2u, an = valid && norm >= 2u;
     if (uniform_nbhd) {
-        const uint32_t hsum = __reduce_add_sync(0xFFFFFFFFu, valid ? 1u << (8u * mode) : 0u);   // 4 counts <= 32 each
-        const uint32_t nb = __shfl_sync(0xFFFFFFFFu, st_nbhd(stat), 0);   // lane 0 of a non-hub slice is always valid
-        if (lane < 4) {
-            const uint32_t c = (hsum >> (8u * lane)) & 0xFFu;
-            if (c) atomicAdd(&s_rec[4 * nb + lane], c);
-        }
+        const uint32_t nb0 = __shfl_sync(0xFFFFFFFFu, nb, 0);              // lane 0 of a non-hub slice is valid if any lane is
+        if (nb0 != st.nbhd) { flush_hist(lane, s_rec, st); st.nbhd = nb0; }
+        st.hist += valid ? 1u << (8u * mode) : 0u;
     } else if (valid) {
-        atomicAdd(&s_rec[4 * st_nbhd(stat) + mode], 1u);
+        atomicAdd(&s_rec[4 * nb + mode], 1u);
     }
-    const uint32_t jsum = __reduce_add_sync(0xFFFFFFFFu, valid ? 1u << (8u * (a * 2u + an)) : 0u);
-    const uint32_t csum = __reduce_add_sync(0xFFFFFFFFu, a ? 1u << (8u * st_commute(stat)) : 0u);
-    st.joint_lo += jsum & 0x00FF00FFu;   st.joint_hi += (jsum >> 8) & 0x00FF00FFu;
-    st.commute_lo += csum & 0x00FF00FFu; st.commute_hi += (csum >> 8) & 0x00FF00FFu;
-    if (r.S <= 4) {
-        const uint32_t ssum = __reduce_add_sync(0xFFFFFFFFu, a ? 1u << (8u * st_sub(stat)) : 0u);
-        st.sub_lo += ssum & 0x00FF00FFu; st.sub_hi += (ssum >> 8) & 0x00FF00FFu;
-    } else if (a) {
-        atomicAdd(&s_rec[4 * r.H + 7 + st_sub(stat)], 1u);
-    }
-    st.slices++;
-}
-
-__device__ __forceinline__ void flush_warp_stats(const RepDev& r, uint32_t lane, uint32_t* s_rec, WarpStats& st) {
-    // 16-bit fields: lo = classes 0,2 ; hi = classes 1,3
-    if (lane < 4) {
-        const uint32_t j = ((lane & 1u) ? st.joint_hi : st.joint_lo) >> (16u * (lane >> 1)) & 0xFFFFu;
-        if (j) atomicAdd(&s_rec[4 * r.H + lane], j);
-        const uint32_t c = ((lane & 1u) ? st.commute_hi : st.commute_lo) >> (16u * (lane >> 1)) & 0xFFFFu;
-        if (c && lane < 3) atomicAdd(&s_rec[4 * r.H + 4 + lane], c);
-        const uint32_t s = ((lane & 1u) ? st.sub_hi : st.sub_lo) >> (16u * (lane >> 1)) & 0xFFFFu;
-        if (s && r.S <= 4 && lane < r.S) atomicAdd(&s_rec[4 * r.H + 7 + lane], s);
-    }
-    st = WarpStats{0, 0, 0, 0, 0, 0, 0};
+    st.joint += valid ? 1u << (8u * (a * 2u + an)) : 0u;
+    st.commute += a << (8u * cm);
+    if (r.S <= 4) st.sub += a << (8u * st_sub(stat));
+    else if (a) atomicAdd(&s_rec[4 * r.H + 7 + st_sub(stat)], 1u);
+    if (++st.n == 255) flush_stats(lane, r.H, r.S, s_rec, st);
 }
 
 // ---- the weekday kernel ----------------------------------------------------------------------------
@@ -312,7 +322,8 @@ day_kernel(const __grid_constant__ RepArray reps, uint32_t R, uint32_t P, uint32
         const uint32_t p = part % P;
         const RepDev& r = reps.r[part / P];
         const uint32_t H = r.H, S = r.S;
-        float* s_cong = reinterpret_cast<float*>(s_tail + 4);
+        uint32_t* s_crank = s_tail + 4;                // [H][3] cost ranks on a Good-weather day
+        float* s_cong = reinterpret_cast<float*>(s_crank + 3 * H);
         __syncthreads();                              // previous part is done with shared memory
         float* s_cost = s_cong + 4 * H;
         float* s_des = s_cost + 12 * H;
@@ -340,13 +351,20 @@ day_kernel(const __grid_constant__ RepArray reps, uint32_t R, uint32_t P, uint32
             const uint32_t hh = k / 12, c = (k >> 2) % 3, m = k & 3;
             s_cost[k] = cost_base_entry(r.supp[4 * hh + m], c, m);
         }
+        for (uint32_t k = tid; k < 3 * H; k += THREADS) {                 // agent.rs:224-232 without a weather factor
+            const uint32_t hh = k / 3, c = k % 3;
+            float cc[4];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) cc[m] = cost_base_entry(r.supp[4 * hh + m], c, m);
+            if (c == 2u) { cc[2] = __int_as_float(0x7f800000); cc[3] = cc[2]; }
+            s_crank[k] = cost_ranks(cc);
+        }
         for (uint32_t k = tid; k < 4 * S; k += THREADS) s_des[k] = r.desir[k];
         for (uint32_t k = tid; k < rec_width(S, H); k += THREADS) s_rec[k] = 0;
         __syncthreads();
         mbar_wait(s_bar, phase);
         phase ^= 1u;
 
-        WarpStats st{0, 0, 0, 0, 0, 0, 0};
 
         // 2. hubs of this part's hub slices (p, p+P, ...): one warp per hub agent, the hub's lists cut into 32 chunks
         // (one per lane).  The 8 counts of a hub go to a small global scratch; the hub slices are finished below
@@ -368,15 +386,17 @@ day_kernel(const __grid_constant__ RepArray reps, uint32_t R, uint32_t P, uint32
                                  min(max((int)hd.z - oc, 0), (int)Kc), min(max((int)n_cold - oc, 0), (int)Kc),
                                  s_vec, g_vec, acc_s, acc_n);
 #pragma unroll
-                for (int m = 0; m < 4; ++m) { cs[m] += (acc_s >> (8 * m)) & 0xFFu; cn[m] += (acc_n >> (8 * m)) & 0xFFu; }
+                for (int m = 1; m < 4; ++m) { cs[m] += (acc_s >> (8 * m)) & 0xFFu; cn[m] += (acc_n >> (8 * m)) & 0xFFu; }
                 blk += (size_t)32 * (K + Kc);
                 done_h += 32u * K; done_c += 32u * Kc;
             }
 #pragma unroll
-            for (int m = 0; m < 4; ++m) {
+            for (int m = 1; m < 4; ++m) {
                 cs[m] = __reduce_add_sync(0xFFFFFFFFu, cs[m]);
                 cn[m] = __reduce_add_sync(0xFFFFFFFFu, cn[m]);
             }
+            cs[0] = hd.x + hd.z - cs[1] - cs[2] - cs[3];        // Car = what is left of the list (count_fields)
+            cn[0] = hd.y + hd.w - cn[1] - cn[2] - cn[3];
             if (lane < 8) {
                 const uint32_t v = lane == 0 ? cs[0] : lane == 1 ? cs[1] : lane == 2 ? cs[2] : lane == 3 ? cs[3]
                                  : lane == 4 ? cn[0] : lane == 5 ? cn[1] : lane == 6 ? cn[2] : cn[3];
@@ -400,6 +420,7 @@ day_kernel(const __grid_constant__ RepArray reps, uint32_t R, uint32_t P, uint32
             if (item < n_my_hub_slices || item >= n_items) return make_uint4(0, 0, 0, 0);
             return ld_stream_v4(r.sell_meta + (p + (uint64_t)P * (item - n_my_hub_slices)));
         };
+        LaneStats st{0, 0, 0, 0, 0, 0};
         uint32_t it0 = next_item(), it1 = next_item();
         uint4 meta = meta_of(it0), meta1 = meta_of(it1);
         while (it0 < n_items) {
@@ -424,7 +445,7 @@ day_kernel(const __grid_constant__ RepArray reps, uint32_t R, uint32_t P, uint32
                 const uint2 own = r.vec[parity][hs];
                 const uint32_t last = ((lane < 16 ? own.x : own.y) >> ((lane & 15u) * 2u)) & 3u;
                 finish_slice<PER_AGENT>(r, hs, lane, false, hcs, ad.x + ad.z, hcn, ad.y + ad.w, stat, r.ws[agent],
-                                        r.habit[agent], last, uw, s_cong, s_cost, s_des, s_rec, weather, changed, parity, st);
+                                        r.habit[agent], last, uw, s_cong, s_cost, s_crank, s_des, s_rec, weather, changed, parity, st);
             } else {
             const uint32_t s = p + P * (it0 - n_my_hub_slices);
             const uint32_t slice = r.n_hub_slices + s, agent = slice * 32 + lane;
@@ -441,17 +462,18 @@ day_kernel(const __grid_constant__ RepArray reps, uint32_t R, uint32_t P, uint32
             const int ds_h = (int)(dg & 0xFFu), dn_h = (int)((dg >> 8) & 0xFFu), ds_c = (int)((dg >> 16) & 0xFFu), dn_c = (int)(dg >> 24);
             uint32_t acc_s = 0, acc_n = 0;
             accumulate_block(blk, KK & 0xFFFFu, KK >> 16, lane, ds_h, ds_h + dn_h, ds_c, ds_c + dn_c, s_vec, g_vec, acc_s, acc_n);
+            acc_s = car_counts(acc_s, (uint32_t)(ds_h + ds_c));
+            acc_n = car_counts(acc_n, (uint32_t)(dn_h + dn_c));
             uint32_t cs[4], cn[4];
 #pragma unroll
             for (int m = 0; m < 4; ++m) { cs[m] = (acc_s >> (8 * m)) & 0xFFu; cn[m] = (acc_n >> (8 * m)) & 0xFFu; }
             const uint32_t last = ((lane < 16 ? own.x : own.y) >> ((lane & 15u) * 2u)) & 3u;
             finish_slice<PER_AGENT>(r, slice, lane, true, cs, (uint32_t)(ds_h + ds_c), cn, (uint32_t)(dn_h + dn_c), stat, wsv, hv,
-                                    last, uw, s_cong, s_cost, s_des, s_rec, weather, changed, parity, st);
+                                    last, uw, s_cong, s_cost, s_crank, s_des, s_rec, weather, changed, parity, st);
             }
-            if (st.slices >= 1024) flush_warp_stats(r, lane, s_rec, st);
             it0 = it1; it1 = it2; meta = meta1; meta1 = meta2;
         }
-        flush_warp_stats(r, lane, s_rec, st);
+        flush_stats(lane, H, S, s_rec, st);
         __syncthreads();
         for (uint32_t k = tid; k < rec_width(S, H); k += THREADS)
             if (s_rec[k]) atomicAdd(&rec_next[r.rec_off + k], s_rec[k]);
