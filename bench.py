@@ -274,7 +274,7 @@ def main():
         "dtype": "f32", "data": "synthetic", "config": workload_config(args),
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                     "traffic": profile_traffic(), "peak_source": peak_src,
+                     "traffic": profile_traffic(per) if args.agents == 1_000_000 else None, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes,
                      "kernel": "day kernel (one launch per weekday per rank), rank 0"},
         "clocks": clocks,
@@ -294,12 +294,13 @@ def main():
         dist.destroy_process_group()
 
 
-def profile_traffic():
-    """dram bytes per launch of the day kernel from the committed ncu capture, if one exists."""
+def profile_traffic(replicas_on_rank):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the day kernel, from the committed `ncu --set full`
+    capture (profiles/traffic.json holds it per replica of 1M agents; a launch steps `replicas_on_rank` of them)."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get("dram_bytes_per_launch")
+            return json.load(open(p))["dram_bytes_per_replica_launch"] * replicas_on_rank
         except Exception:
             return None
     return None
