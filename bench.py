@@ -33,7 +33,7 @@ UNIT = "agent-days/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100, help="timed weekdays")
+    ap.add_argument("--steps", type=int, default=521, help="timed weekdays (521 = the 2-year calendar of BASELINE config 3)")
     ap.add_argument("--warmup", type=int, default=5, help="untimed weekdays")
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--replicas", type=int, default=64, help="total replicas over all ranks (BASELINE config 3)")

@@ -1,0 +1,154 @@
+// fill_kernels.cuh — create-time kernels that write the link-code arrays of the day kernel's layout (layout.h)
+// in HBM, straight from the caller's two CSR graphs.  Setup only: they run once per distinct graph in
+// mvb_create_batch, so the 120 MB of link indices cross PCIe once, as they are, and the k-major re-encoding
+// (60 M random lookups per 1M-agent population) happens at HBM speed instead of on a host core.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "decide.cuh"
+#include "layout.h"
+
+namespace mvb {
+
+struct FillArgs {
+    const uint64_t* s_rowptr; const uint32_t* s_col;     // caller's social CSR (agent.social_network)
+    const uint64_t* n_rowptr; const uint32_t* n_col;     // caller's neighbour CSR (agent.neighbours)
+    const uint32_t* tcode;                               // [N] code of a target | 1 if hot
+    const uint32_t* int2ext;                             // [N_pad] internal slot -> caller's id or kInvalid
+    uint32_t n_hub_slices, n_sell_slices;
+    const uint4* sell_meta; uint32_t* sell_codes; uint32_t* deg;
+    const uint64_t* hub_off; const uint4* hub_deg; uint32_t* hub_codes;
+};
+
+__device__ __forceinline__ void put_hot(uint32_t* blk, uint32_t K, uint32_t lane, uint32_t k, uint32_t code) {
+    const uint32_t K4 = K >> 2;
+    if (k < 4 * K4) blk[(size_t)(k >> 2) * 128 + lane * 4 + (k & 3u)] = code;
+    else blk[(size_t)K4 * 128 + (size_t)(k - 4 * K4) * 32 + lane] = code;
+}
+__device__ __forceinline__ void put_cold(uint32_t* blk, uint32_t K, uint32_t lane, uint32_t k, uint32_t code) {
+    blk[(size_t)K * 32 + (size_t)k * 32 + lane] = code;
+}
+
+// One thread per agent of a SELL slice (lane = position in the slice): hot links first by list (social, then
+// neighbour), cold links likewise; also writes the agent's four list lengths.
+__global__ void fill_sell_kernel(FillArgs a) {
+    const uint32_t slot_in_sell = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t s = slot_in_sell >> 5, lane = slot_in_sell & 31u;
+    if (s >= a.n_sell_slices) return;
+    const uint32_t slot = (a.n_hub_slices + s) * 32 + lane;
+    const uint32_t e = a.int2ext[slot];
+    if (e == kInvalid) { a.deg[slot] = 0; return; }
+    const uint4 meta = a.sell_meta[s];
+    uint32_t* blk = a.sell_codes + (((uint64_t)meta.y << 32) | meta.x);
+    const uint32_t K = meta.z & 0xFFFFu;
+    uint32_t kh = 0, kc = 0;
+    for (uint64_t x = a.s_rowptr[e]; x < a.s_rowptr[e + 1]; ++x) {
+        const uint32_t c = a.tcode[a.s_col[x]];
+        if (c & 1u) put_hot(blk, K, lane, kh++, c & ~1u); else put_cold(blk, K, lane, kc++, c);
+    }
+    const uint32_t c_sh = kh, c_sc = kc;
+    for (uint64_t x = a.n_rowptr[e]; x < a.n_rowptr[e + 1]; ++x) {
+        const uint32_t c = a.tcode[a.n_col[x]];
+        if (c & 1u) put_hot(blk, K, lane, kh++, c & ~1u); else put_cold(blk, K, lane, kc++, c);
+    }
+    a.deg[slot] = c_sh | (kh - c_sh) << 8 | c_sc << 16 | (kc - c_sc) << 24;
+}
+
+// One warp per hub: the hub's hot (cold) list is the sequence of its hot (cold) links in list order; link number i
+// of the list goes to block `seg`, lane (i - start_of_seg) / K, position (i - start_of_seg) % K (hub_segment).
+// Lane l of the warp handles list positions by ballot-compaction, so the order of the lists is the link order.
+__global__ void fill_hub_kernel(FillArgs a, uint32_t n_hubs) {
+    const uint32_t hub = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    if (hub >= n_hubs) return;
+    const uint32_t e = a.int2ext[hub];
+    if (e == kInvalid) return;
+    const uint4 hd = a.hub_deg[hub];
+    const uint32_t n_hot = hd.x + hd.y, n_cold = hd.z + hd.w;
+    uint32_t* const base = a.hub_codes + a.hub_off[hub];
+    // walker over the hub's blocks for one list (hot or cold): position i -> (block pointer, K, Kc, offset in block)
+    struct Walker {
+        uint32_t* blk; uint32_t dh, dc, K, Kc, n_hot, n_cold;
+        __device__ void init(uint32_t* b, uint32_t nh, uint32_t nc) { blk = b; dh = dc = 0; n_hot = nh; n_cold = nc; hub_segment(nh, nc, K, Kc); }
+        __device__ void advance() {
+            blk += (size_t)32 * (K + Kc); dh += 32 * K; dc += 32 * Kc;
+            hub_segment(n_hot - min(dh, n_hot), n_cold - min(dc, n_cold), K, Kc);
+        }
+    };
+    for (int pass = 0; pass < 2; ++pass) {                 // 0: hot list, 1: cold list
+        Walker w; w.init(base, n_hot, n_cold);
+        uint32_t pos = 0;                                   // links of this list placed so far (warp-uniform)
+        for (int g = 0; g < 2; ++g) {                       // social links, then neighbour links
+            const uint64_t* rp = g ? a.n_rowptr : a.s_rowptr;
+            const uint32_t* cl = g ? a.n_col : a.s_col;
+            const uint64_t b = rp[e], end = rp[e + 1];
+            for (uint64_t x0 = b; x0 < end; x0 += 32) {
+                const uint64_t x = x0 + lane;
+                uint32_t c = 0; bool mine = false;
+                if (x < end) { c = a.tcode[cl[x]]; mine = ((c & 1u) != 0u) == (pass == 0); }
+                const uint32_t m = __ballot_sync(0xFFFFFFFFu, mine);
+                if (mine) {
+                    uint32_t i = pos + __popc(m & ((1u << lane) - 1u));
+                    Walker v = w;                            // private copy: this link may be a few blocks ahead
+                    while (i >= (pass == 0 ? v.dh + 32 * v.K : v.dc + 32 * v.Kc)) v.advance();
+                    const uint32_t local = i - (pass == 0 ? v.dh : v.dc), per = pass == 0 ? v.K : v.Kc;
+                    if (pass == 0) put_hot(v.blk, v.K, local / per, local % per, c & ~1u);
+                    else put_cold(v.blk, v.K, local / per, local % per, c);
+                }
+                pos += __popc(m);
+                while ((pass == 0 ? w.K : w.Kc) && pos >= (pass == 0 ? w.dh + 32 * w.K : w.dc + 32 * w.Kc) &&
+                       (w.dh + 32 * w.K < n_hot || w.dc + 32 * w.Kc < n_cold)) w.advance();
+            }
+        }
+    }
+}
+
+// Per-agent state of one replica from the caller's arrays (caller order) into internal slot order: packed static
+// word, weather sensitivity, habit, optional per-agent weights, and the 2-bit packed current_mode / norm vectors.
+struct InitArgs {
+    const uint32_t* int2ext; uint32_t N, N_pad;
+    const uint8_t* sub; const uint16_t* nbhd; const uint8_t* commute; const uint8_t* car; const uint8_t* bike;
+    const float* ws; const float4* habit; const uint8_t* mode; const uint8_t* norm;
+    const float* pa_src[5]; float pa_def[5];              // per-agent weights (nullptr = uniform default), agent.rs:44-57
+    uint32_t* stat; float* ws_out; float4* habit_out; float* pa_out;
+    uint2* vec0; uint2* vec1; uint2* normvec;
+};
+__global__ void init_state_kernel(InitArgs a) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31u;
+    if (i >= a.N_pad) return;                             // N_pad is a multiple of 64: whole warps
+    const uint32_t e = a.int2ext[i];
+    const bool valid = e != kInvalid;
+    uint32_t mode = 0, norm = 0;
+    if (valid) {
+        a.stat[i] = 0x80000000u | pack_static(a.nbhd[e], a.sub[e], a.commute[e], a.car[e] != 0, a.bike[e] != 0);
+        a.ws_out[i] = a.ws[e];
+        a.habit_out[i] = a.habit[e];
+        mode = a.mode[e] & 3u; norm = a.norm[e] & 3u;
+    } else {
+        a.stat[i] = 0; a.ws_out[i] = 0.f; a.habit_out[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (a.pa_out)
+        for (int k = 0; k < 5; ++k)
+            a.pa_out[(size_t)k * a.N_pad + i] = (valid && a.pa_src[k]) ? a.pa_src[k][e] : a.pa_def[k];
+    const uint32_t sh = (lane & 15u) * 2u;
+    const uint32_t mlo = __reduce_or_sync(0xFFFFFFFFu, lane < 16 ? mode << sh : 0u);
+    const uint32_t mhi = __reduce_or_sync(0xFFFFFFFFu, lane < 16 ? 0u : mode << sh);
+    const uint32_t nlo = __reduce_or_sync(0xFFFFFFFFu, lane < 16 ? norm << sh : 0u);
+    const uint32_t nhi = __reduce_or_sync(0xFFFFFFFFu, lane < 16 ? 0u : norm << sh);
+    if (lane == 0) { a.vec0[i >> 5] = make_uint2(mlo, mhi); a.vec1[i >> 5] = make_uint2(mlo, mhi); a.normvec[i >> 5] = make_uint2(nlo, nhi); }
+}
+
+// Ownership part of `intervene` (simulation.rs:383-463): rewrite the car / bike bits of the static words.
+__global__ void set_ownership_kernel(const uint32_t* int2ext, uint32_t N_pad, const uint8_t* car, const uint8_t* bike, uint32_t* stat) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N_pad) return;
+    const uint32_t e = int2ext[i];
+    if (e == kInvalid) return;
+    uint32_t w = stat[i];
+    if (car)  w = (w & ~(1u << 26)) | ((car[e] ? 1u : 0u) << 26);
+    if (bike) w = (w & ~(1u << 27)) | ((bike[e] ? 1u : 0u) << 27);
+    stat[i] = w;
+}
+
+}  // namespace mvb

@@ -135,22 +135,13 @@ int build_graph_layout(const mvb_population& pop, uint32_t H, uint32_t capacity_
     L.hot_words = staged / 16;
 
     // ---- link codes ---------------------------------------------------------------------------
-    // code of every possible target, computed once
-    std::vector<uint32_t> tcode(N);
+    // code of every possible target, computed once; the arrays of codes are filled on the device (fill_kernels.cuh)
+    L.tcode.resize(N);
     for (uint32_t e = 0; e < N; ++e) {
         const uint32_t t = L.ext2int[e];
         const uint32_t pos = is_hot[e] ? hot_pos[t] : t;
-        tcode[e] = (pos >> 4) << 7 | (30u - 2u * (pos & 15u));
+        L.tcode[e] = ((pos >> 4) << 7 | (30u - 2u * (pos & 15u))) | (is_hot[e] ? 1u : 0u);
     }
-    // write code number k of a lane's hot (or cold) chunk into a block of the k-major SELL format
-    auto put_hot = [](uint32_t* blk, uint32_t K, uint32_t lane, uint32_t k, uint32_t code) {
-        const uint32_t K4 = K / 4;
-        if (k < 4 * K4) blk[(size_t)(k / 4) * 128 + lane * 4 + (k & 3)] = code;
-        else blk[(size_t)K4 * 128 + (size_t)(k - 4 * K4) * 32 + lane] = code;
-    };
-    auto put_cold = [](uint32_t* blk, uint32_t K, uint32_t lane, uint32_t k, uint32_t code) {
-        blk[(size_t)K * 32 + (size_t)k * 32 + lane] = code;
-    };
     // hub blocks: lane l of a block holds links [l*K, (l+1)*K) of what is left of the list
     const uint32_t n_hub_rows = L.n_hub_slices * 32;
     L.hub_off.assign(n_hub_rows, 0);
@@ -160,6 +151,9 @@ int build_graph_layout(const mvb_population& pop, uint32_t H, uint32_t capacity_
         L.hub_off[k] = hoff;
         if (k >= hubs.size()) continue;
         const uint32_t e = hubs[k];
+        const uint32_t ds = (uint32_t)(srp[e + 1] - srp[e]), dn = (uint32_t)(nrp[e + 1] - nrp[e]);
+        uint32_t* dg = &L.hub_deg[(size_t)4 * k];
+        dg[0] = nsh[e]; dg[1] = nnh[e]; dg[2] = ds - nsh[e]; dg[3] = dn - nnh[e];
         const uint32_t nh = nsh[e] + nnh[e], nc = (uint32_t)d[e] - nh;
         for (uint32_t dh = 0, dc = 0; dh < nh || dc < nc;) {
             uint32_t K, Kc;
@@ -168,31 +162,8 @@ int build_graph_layout(const mvb_population& pop, uint32_t H, uint32_t capacity_
             dh += 32 * K; dc += 32 * Kc;
         }
     }
-    L.hub_codes.assign(hoff + 256, 0);                   // + slack for the row prefetch
-    std::vector<uint32_t> lh, lc;
-    for (uint32_t k = 0; k < hubs.size(); ++k) {
-        const uint32_t e = hubs[k];
-        lh.clear(); lc.clear();
-        for (uint64_t x = srp[e]; x < srp[e + 1]; ++x) { const uint32_t t = pop.social_col[x]; (is_hot[t] ? lh : lc).push_back(tcode[t]); }
-        const uint32_t c_sh = (uint32_t)lh.size(), c_sc = (uint32_t)lc.size();
-        for (uint64_t x = nrp[e]; x < nrp[e + 1]; ++x) { const uint32_t t = pop.neighbour_col[x]; (is_hot[t] ? lh : lc).push_back(tcode[t]); }
-        uint32_t* dg = &L.hub_deg[(size_t)4 * k];
-        dg[0] = c_sh; dg[1] = (uint32_t)lh.size() - c_sh; dg[2] = c_sc; dg[3] = (uint32_t)lc.size() - c_sc;
-        const uint32_t nh = (uint32_t)lh.size(), nc = (uint32_t)lc.size();
-        uint32_t* blk = L.hub_codes.data() + L.hub_off[k];
-        for (uint32_t dh = 0, dc = 0; dh < nh || dc < nc;) {
-            uint32_t K, Kc;
-            hub_segment(nh - std::min(dh, nh), nc - std::min(dc, nc), K, Kc);
-            for (uint32_t l = 0; l < 32; ++l) {
-                for (uint32_t j = 0; j < K && dh + l * K + j < nh; ++j) put_hot(blk, K, l, j, lh[dh + l * K + j]);
-                for (uint32_t j = 0; j < Kc && dc + l * Kc + j < nc; ++j) put_cold(blk, K, l, j, lc[dc + l * Kc + j]);
-            }
-            blk += (size_t)32 * (K + Kc);
-            dh += 32 * K; dc += 32 * Kc;
-        }
-    }
+    L.hub_codes_len = hoff + 256;                        // + slack for the row prefetch
     // SELL slices
-    L.deg.assign(L.N_pad, 0);
     L.sell_off.assign(L.n_sell_slices, 0);
     L.sell_K.assign(L.n_sell_slices, 0);
     uint64_t off = 0;
@@ -210,26 +181,7 @@ int build_graph_layout(const mvb_population& pop, uint32_t H, uint32_t capacity_
         L.sell_K[s] = K | Kc << 16;
         off += (uint64_t)32 * (K + Kc);
     }
-    L.sell_codes.assign(off + 256, 0);                   // + slack: the kernel's row prefetch may run 2 rows past a slice
-    for (uint32_t s = 0; s < L.n_sell_slices; ++s) {
-        const uint32_t base = hub_pad + s * 32, K = L.sell_K[s] & 0xFFFFu;
-        uint32_t* blk = L.sell_codes.data() + L.sell_off[s];
-        for (uint32_t l = 0; l < 32; ++l) {
-            const uint32_t e = L.int2ext[base + l];
-            if (e == kInvalid) continue;
-            uint32_t kh = 0, kc = 0;
-            for (uint64_t x = srp[e]; x < srp[e + 1]; ++x) {
-                const uint32_t t = pop.social_col[x];
-                if (is_hot[t]) put_hot(blk, K, l, kh++, tcode[t]); else put_cold(blk, K, l, kc++, tcode[t]);
-            }
-            const uint32_t c_sh = kh, c_sc = kc;
-            for (uint64_t x = nrp[e]; x < nrp[e + 1]; ++x) {
-                const uint32_t t = pop.neighbour_col[x];
-                if (is_hot[t]) put_hot(blk, K, l, kh++, tcode[t]); else put_cold(blk, K, l, kc++, tcode[t]);
-            }
-            L.deg[base + l] = c_sh | (kh - c_sh) << 8 | c_sc << 16 | (kc - c_sc) << 24;
-        }
-    }
+    L.sell_codes_len = off + 256;                        // + slack: the kernel's row prefetch may run 2 rows past a slice
     // one 16-byte record per slice; 64 zero records of slack let the kernel prefetch past the end
     L.sell_meta.assign((size_t)L.n_sell_slices + 64, uint4x{0, 0, 0, 0});
     for (uint32_t s = 0; s < L.n_sell_slices; ++s)

@@ -73,19 +73,22 @@ struct GraphLayout {
     uint64_t Es = 0, En = 0;       // link counts of the source graph
     std::vector<uint32_t> int2ext; // [N_pad] internal slot -> caller's agent id, kInvalid for padding
     std::vector<uint32_t> ext2int; // [N]
-    std::vector<uint32_t> deg;     // [N_pad] SELL agents: ds_hot | dn_hot<<8 | ds_cold<<16 | dn_cold<<24
+    std::vector<uint32_t> tcode;   // [N] link code of every possible target (caller's id) | 1 if the target is hot
+                                   // (the low bit is free: the shift field of a code is even); input of the fill kernels
     std::vector<StageRange> ranges;
     // hubs
     std::vector<uint64_t> hub_off;         // [n_hub_slices*32] offset of the hub's first block in hub_codes (u32 units)
     std::vector<uint32_t> hub_deg;         // [n_hub_slices*32][4] ds_hot, dn_hot, ds_cold, dn_cold
-    std::vector<uint32_t> hub_codes;
+    uint64_t hub_codes_len = 0;            // u32 entries of the device array hub_codes (incl. prefetch slack)
     // SELL
     std::vector<uint64_t> sell_off;        // [n_sell_slices] offset of the slice in sell_codes (u32 units)
     std::vector<uint32_t> sell_K;          // [n_sell_slices] K | Kc << 16
     std::vector<uint4x> sell_meta;         // [n_sell_slices + 64] {off_lo, off_hi, K | Kc << 16, 0}: what the kernel reads
-    std::vector<uint32_t> sell_codes;
+    uint64_t sell_codes_len = 0;           // u32 entries of the device array sell_codes (incl. prefetch slack)
 };
 
+// Host part of the layout: orders, sizes and offsets.  The link-code arrays themselves (hub_codes, sell_codes)
+// and the per-agent length words (deg) are written on the device by fill_kernels.cuh from the caller's CSR.
 // capacity_agents: how many agents of the mode vector fit in shared memory (multiple of 64, >= 64).
 // Returns MVB_OK or an error code (message via set_error).
 int build_graph_layout(const mvb_population& pop, uint32_t n_neighbourhoods, uint32_t capacity_agents,

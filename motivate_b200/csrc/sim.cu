@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "day_kernels.cuh"
+#include "fill_kernels.cuh"
 #include "layout.h"
 #include "mvb_internal.h"
 
@@ -41,8 +42,7 @@ struct DevBuf {                       // owning device allocation
 // (scenario sweeps over one population pass the same graph + neighbourhood arrays).
 struct Graph {
     GraphLayout L;                 // host copy: permutation, sizes (code arrays are released after upload)
-    DevBuf deg, ranges, hub_off, hub_deg, hub_codes, sell_meta, sell_codes;
-    uint32_t n_hub_rows = 0;
+    DevBuf deg, ranges, hub_off, hub_deg, hub_codes, sell_meta, sell_codes, int2ext;
     const void* key[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // caller pointers it was built from
 };
 
@@ -51,7 +51,6 @@ struct Replica {
     uint32_t rec_width = 0, rec_off = 0;
     std::shared_ptr<Graph> graph;
     DevBuf stat, ws, habit, vec[2], normvec, pa, tables_f, tables_u, cong, hub_cnt;
-    std::vector<uint32_t> h_stat;       // host mirror of the packed static words, internal order (ownership edits)
     bool per_agent = false;
 };
 
@@ -153,17 +152,7 @@ int upload(DevBuf& b, const std::vector<T>& v, cudaStream_t st) {
     return MVB_OK;
 }
 
-// 32 two-bit values -> the u64 of one slice (lanes 0-15 in .x, 16-31 in .y), as finish_slice packs them
-void pack_slices(const std::vector<uint32_t>& int2ext, const uint8_t* values, std::vector<uint2>& out) {
-    out.assign(int2ext.size() / 32, make_uint2(0, 0));
-    for (size_t i = 0; i < int2ext.size(); ++i) {
-        if (int2ext[i] == kInvalid) continue;
-        const uint32_t v = values[int2ext[i]] & 3u, l = (uint32_t)(i & 31);
-        uint2& w = out[i >> 5];
-        (l < 16 ? w.x : w.y) |= v << ((l & 15u) * 2u);
-    }
-}
-
+// the u64 of one slice (lanes 0-15 in .x, 16-31 in .y, as finish_slice packs them) -> 32 two-bit values
 void unpack_slices(const std::vector<uint32_t>& int2ext, const std::vector<uint2>& in, uint8_t* values) {
     for (size_t i = 0; i < int2ext.size(); ++i) {
         if (int2ext[i] == kInvalid) continue;
@@ -357,61 +346,89 @@ int mvb_create_batch(uint32_t R, const mvb_population* const* pops, const mvb_ta
             Graph* g = rp.graph.get();
             GraphLayout& L = g->L;
             int rc;
-            if ((rc = upload(g->deg, L.deg, s->stream)) || (rc = upload(g->ranges, L.ranges, s->stream)) ||
-                (rc = upload(g->hub_off, L.hub_off, s->stream)) || (rc = upload(g->hub_deg, L.hub_deg, s->stream)) ||
-                (rc = upload(g->hub_codes, L.hub_codes, s->stream)) ||
-                (rc = upload(g->sell_meta, L.sell_meta, s->stream)) || (rc = upload(g->sell_codes, L.sell_codes, s->stream)))
+            if ((rc = upload(g->ranges, L.ranges, s->stream)) || (rc = upload(g->hub_off, L.hub_off, s->stream)) ||
+                (rc = upload(g->hub_deg, L.hub_deg, s->stream)) || (rc = upload(g->sell_meta, L.sell_meta, s->stream)))
                 return rc;
-            MVB_CUDA(cudaStreamSynchronize(s->stream));
-            std::vector<uint32_t>().swap(L.hub_codes);           // the big arrays now live on the device only
-            std::vector<uint32_t>().swap(L.sell_codes);
-            std::vector<uint32_t>().swap(L.deg);
+            MVB_CUDA(g->deg.alloc(sizeof(uint32_t) * (size_t)L.N_pad));
+            MVB_CUDA(g->hub_codes.alloc(sizeof(uint32_t) * L.hub_codes_len));
+            MVB_CUDA(g->sell_codes.alloc(sizeof(uint32_t) * L.sell_codes_len));
+            MVB_CUDA(cudaMemsetAsync(g->hub_codes.p, 0, g->hub_codes.bytes, s->stream));      // padding = code 0
+            MVB_CUDA(cudaMemsetAsync(g->sell_codes.p, 0, g->sell_codes.bytes, s->stream));
+            // the caller's CSR goes to the device as it is; the fill kernels re-encode it there, then it is dropped
+            DevBuf t_srp, t_scol, t_nrp, t_ncol, t_tcode;
+            const size_t nb_rp = 8 * ((size_t)N + 1);
+            MVB_CUDA(t_srp.alloc(nb_rp)); MVB_CUDA(t_nrp.alloc(nb_rp));
+            MVB_CUDA(t_scol.alloc(4 * L.Es)); MVB_CUDA(t_ncol.alloc(4 * L.En));
+            MVB_CUDA(cudaMemcpyAsync(t_srp.p, p->social_rowptr, nb_rp, cudaMemcpyHostToDevice, s->stream));
+            MVB_CUDA(cudaMemcpyAsync(t_nrp.p, p->neighbour_rowptr, nb_rp, cudaMemcpyHostToDevice, s->stream));
+            if (L.Es) MVB_CUDA(cudaMemcpyAsync(t_scol.p, p->social_col, 4 * L.Es, cudaMemcpyHostToDevice, s->stream));
+            if (L.En) MVB_CUDA(cudaMemcpyAsync(t_ncol.p, p->neighbour_col, 4 * L.En, cudaMemcpyHostToDevice, s->stream));
+            if ((rc = upload(t_tcode, L.tcode, s->stream)) || (rc = upload(g->int2ext, L.int2ext, s->stream))) return rc;
+            FillArgs fa{t_srp.as<uint64_t>(), t_scol.as<uint32_t>(), t_nrp.as<uint64_t>(), t_ncol.as<uint32_t>(),
+                        t_tcode.as<uint32_t>(), g->int2ext.as<uint32_t>(), L.n_hub_slices, L.n_sell_slices,
+                        g->sell_meta.as<uint4>(), g->sell_codes.as<uint32_t>(), g->deg.as<uint32_t>(),
+                        g->hub_off.as<uint64_t>(), g->hub_deg.as<uint4>(), g->hub_codes.as<uint32_t>()};
+            MVB_CUDA(cudaMemsetAsync(g->deg.p, 0, g->deg.bytes, s->stream));
+            if (L.n_sell_slices) {
+                fill_sell_kernel<<<(L.n_sell_slices * 32 + 255) / 256, 256, 0, s->stream>>>(fa);
+                MVB_CUDA(cudaGetLastError());
+            }
+            if (L.n_hub_slices) {
+                fill_hub_kernel<<<(L.n_hub_slices * 32 * 32 + 255) / 256, 256, 0, s->stream>>>(fa, L.n_hub_slices * 32);
+                MVB_CUDA(cudaGetLastError());
+            }
+            MVB_CUDA(cudaStreamSynchronize(s->stream));          // temporaries are freed when they go out of scope
+            std::vector<uint32_t>().swap(L.tcode);
             std::vector<uint4x>().swap(L.sell_meta);
         }
         const GraphLayout& L = rp.graph->L;
         const uint32_t NP = L.N_pad;
         s->max_npad = std::max(s->max_npad, NP);
-        // per-agent state in internal order
-        rp.h_stat.assign(NP, 0u);
-        std::vector<float> ws(NP, 0.f), habit((size_t)4 * NP, 0.f);
-        for (uint32_t i = 0; i < NP; ++i) {
-            const uint32_t e = L.int2ext[i];
-            if (e == kInvalid) continue;
-            rp.h_stat[i] = kStatValid | pack_static(p->neighbourhood[e], p->subculture[e], p->commute[e],
-                                                    p->owns_car[e] != 0, p->owns_bike[e] != 0);
-            ws[i] = p->weather_sensitivity[e];
-            memcpy(&habit[(size_t)4 * i], p->habit + (size_t)4 * e, 16);
-        }
-        std::vector<uint2> mv, nv;
-        pack_slices(L.int2ext, p->current_mode, mv);
-        pack_slices(L.int2ext, p->norm, nv);
-        int rc;
-        if ((rc = upload(rp.stat, rp.h_stat, s->stream)) || (rc = upload(rp.ws, ws, s->stream)) ||
-            (rc = upload(rp.habit, habit, s->stream)) || (rc = upload(rp.vec[0], mv, s->stream)) ||
-            (rc = upload(rp.vec[1], mv, s->stream)) || (rc = upload(rp.normvec, nv, s->stream)))
-            return rc;
+        // per-agent state: the caller's arrays go up as they are, a kernel permutes them into internal slot order
         const float* pa_src[5] = {p->consistency, p->social_connectivity, p->subculture_connectivity,
                                   p->neighbourhood_connectivity, p->average_weight};
         const float pa_def[5] = {prm->consistency, prm->social_connectivity, prm->subculture_connectivity,
                                  prm->neighbourhood_connectivity, prm->average_weight};
         rp.per_agent = false;
         for (int k = 0; k < 5; ++k) rp.per_agent |= (pa_src[k] != nullptr);
-        std::vector<float> pa;
-        if (rp.per_agent) {
-            s->any_per_agent = true;
-            pa.assign((size_t)5 * NP, 0.f);
-            for (int k = 0; k < 5; ++k)
-                for (uint32_t i = 0; i < NP; ++i) {
-                    const uint32_t e = L.int2ext[i];
-                    pa[(size_t)k * NP + i] = e == kInvalid ? pa_def[k] : (pa_src[k] ? pa_src[k][e] : pa_def[k]);
-                }
-            if ((rc = upload(rp.pa, pa, s->stream))) return rc;
+        if (rp.per_agent) s->any_per_agent = true;
+        {
+            MVB_CUDA(rp.stat.alloc(4 * (size_t)NP)); MVB_CUDA(rp.ws.alloc(4 * (size_t)NP)); MVB_CUDA(rp.habit.alloc(16 * (size_t)NP));
+            MVB_CUDA(rp.vec[0].alloc(NP / 4)); MVB_CUDA(rp.vec[1].alloc(NP / 4)); MVB_CUDA(rp.normvec.alloc(NP / 4));
+            if (rp.per_agent) MVB_CUDA(rp.pa.alloc(20 * (size_t)NP));
+            DevBuf t[14];
+            auto up = [&](DevBuf& b, const void* src, size_t bytes) -> int {
+                MVB_CUDA(b.alloc(bytes));
+                MVB_CUDA(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, s->stream));
+                return MVB_OK;
+            };
+            int rc;
+            if ((rc = up(t[0], p->subculture, N)) || (rc = up(t[1], p->neighbourhood, 2 * (size_t)N)) ||
+                (rc = up(t[2], p->commute, N)) || (rc = up(t[3], p->owns_car, N)) || (rc = up(t[4], p->owns_bike, N)) ||
+                (rc = up(t[5], p->weather_sensitivity, 4 * (size_t)N)) || (rc = up(t[6], p->habit, 16 * (size_t)N)) ||
+                (rc = up(t[7], p->current_mode, N)) || (rc = up(t[8], p->norm, N)))
+                return rc;
+            InitArgs ia{};
+            ia.int2ext = rp.graph->int2ext.as<uint32_t>(); ia.N = N; ia.N_pad = NP;
+            ia.sub = t[0].as<uint8_t>(); ia.nbhd = t[1].as<uint16_t>(); ia.commute = t[2].as<uint8_t>();
+            ia.car = t[3].as<uint8_t>(); ia.bike = t[4].as<uint8_t>(); ia.ws = t[5].as<float>();
+            ia.habit = t[6].as<float4>(); ia.mode = t[7].as<uint8_t>(); ia.norm = t[8].as<uint8_t>();
+            for (int k = 0; k < 5; ++k) {
+                ia.pa_src[k] = nullptr; ia.pa_def[k] = pa_def[k];
+                if (rp.per_agent && pa_src[k]) { if ((rc = up(t[9 + k], pa_src[k], 4 * (size_t)N))) return rc; ia.pa_src[k] = t[9 + k].as<float>(); }
+            }
+            ia.stat = rp.stat.as<uint32_t>(); ia.ws_out = rp.ws.as<float>(); ia.habit_out = rp.habit.as<float4>();
+            ia.pa_out = rp.per_agent ? rp.pa.as<float>() : nullptr;
+            ia.vec0 = rp.vec[0].as<uint2>(); ia.vec1 = rp.vec[1].as<uint2>(); ia.normvec = rp.normvec.as<uint2>();
+            init_state_kernel<<<(NP + 255) / 256, 256, 0, s->stream>>>(ia);
+            MVB_CUDA(cudaGetLastError());
+            MVB_CUDA(cudaStreamSynchronize(s->stream));          // temporaries are freed on scope exit
         }
         // tables + residents
         MVB_CUDA(rp.tables_f.alloc(sizeof(float) * 4 * (rp.H + rp.S)));
         MVB_CUDA(rp.tables_u.alloc(sizeof(uint32_t) * 5 * rp.H));
         MVB_CUDA(rp.cong.alloc(sizeof(float) * 4 * rp.H));
-        if ((rc = upload_tables(s, rp, t))) return rc;
+        if (int rc = upload_tables(s, rp, t)) return rc;
         std::vector<uint32_t> nres(rp.H, 0);
         for (uint32_t i = 0; i < N; ++i) nres[p->neighbourhood[i]]++;
         MVB_CUDA(cudaMemcpyAsync(rp.tables_u.as<uint32_t>() + 4 * rp.H, nres.data(), 4 * rp.H, cudaMemcpyHostToDevice, s->stream));
@@ -502,18 +519,16 @@ int mvb_set_ownership(mvb_sim* s, uint32_t r, const uint8_t* car, const uint8_t*
     if (!s || r >= s->reps.size()) { set_error("bad handle/replica"); return MVB_ERR_ARG; }
     if (!car && !bike) return MVB_OK;
     Replica& rp = s->reps[r];
-    const std::vector<uint32_t>& int2ext = rp.graph->L.int2ext;
-    for (size_t i = 0; i < int2ext.size(); ++i) {
-        const uint32_t e = int2ext[i];
-        if (e == kInvalid) continue;
-        uint32_t w = rp.h_stat[i];
-        if (car)  w = (w & ~(1u << 26)) | ((car[e] ? 1u : 0u) << 26);
-        if (bike) w = (w & ~(1u << 27)) | ((bike[e] ? 1u : 0u) << 27);
-        rp.h_stat[i] = w;
-    }
+    const uint32_t NP = rp.graph->L.N_pad;
     MVB_CUDA(cudaSetDevice(s->device));
-    MVB_CUDA(cudaMemcpyAsync(rp.stat.p, rp.h_stat.data(), 4 * rp.h_stat.size(), cudaMemcpyHostToDevice, s->stream));
-    MVB_CUDA(cudaStreamSynchronize(s->stream));   // h_stat may be edited again right after return
+    DevBuf tc, tb;
+    if (car)  { MVB_CUDA(tc.alloc(rp.N)); MVB_CUDA(cudaMemcpyAsync(tc.p, car, rp.N, cudaMemcpyHostToDevice, s->stream)); }
+    if (bike) { MVB_CUDA(tb.alloc(rp.N)); MVB_CUDA(cudaMemcpyAsync(tb.p, bike, rp.N, cudaMemcpyHostToDevice, s->stream)); }
+    set_ownership_kernel<<<(NP + 255) / 256, 256, 0, s->stream>>>(rp.graph->int2ext.as<uint32_t>(), NP,
+                                                                  car ? tc.as<uint8_t>() : nullptr, bike ? tb.as<uint8_t>() : nullptr,
+                                                                  rp.stat.as<uint32_t>());
+    MVB_CUDA(cudaGetLastError());
+    MVB_CUDA(cudaStreamSynchronize(s->stream));   // the caller's buffers and the temporaries are released on return
     return MVB_OK;
 }
 
