@@ -49,7 +49,7 @@ extern "C" {
 #define MVB_ERR_NOMEM    -3   /* host or device allocation failed                            */
 #define MVB_ERR_STATE    -4   /* call not valid in this state                                */
 #define MVB_ERR_DOMAIN   -5   /* input violates a precondition of the reference (see below)  */
-#define MVB_ERR_COMM     -6   /* communicator (NCCL) failure in partitioned mode             */
+#define MVB_ERR_COMM     -6   /* communicator (NCCL) failure, or NCCL not loadable, in partitioned mode */
 
 #define MVB_N_MODES       4
 #define MVB_N_COMMUTES    3
@@ -218,6 +218,27 @@ int  mvb_get_state(mvb_sim* sim, uint32_t replica, float* habit, uint8_t* curren
  * by the definition of SURVEY.md §8(d): sum over agents of
  * 4*(d_s+d_n) + 51.  Used by bench.py for the roofline. */
 uint64_t mvb_algorithmic_bytes_per_day(const mvb_sim* sim, uint32_t replica);
+
+/* ---- one population partitioned over the GPUs of a box ---------------------------------------
+ * BASELINE config 4 / SURVEY.md §8e: the reference cannot do this (one replica is single-threaded,
+ * src/simulation.rs:64); it is the "number_of_people" axis scaled over GPUs.  One process per GPU.  Every rank
+ * passes the SAME population and tables; the library cuts the agents into `world` contiguous ranges of its internal
+ * order, balanced by link count, and each rank updates its own agents.  After every weekday the ranks exchange, over
+ * NCCL, the packed 2-bit current_mode / norm words they own (the social network is global, src/simulation.rs:160:
+ * tomorrow every rank needs every agent's mode) and all-reduce the day's counters (hist + statistics).  Afterwards
+ * every rank holds the full mode / norm vectors and identical statistics rows; habits are current only for the agents
+ * a rank owns (mvb_partition_owner).  All other entry points (mvb_step, mvb_run, mvb_set_*, mvb_get_state, ...) work
+ * as for a one-replica handle and must be called by all ranks in the same order. */
+#define MVB_UNIQUE_ID_BYTES 128
+/* Rank 0 calls this and hands the 128 bytes to the other ranks (file, socket, torch.distributed broadcast ...). */
+int  mvb_comm_unique_id(void* id_out);
+int  mvb_create_partitioned(const mvb_population* pop, const mvb_tables* tab, const mvb_params* prm,
+                            int device, uint32_t rank, uint32_t world, const void* unique_id, mvb_sim** out);
+/* rank_out[N]: which rank updates each agent (caller's agent order).  Host-only overload below needs no device. */
+int  mvb_partition_owner(const mvb_sim* sim, uint32_t* rank_out);
+/* The same plan without creating anything (no device needed): how `world` ranks would split this population. */
+int  mvb_partition_plan(const mvb_population* pop, uint32_t n_subcultures, uint32_t n_neighbourhoods,
+                        uint32_t world, uint32_t* rank_out);
 
 /* ---- synthetic populations (host-side utility, seeded, no device needed) --- */
 

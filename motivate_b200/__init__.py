@@ -6,7 +6,7 @@ This package is the thin ctypes face of that ABI used by the tests and bench; im
 """
 from .api import (BAD, CAR, CITY_COMMUTE, CYCLE, DEFAULT_GMM, DISTANT_COMMUTE, GOOD, LOCAL_COMMUTE,
                   PUBLIC_TRANSPORT, STATS_FIXED, WALK, InterventionData, MotivateError, PopulationData,
-                  Simulation, TablesData, make_params, params_dict, run_rows, synth_population,
+                  Simulation, TablesData, comm_unique_id, make_params, partition_plan, params_dict, run_rows, synth_population,
                   synth_tables, weather_pattern)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -78,6 +78,10 @@ SIGNATURES = {
     "mvb_stats_row": (C.c_int, [SimP, C.c_uint32, u32p]),
     "mvb_get_state": (C.c_int, [SimP, C.c_uint32, f32p, u8p, u8p, u8p, u32p, f32p]),
     "mvb_algorithmic_bytes_per_day": (C.c_uint64, [SimP, C.c_uint32]),
+    "mvb_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "mvb_create_partitioned": (C.c_int, [PopP, TabP, PrmP, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(SimP)]),
+    "mvb_partition_owner": (C.c_int, [SimP, u32p]),
+    "mvb_partition_plan": (C.c_int, [PopP, C.c_uint32, C.c_uint32, C.c_uint32, u32p]),
     "mvb_synth_create": (C.c_int, [C.POINTER(SynthSpec), C.POINTER(C.c_void_p)]),
     "mvb_synth_destroy": (None, [C.c_void_p]),
     "mvb_synth_population": (PopP, [C.c_void_p]),

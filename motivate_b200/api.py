@@ -253,6 +253,20 @@ def run_rows(n_days):
     return 1 + sum(1 for d in range(1, n_days) if d % 7 < 5)
 
 
+def comm_unique_id() -> bytes:
+    """128-byte NCCL id for the agent-partitioned mode: rank 0 makes it, every rank passes it to Simulation.partitioned."""
+    buf = C.create_string_buffer(128)
+    _check(_ffi.load().mvb_comm_unique_id(buf))
+    return buf.raw
+
+
+def partition_plan(pop: PopulationData, n_subcultures: int, n_neighbourhoods: int, world: int) -> np.ndarray:
+    """Which rank would update each agent if `world` B200s shared this population (no device needed)."""
+    out = np.zeros(pop.n_agents, np.uint32)
+    _check(_ffi.load().mvb_partition_plan(C.byref(pop.struct()), n_subcultures, n_neighbourhoods, world, _ptr(out, _ffi.u32p)))
+    return out
+
+
 class Simulation:
     """R replicas resident on one B200 (mvb_sim).  `pops`/`tabs` are sequences (or single objects)."""
 
@@ -273,6 +287,26 @@ class Simulation:
         _check(self._lib.mvb_create_batch(R, pp, tp, C.byref(self.params), device, C.byref(self._h)))
         self.n_replicas = R
         self.widths = [int(self._lib.mvb_stats_width(self._h, r)) for r in range(R)]
+
+    @classmethod
+    def partitioned(cls, pop: PopulationData, tab: TablesData, params, device: int, rank: int, world: int, unique_id: bytes):
+        """One population shared by `world` GPUs (mvb_create_partitioned): one process per GPU, same inputs on every rank."""
+        self = cls.__new__(cls)
+        self._lib = _ffi.load()
+        self.pops, self.tabs = [pop], [tab]
+        self.params = params if params is not None else make_params()
+        self._h = _ffi.SimP()
+        idbuf = C.create_string_buffer(unique_id, 128) if unique_id is not None else None
+        _check(self._lib.mvb_create_partitioned(C.byref(pop.struct()), C.byref(tab.struct()), C.byref(self.params), device,
+                                                rank, world, idbuf, C.byref(self._h)))
+        self.n_replicas = 1
+        self.widths = [int(self._lib.mvb_stats_width(self._h, 0))]
+        return self
+
+    def partition_owner(self):
+        out = np.zeros(self.pops[0].n_agents, np.uint32)
+        _check(self._lib.mvb_partition_owner(self._h, _ptr(out, _ffi.u32p)))
+        return out
 
     def close(self):
         if getattr(self, "_h", None):

@@ -42,6 +42,7 @@ constexpr uint32_t kStatValid = 0x80000000u;        // bit 31 of the packed stat
 struct RepDev {                     // device-side descriptor of one replica
     uint32_t N, N_pad, S, H, rec_off;
     uint32_t n_hub_slices, n_sell_slices, n_ranges, hot_words;
+    uint32_t hub_begin, hub_end, sell_begin, sell_end;   // slices this rank updates (everything unless agent-partitioned)
     const uint32_t* stat;           // [N_pad] packed static word (decide.cuh) | kStatValid
     const float* ws;                // [N_pad] weather_sensitivity
     float4* habit;                  // [N_pad] dense habit, updated in place
@@ -369,9 +370,10 @@ day_kernel(const __grid_constant__ RepArray reps, uint32_t R, uint32_t P, uint32
         // 2. hubs of this part's hub slices (p, p+P, ...): one warp per hub agent, the hub's lists cut into 32 chunks
         // (one per lane).  The 8 counts of a hub go to a small global scratch; the hub slices are finished below
         // like any other slice, so no warp waits for another here.
-        const uint32_t n_my_hub_slices = r.n_hub_slices > p ? (r.n_hub_slices - p + P - 1) / P : 0;
+        const uint32_t n_own_hub = r.hub_end - r.hub_begin;
+        const uint32_t n_my_hub_slices = n_own_hub > p ? (n_own_hub - p + P - 1) / P : 0;
         for (uint32_t j = warp; j < n_my_hub_slices * 32; j += THREADS / 32) {
-            const uint32_t hub = (p + P * (j >> 5)) * 32 + (j & 31u);
+            const uint32_t hub = (r.hub_begin + p + P * (j >> 5)) * 32 + (j & 31u);
             const uint4 hd = ld_stream_v4(reinterpret_cast<const uint4*>(r.hub_deg) + hub);   // ds_hot, dn_hot, ds_cold, dn_cold
             const uint32_t n_hot = hd.x + hd.y, n_cold = hd.z + hd.w;
             uint32_t cs[4] = {0, 0, 0, 0}, cn[4] = {0, 0, 0, 0};
@@ -408,7 +410,7 @@ day_kernel(const __grid_constant__ RepArray reps, uint32_t R, uint32_t P, uint32
         // 3. work items handed out by a block-wide counter: first this part's hub slices (finish only), then its
         // SELL slices p + P*k: one lane per agent.  The slice record is read two items ahead, and the next slice is
         // pulled into L2 (its link codes and its agents' state) by TMA prefetches while this one is processed.
-        const uint32_t n_sell = r.n_sell_slices;
+        const uint32_t n_sell = r.sell_end - r.sell_begin;
         const uint32_t n_my_sell = n_sell > p ? (n_sell - p + P - 1) / P : 0;
         const uint32_t n_items = n_my_hub_slices + n_my_sell;
         auto next_item = [&]() -> uint32_t {
@@ -418,7 +420,7 @@ day_kernel(const __grid_constant__ RepArray reps, uint32_t R, uint32_t P, uint32
         };
         auto meta_of = [&](uint32_t item) -> uint4 {   // SELL items only; zero for hub items / past the end
             if (item < n_my_hub_slices || item >= n_items) return make_uint4(0, 0, 0, 0);
-            return ld_stream_v4(r.sell_meta + (p + (uint64_t)P * (item - n_my_hub_slices)));
+            return ld_stream_v4(r.sell_meta + (r.sell_begin + p + (uint64_t)P * (item - n_my_hub_slices)));
         };
         LaneStats st{0, 0, 0, 0, 0, 0};
         uint32_t it0 = next_item(), it1 = next_item();
@@ -427,7 +429,7 @@ day_kernel(const __grid_constant__ RepArray reps, uint32_t R, uint32_t P, uint32
             const uint32_t it2 = next_item();
             const uint4 meta2 = meta_of(it2);
             if (it1 < n_items && it1 >= n_my_hub_slices) {
-                const uint32_t s1 = p + P * (it1 - n_my_hub_slices), a1 = (r.n_hub_slices + s1) * 32;
+                const uint32_t s1 = r.sell_begin + p + P * (it1 - n_my_hub_slices), a1 = (r.n_hub_slices + s1) * 32;
                 const uint32_t nrow = (meta1.z & 0xFFFFu) + (meta1.z >> 16);
                 if (lane == 0 && nrow) prefetch_l2(r.sell_codes + (((uint64_t)meta1.y << 32) | meta1.x), nrow * 128u);
                 if (lane == 1) prefetch_l2(r.stat + a1, 128u);
@@ -436,7 +438,7 @@ day_kernel(const __grid_constant__ RepArray reps, uint32_t R, uint32_t P, uint32
                 if (lane == 4) prefetch_l2(r.habit + a1, 512u);
             }
             if (it0 < n_my_hub_slices) {              // finish one hub slice: counts come from the scratch
-                const uint32_t hs = p + P * it0, agent = hs * 32 + lane;
+                const uint32_t hs = r.hub_begin + p + P * it0, agent = hs * 32 + lane;
                 const uint4 ca = *reinterpret_cast<const uint4*>(r.hub_cnt + (size_t)agent * 8);
                 const uint4 cb = *reinterpret_cast<const uint4*>(r.hub_cnt + (size_t)agent * 8 + 4);
                 const uint32_t hcs[4] = {ca.x, ca.y, ca.z, ca.w}, hcn[4] = {cb.x, cb.y, cb.z, cb.w};
@@ -447,7 +449,7 @@ day_kernel(const __grid_constant__ RepArray reps, uint32_t R, uint32_t P, uint32
                 finish_slice<PER_AGENT>(r, hs, lane, false, hcs, ad.x + ad.z, hcn, ad.y + ad.w, stat, r.ws[agent],
                                         r.habit[agent], last, uw, s_cong, s_cost, s_crank, s_des, s_rec, weather, changed, parity, st);
             } else {
-            const uint32_t s = p + P * (it0 - n_my_hub_slices);
+            const uint32_t s = r.sell_begin + p + P * (it0 - n_my_hub_slices);
             const uint32_t slice = r.n_hub_slices + s, agent = slice * 32 + lane;
             const uint32_t KK = meta.z;
             const uint32_t* blk = r.sell_codes + (((uint64_t)meta.y << 32) | meta.x);

@@ -189,4 +189,29 @@ int build_graph_layout(const mvb_population& pop, uint32_t H, uint32_t capacity_
     return MVB_OK;
 }
 
+void partition_slices(const GraphLayout& L, uint32_t world, std::vector<uint32_t>& bounds) {
+    const uint32_t n = L.n_hub_slices + L.n_sell_slices;
+    std::vector<uint64_t> work(n);
+    for (uint32_t hs = 0; hs < L.n_hub_slices; ++hs) {
+        uint64_t w = 0;
+        for (uint32_t k = 0; k < 32; ++k) {
+            const uint32_t* dg = &L.hub_deg[(size_t)4 * (hs * 32 + k)];
+            w += (uint64_t)dg[0] + dg[1] + 2ull * (dg[2] + dg[3]) + 64;     // cold links cost about twice; + per-agent work
+        }
+        work[hs] = w;
+    }
+    for (uint32_t s = 0; s < L.n_sell_slices; ++s)
+        work[L.n_hub_slices + s] = 32ull * ((L.sell_K[s] & 0xFFFFu) + 2ull * (L.sell_K[s] >> 16) + 64);
+    uint64_t total = 0;
+    for (uint64_t w : work) total += w;
+    bounds.assign(world + 1, n);
+    bounds[0] = 0;
+    uint64_t acc = 0;
+    uint32_t r = 1;
+    for (uint32_t i = 0; i < n && r < world; ++i) {
+        acc += work[i];
+        while (r < world && acc * world >= total * r) bounds[r++] = i + 1;
+    }
+}
+
 }  // namespace mvb

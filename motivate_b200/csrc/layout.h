@@ -94,4 +94,9 @@ struct GraphLayout {
 int build_graph_layout(const mvb_population& pop, uint32_t n_neighbourhoods, uint32_t capacity_agents,
                        GraphLayout& out);
 
+// Agent-partitioned mode: cut the slices (hub slices first, then SELL slices, i.e. internal slot order) into `world`
+// contiguous ranges of about equal link count.  bounds[r] .. bounds[r+1] are rank r's slices (global slice index:
+// hub slice hs -> hs, SELL slice s -> n_hub_slices + s); bounds has world + 1 entries.
+void partition_slices(const GraphLayout& L, uint32_t world, std::vector<uint32_t>& bounds);
+
 }  // namespace mvb

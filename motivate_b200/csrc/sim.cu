@@ -2,6 +2,8 @@
 // weekday loop of src/simulation.rs:95-136 driven on one CUDA stream, state access.
 // Kernels live in day_kernels.cuh.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>          // types and enums only: the functions are resolved with dlsym (no link-time dependency)
 
 #include <algorithm>
 #include <numeric>
@@ -54,6 +56,47 @@ struct Replica {
     bool per_agent = false;
 };
 
+// NCCL, loaded on first use: the replica path (no communication) never needs it.
+struct Nccl {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+Nccl* nccl() {
+    static Nccl n;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+            n.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (n.lib) break;
+        }
+        if (n.lib) {
+#define MVB_SYM(f) n.f = reinterpret_cast<decltype(n.f)>(dlsym(n.lib, "nccl" #f))
+            MVB_SYM(GetUniqueId); MVB_SYM(CommInitRank); MVB_SYM(CommDestroy); MVB_SYM(GroupStart); MVB_SYM(GroupEnd);
+            MVB_SYM(Broadcast); MVB_SYM(AllReduce); MVB_SYM(GetErrorString);
+#undef MVB_SYM
+            if (!n.GetUniqueId || !n.CommInitRank || !n.CommDestroy || !n.GroupStart || !n.GroupEnd || !n.Broadcast ||
+                !n.AllReduce || !n.GetErrorString) n.lib = nullptr;
+        }
+    }
+    return n.lib ? &n : nullptr;
+}
+#define MVB_NCCL(call)                                                                              \
+    do {                                                                                            \
+        ncclResult_t r_ = (call);                                                                   \
+        if (r_ != ncclSuccess) {                                                                    \
+            mvb::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #call, nccl()->GetErrorString(r_)); \
+            return MVB_ERR_COMM;                                                                    \
+        }                                                                                           \
+    } while (0)
+
 }  // namespace
 
 struct mvb_sim {
@@ -82,6 +125,10 @@ struct mvb_sim {
     float last_ms = 0.f;
     uint64_t last_launches = 0;
     bool timing_valid = false;
+    // agent-partitioned mode (one population over `world` GPUs)
+    uint32_t rank = 0, world = 1;
+    ncclComm_t comm = nullptr;
+    std::vector<uint32_t> bounds;        // [world+1] global slice index where each rank's range starts
 };
 
 namespace {
@@ -139,6 +186,23 @@ int launch_day(mvb_sim* s, uint8_t weather, uint8_t changed) {
         s->last_launches++;
     }
 #undef MVB_LAUNCH
+    if (s->world > 1) {
+        // agent-partitioned: every rank now holds new modes / norms for its own slices and a partial record.
+        // One NCCL group: each rank broadcasts the packed words of its slice range, the record is all-reduced.
+        Replica& rp = s->reps[0];
+        Nccl* n = nccl();
+        uint2* vec_next = rp.vec[s->parity ^ 1u].as<uint2>();
+        uint2* normvec = rp.normvec.as<uint2>();
+        MVB_NCCL(n->GroupStart());
+        for (uint32_t r = 0; r < s->world; ++r) {
+            const size_t b = s->bounds[r], cnt = (size_t)s->bounds[r + 1] - b;
+            if (!cnt) continue;
+            MVB_NCCL(n->Broadcast(vec_next + b, vec_next + b, cnt * 8, ncclUint8, (int)r, s->comm, s->stream));
+            MVB_NCCL(n->Broadcast(normvec + b, normvec + b, cnt * 8, ncclUint8, (int)r, s->comm, s->stream));
+        }
+        MVB_NCCL(n->AllReduce(next, next, s->rec_stride, ncclUint32, ncclSum, s->comm, s->stream));
+        MVB_NCCL(n->GroupEnd());
+    }
     s->cursor++;
     s->parity ^= 1u;
     s->stepped = true;
@@ -238,14 +302,16 @@ void mvb_destroy(mvb_sim* s) {
     if (!s) return;
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
+    if (s->comm && nccl()) nccl()->CommDestroy(s->comm);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
 
-int mvb_create_batch(uint32_t R, const mvb_population* const* pops, const mvb_tables* const* tabs,
-                     const mvb_params* prm, int device, mvb_sim** out) {
+static int create_impl(uint32_t R, const mvb_population* const* pops, const mvb_tables* const* tabs,
+                       const mvb_params* prm, int device, uint32_t rank, uint32_t world, const void* unique_id,
+                       mvb_sim** out) {
     if (!out || !pops || !tabs || !prm || R == 0) { set_error("null argument or zero replicas"); return MVB_ERR_ARG; }
     *out = nullptr;
     int ndev = mvb_device_count();
@@ -441,6 +507,13 @@ int mvb_create_batch(uint32_t R, const mvb_population* const* pops, const mvb_ta
         d.N = N; d.N_pad = NP; d.S = rp.S; d.H = rp.H; d.rec_off = rp.rec_off;
         d.n_hub_slices = L.n_hub_slices; d.n_sell_slices = L.n_sell_slices;
         d.n_ranges = (uint32_t)L.ranges.size(); d.hot_words = L.hot_words;
+        d.hub_begin = 0; d.hub_end = L.n_hub_slices; d.sell_begin = 0; d.sell_end = L.n_sell_slices;
+        if (world > 1) {                               // this rank's slice range, split into its hub and SELL parts
+            partition_slices(L, world, s->bounds);
+            const uint32_t b = s->bounds[rank], e = s->bounds[rank + 1], nh = L.n_hub_slices;
+            d.hub_begin = std::min(b, nh); d.hub_end = std::min(e, nh);
+            d.sell_begin = std::max(b, nh) - nh; d.sell_end = std::max(e, nh) - nh;
+        }
         d.stat = rp.stat.as<uint32_t>(); d.ws = rp.ws.as<float>(); d.habit = rp.habit.as<float4>();
         d.pa = rp.per_agent ? rp.pa.as<float>() : nullptr;
         d.vec[0] = rp.vec[0].as<uint2>(); d.vec[1] = rp.vec[1].as<uint2>(); d.normvec = rp.normvec.as<uint2>();
@@ -461,6 +534,14 @@ int mvb_create_batch(uint32_t R, const mvb_population* const* pops, const mvb_ta
     MVB_CUDA(cudaFuncSetAttribute(day_kernel<false, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
     if (s->census_smem > 48 * 1024)
         MVB_CUDA(cudaFuncSetAttribute(census_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->census_smem));
+    s->rank = rank; s->world = world;
+    if (world > 1) {
+        Nccl* n = nccl();
+        if (!n) { set_error("agent-partitioned mode needs NCCL (libnccl.so.2 could not be loaded: %s)", dlerror()); return MVB_ERR_COMM; }
+        ncclUniqueId id;
+        memcpy(&id, unique_id, sizeof id);
+        MVB_NCCL(n->CommInitRank(&s->comm, (int)world, id, (int)rank));
+    }
     s->rep_args.assign((R + kMaxRepsPerLaunch - 1) / kMaxRepsPerLaunch, RepArray{});
     for (uint32_t r = 0; r < R; ++r) s->rep_args[r / kMaxRepsPerLaunch].r[r % kMaxRepsPerLaunch] = s->h_reps[r];
     MVB_CUDA(s->d_reps.alloc(sizeof(RepDev) * R));
@@ -477,8 +558,60 @@ int mvb_create_batch(uint32_t R, const mvb_population* const* pops, const mvb_ta
     return MVB_OK;
 }
 
+int mvb_create_batch(uint32_t R, const mvb_population* const* pops, const mvb_tables* const* tabs,
+                     const mvb_params* prm, int device, mvb_sim** out) {
+    return create_impl(R, pops, tabs, prm, device, 0, 1, nullptr, out);
+}
+
 int mvb_create(const mvb_population* pop, const mvb_tables* tab, const mvb_params* prm, int device, mvb_sim** out) {
-    return mvb_create_batch(1, &pop, &tab, prm, device, out);
+    return create_impl(1, &pop, &tab, prm, device, 0, 1, nullptr, out);
+}
+
+int mvb_comm_unique_id(void* id_out) {
+    if (!id_out) { set_error("null argument"); return MVB_ERR_ARG; }
+    Nccl* n = nccl();
+    if (!n) { set_error("NCCL (libnccl.so.2) could not be loaded: %s", dlerror()); return MVB_ERR_COMM; }
+    static_assert(sizeof(ncclUniqueId) == MVB_UNIQUE_ID_BYTES, "unique id size");
+    ncclUniqueId id;
+    MVB_NCCL(n->GetUniqueId(&id));
+    memcpy(id_out, &id, sizeof id);
+    return MVB_OK;
+}
+
+int mvb_create_partitioned(const mvb_population* pop, const mvb_tables* tab, const mvb_params* prm, int device,
+                           uint32_t rank, uint32_t world, const void* unique_id, mvb_sim** out) {
+    if (world == 0 || rank >= world) { set_error("rank %u out of range for world %u", rank, world); return MVB_ERR_ARG; }
+    if (world > 1 && !unique_id) { set_error("a communicator id is required for world > 1"); return MVB_ERR_ARG; }
+    return create_impl(1, &pop, &tab, prm, device, rank, world, unique_id, out);
+}
+
+static void owners_from_bounds(const GraphLayout& L, const std::vector<uint32_t>& bounds, uint32_t world, uint32_t* rank_out) {
+    for (uint32_t r = 0; r < world; ++r)
+        for (size_t slot = (size_t)bounds[r] * 32; slot < (size_t)bounds[r + 1] * 32; ++slot)
+            if (L.int2ext[slot] != kInvalid) rank_out[L.int2ext[slot]] = r;
+}
+
+int mvb_partition_owner(const mvb_sim* s, uint32_t* rank_out) {
+    if (!s || !rank_out) { set_error("null argument"); return MVB_ERR_ARG; }
+    const GraphLayout& L = s->reps[0].graph->L;
+    if (s->world <= 1) { for (uint32_t i = 0; i < L.N; ++i) rank_out[i] = 0; return MVB_OK; }
+    owners_from_bounds(L, s->bounds, s->world, rank_out);
+    return MVB_OK;
+}
+
+int mvb_partition_plan(const mvb_population* pop, uint32_t S, uint32_t H, uint32_t world, uint32_t* rank_out) {
+    if (!pop || !rank_out || world == 0 || H == 0 || S == 0) { set_error("bad argument"); return MVB_ERR_ARG; }
+    GraphLayout L;
+    // same shared-memory capacity as mvb_create* computes on a B200 (227 KB opt-in limit), so the plan is the
+    // split a B200 handle really uses
+    const uint32_t tail = (tail_words(S, H) + 3u) & ~3u;
+    const uint32_t capacity = ((232448u / 4u - tail) & ~3u) * 16u / 64u * 64u;
+    int rc = build_graph_layout(*pop, H, capacity, L);
+    if (rc) return rc;
+    std::vector<uint32_t> bounds;
+    partition_slices(L, world, bounds);
+    owners_from_bounds(L, bounds, world, rank_out);
+    return MVB_OK;
 }
 
 uint32_t mvb_n_replicas(const mvb_sim* s) { return s ? (uint32_t)s->reps.size() : 0; }

@@ -1,0 +1,132 @@
+"""Agent-partitioned mode (BASELINE config 4): one population, `world` ranks, each updating its own
+agents; after every weekday the ranks exchange packed modes and all-reduce the counters.
+
+CPU part: the partition plan (host logic of the library, no device) and a world_size-2 gloo emulation of the exchange
+protocol on the oracle.  GPU part (needs 2 devices; run with `gpurun --gpus 2 -- python -m pytest tests -m gpu -k partitioned`):
+2 NCCL ranks against one oracle run, bit for bit."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import motivate_b200 as mb
+from motivate_b200 import _ffi
+from common import assert_state_equal
+from oracle.binding import OracleSimulation
+
+N, S, H, N_DAYS = 6000, 3, 5, 16
+
+
+def inputs():
+    return (mb.synth_population(N, S, H, 4, 6, seed=77), mb.synth_tables(S, H, N, seed=77), mb.make_params(),
+            mb.weather_pattern(N_DAYS, seed=77, p_good_given_good=0.6, p_good_given_bad=0.5))
+
+
+def free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def test_partition_plan_is_balanced_partition():
+    pop, _, _, _ = inputs()
+    deg = (np.diff(pop["social_rowptr"]) + np.diff(pop["neighbour_rowptr"])).astype(np.int64)
+    for world in (1, 2, 3, 8):
+        owner = mb.partition_plan(pop, S, H, world)
+        assert owner.min() == 0 and owner.max() == world - 1           # everyone is owned, every rank owns someone
+        links = np.bincount(owner, weights=deg + 64, minlength=world)   # the plan's work measure: links + per-agent work
+        if world <= 3:                                                  # (slice granularity: 6 000 agents are 190 slices,
+            assert links.max() / links.mean() < 1.15, (world, links)    #  the first of them all hubs)
+    assert np.array_equal(mb.partition_plan(pop, S, H, 2), mb.partition_plan(pop, S, H, 2))
+
+
+def gloo_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    pop, tab, prm, w = inputs()
+    owner = mb.partition_plan(pop, S, H, world)
+    mine = owner == rank
+    # every rank keeps the whole population (as the GPU ranks do) but only its own agents' results count
+    o = OracleSimulation(pop, tab, prm)
+    rows = [o.stats_row()]
+    prev = w[0]
+    for day in range(1, N_DAYS):
+        if day % 7 >= 5:
+            continue
+        o.step(w[day], prev != w[day]); prev = w[day]
+        st = o.get_state()
+        # exchange: own modes / norms to everyone (allgather), counters summed (allreduce) — what NCCL does on the GPUs
+        mode = torch.from_numpy(np.where(mine, st["current_mode"], 0).astype(np.int32))
+        norm = torch.from_numpy(np.where(mine, st["norm"], 0).astype(np.int32))
+        dist.all_reduce(mode); dist.all_reduce(norm)
+        assert np.array_equal(mode.numpy(), st["current_mode"]) and np.array_equal(norm.numpy(), st["norm"])
+        part = np.zeros(7 + S + H, np.int64)
+        a, an = st["current_mode"] >= 2, st["norm"] >= 2
+        for i in np.flatnonzero(mine):
+            part[0] += a[i]; part[1] += an[i]; part[2] += a[i] and not an[i]; part[3] += (not a[i]) and an[i]
+            if a[i]:
+                part[4 + pop["commute"][i]] += 1; part[7 + pop["subculture"][i]] += 1; part[7 + S + pop["neighbourhood"][i]] += 1
+        t = torch.from_numpy(part); dist.all_reduce(t)
+        assert np.array_equal(t.numpy(), o.stats_row().astype(np.int64))
+        rows.append(o.stats_row())
+    if rank == 0:
+        np.save(out, np.array(rows))
+    dist.destroy_process_group()
+
+
+def test_exchange_protocol_two_gloo_ranks(tmp_path):
+    out = str(tmp_path / "rows.npy")
+    mp.spawn(gloo_worker, args=(2, free_port(), out), nprocs=2, join=True)
+    pop, tab, prm, w = inputs()
+    _, rows = OracleSimulation(pop, tab, prm).run(w)
+    assert np.array_equal(np.load(out), rows)
+
+
+def nccl_worker(rank, world, idfile, out):
+    pop, tab, prm, w = inputs()
+    if rank == 0:
+        open(idfile + ".tmp", "wb").write(mb.comm_unique_id()); os.rename(idfile + ".tmp", idfile)
+    import time
+    while not os.path.exists(idfile):
+        time.sleep(0.05)
+    uid = open(idfile, "rb").read()
+    sim = mb.Simulation.partitioned(pop, tab, prm, device=rank, rank=rank, world=world, unique_id=uid)
+    days, rows = sim.run(w)
+    st = sim.get_state(0)
+    np.savez(out + f".{rank}.npz", days=days, rows=rows[0], owner=sim.partition_owner(), **st)
+    sim.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(_ffi.load().mvb_device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_partitioned_two_gpus_equal_oracle(tmp_path):
+    out, idfile = str(tmp_path / "state"), str(tmp_path / "nccl_id")
+    mp.spawn(nccl_worker, args=(2, idfile, out), nprocs=2, join=True)
+    pop, tab, prm, w = inputs()
+    o = OracleSimulation(pop, tab, prm)
+    days, rows = o.run(w)
+    ref = o.get_state()
+    z = [np.load(out + f".{r}.npz") for r in range(2)]
+    assert np.array_equal(z[0]["owner"], z[1]["owner"]) and set(np.unique(z[0]["owner"])) == {0, 1}
+    for r in range(2):
+        assert np.array_equal(z[r]["days"], days) and np.array_equal(z[r]["rows"], rows), f"rows on rank {r}"
+        for k in ("current_mode", "norm", "hist"):
+            assert np.array_equal(z[r][k], ref[k]), (r, k)              # every rank holds the full vectors
+        mine = z[r]["owner"] == r
+        assert np.array_equal(z[r]["habit"][mine].view(np.uint32), ref["habit"][mine].view(np.uint32))   # own habits
+
+
+@pytest.mark.gpu
+def test_partitioned_world_1_is_a_plain_run():
+    pop, tab, prm, w = inputs()
+    sim = mb.Simulation.partitioned(pop, tab, prm, device=0, rank=0, world=1, unique_id=None)
+    days, rows = sim.run(w)
+    o = OracleSimulation(pop, tab, prm)
+    d2, r2 = o.run(w)
+    assert np.array_equal(rows[0], r2)
+    assert_state_equal(sim.get_state(0), o.get_state(), "world 1")
+    assert np.all(sim.partition_owner() == 0)
+    sim.close()
