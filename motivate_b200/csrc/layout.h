@@ -40,7 +40,7 @@
 
 namespace mvb {
 
-constexpr uint32_t kHubDegree = 128;        // total links above which an agent is a hub (must be <= 255)
+constexpr uint32_t kHubDegree = 252;        // total links above which an agent is a hub (must be <= 255: 8-bit counters)
 constexpr uint32_t kInvalid = 0xFFFFFFFFu;
 
 // Lengths (per lane) of the next block of a hub whose lists still have rem_hot / rem_cold links to go.
