@@ -40,6 +40,8 @@ def parse():
     ap.add_argument("--agents", type=int, default=1_000_000)
     ap.add_argument("--partitioned", action="store_true",
                     help="BASELINE config 4: ONE population of --agents agents partitioned over the ranks (NCCL exchange per weekday)")
+    ap.add_argument("--sweep", action="store_true",
+                    help="BASELINE config 5: --replicas scenario variants (tables + ownership differ) over ONE shared population")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-baseline-days", type=int, default=8)
@@ -127,6 +129,26 @@ def make_inputs(args, replica_ids, pinned=False):
             p._struct = None
         return p, mb.synth_tables(4, 10, args.agents, seed=r)
 
+    if args.sweep:
+        # config 5: one population; variant v has its own tables (supportiveness +-0.1 on a subset of neighbourhoods,
+        # Car capacity cut) and its own car / bike ownership (+-5 %); the link graph arrays are shared objects, so the
+        # library stores the graph once on the device
+        base, tab0 = one(0)
+        pops, tabs = [], []
+        rng = np.random.default_rng(5)
+        for v in replica_ids:
+            p = mb.PopulationData(dict(base.arrays))             # same array objects: same pointers
+            for k in ("owns_car", "owns_bike"):
+                a = base[k].copy()
+                flip = rng.choice(args.agents, args.agents // 20, replace=False)
+                a[flip] = (v + (k == "owns_bike")) % 2
+                p.arrays[k] = a
+            t = tab0.copy()
+            sel = rng.random(t.H) < 0.5
+            t.supportiveness[sel, 2:] += np.float32(0.1); t.supportiveness[sel, 0] -= np.float32(0.1)
+            t.capacity[sel, 0] = (t.capacity[sel, 0] * 0.8).astype(np.uint32)
+            pops.append(p); tabs.append(t)
+        return pops, tabs
     with ThreadPoolExecutor(max_workers=min(len(replica_ids), os.cpu_count() or 1)) as ex:
         res = list(ex.map(one, replica_ids))
     return [p for p, _ in res], [t for _, t in res]
@@ -201,6 +223,13 @@ def run_reference(args, rank):
 
 
 def workload_config(args, note=None):
+    if args.sweep:
+        return {"workload": f"C5: {args.replicas} scenario variants (tables + car/bike ownership) x {args.agents} agents over ONE "
+                            "shared population and link graph, 4 subcultures, 10 neighbourhoods, BA links 5+10",
+                "replicas": args.replicas, "agents_per_replica": args.agents,
+                "parallelism": f"variant-sharded x{args.gpus}, no communication",
+                "l2": "link codes of the shared graph are L2-resident by design; per-variant state streams from HBM",
+                **({"note": note} if note else {})}
     c = {"workload": f"C3: {args.replicas} independent replicas x {args.agents} agents, 4 subcultures, 10 neighbourhoods, "
                      "BA links min 5 social + 10 neighbour (mean 30/agent), steps = weekdays of the 2-year calendar",
          "replicas": args.replicas, "agents_per_replica": args.agents, "parallelism": f"replica-sharded x{args.gpus}, no communication",
@@ -258,7 +287,7 @@ def main():
         dist.barrier()
     ms, launches = sim.last_run_stats()
     clocks = sampler.stop()
-    assert launches == args.steps, (launches, args.steps)
+    assert launches == args.steps * -(-per // 64), (launches, args.steps)       # 64 replicas per launch
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -52,7 +52,8 @@ struct RepDev {                     // device-side descriptor of one replica
     const uint32_t* deg;            // [N_pad] SELL agents: ds_hot | dn_hot<<8 | ds_cold<<16 | dn_cold<<24
     const StageRange* ranges;
     const uint64_t* hub_off; const uint4* hub_deg; const uint32_t* hub_codes;   // per hub: block offset, (ds_hot, dn_hot, ds_cold, dn_cold)
-    uint32_t* hub_cnt;              // [n_hub_slices*32][8] scratch: a hub's 4 social + 4 neighbour counts of the day
+    const uint4* hub_units; const uint32_t* hub_unit_begin;   // units (<= 1 024 links) of every hub slice, layout.h
+    uint32_t* hub_cnt;              // [n_hub_slices*32][8] scratch, zero between days: [1..3] social, [5..7] neighbour counts of modes 1..3
     const uint4* sell_meta; const uint32_t* sell_codes;       // per slice {off_lo, off_hi, K | Kc << 16, 0}
     const float* supp; const float* desir;       // [H][4], [S][4]
     const uint32_t* cap; const uint32_t* nres;   // [H][4], [H]
@@ -367,42 +368,35 @@ day_kernel(const __grid_constant__ RepArray reps, uint32_t R, uint32_t P, uint32
         phase ^= 1u;
 
 
-        // 2. hubs of this part's hub slices (p, p+P, ...): one warp per hub agent, the hub's lists cut into 32 chunks
-        // (one per lane).  The 8 counts of a hub go to a small global scratch; the hub slices are finished below
-        // like any other slice, so no warp waits for another here.
+        // 2. hubs of this part's hub slices (hub_begin + p, + P, ...).  A hub's lists are cut into units of at most
+        // 1 024 links (layout.h); a warp takes a unit, its 32 lanes take 32 contiguous chunks of it, and the unit's
+        // counts of modes 1..3 are added to the hub's entry of a small global scratch.  The hub slices are finished
+        // below like any other slice, so no warp waits for another here and the biggest hubs spread over many warps.
         const uint32_t n_own_hub = r.hub_end - r.hub_begin;
         const uint32_t n_my_hub_slices = n_own_hub > p ? (n_own_hub - p + P - 1) / P : 0;
-        for (uint32_t j = warp; j < n_my_hub_slices * 32; j += THREADS / 32) {
-            const uint32_t hub = (r.hub_begin + p + P * (j >> 5)) * 32 + (j & 31u);
-            const uint4 hd = ld_stream_v4(reinterpret_cast<const uint4*>(r.hub_deg) + hub);   // ds_hot, dn_hot, ds_cold, dn_cold
-            const uint32_t n_hot = hd.x + hd.y, n_cold = hd.z + hd.w;
-            uint32_t cs[4] = {0, 0, 0, 0}, cn[4] = {0, 0, 0, 0};
-            const uint32_t* blk = r.hub_codes + r.hub_off[hub];
-            // blocks of at most 252 links per lane keep the 8-bit accumulators exact (hub_segment, layout.h)
-            for (uint32_t done_h = 0, done_c = 0; done_h < n_hot || done_c < n_cold;) {
-                uint32_t K, Kc;
-                hub_segment(n_hot - min(done_h, n_hot), n_cold - min(done_c, n_cold), K, Kc);
-                const int oh = (int)(done_h + lane * K), oc = (int)(done_c + lane * Kc);
+        for (uint32_t k = 0; k < n_my_hub_slices; ++k) {
+            const uint32_t hs = r.hub_begin + p + P * k;
+            const uint32_t u_end = r.hub_unit_begin[hs + 1];
+            for (uint32_t u = r.hub_unit_begin[hs] + warp; u < u_end; u += THREADS / 32) {
+                const uint4 ua = ld_stream_v4(r.hub_units + 2 * (size_t)u), ub = ld_stream_v4(r.hub_units + 2 * (size_t)u + 1);
+                const uint32_t K = ua.z & 0xFFu, Kc = (ua.z >> 8) & 0xFFu, hub = ua.w;
+                const uint4 hd = ld_stream_v4(reinterpret_cast<const uint4*>(r.hub_deg) + hub);   // ds_hot, dn_hot, ds_cold, dn_cold
+                const uint32_t* blk = r.hub_codes + (((uint64_t)ua.y << 32) | ua.x);
+                const int oh = (int)(ub.x + lane * K), oc = (int)(ub.y + lane * Kc);
+                const int n_hot = (int)(hd.x + hd.y), n_cold = (int)(hd.z + hd.w);
                 uint32_t acc_s = 0, acc_n = 0;
-                accumulate_block(blk, K, Kc, lane, min(max((int)hd.x - oh, 0), (int)K), min(max((int)n_hot - oh, 0), (int)K),
-                                 min(max((int)hd.z - oc, 0), (int)Kc), min(max((int)n_cold - oc, 0), (int)Kc),
+                accumulate_block(blk, K, Kc, lane, min(max((int)hd.x - oh, 0), (int)K), min(max(n_hot - oh, 0), (int)K),
+                                 min(max((int)hd.z - oc, 0), (int)Kc), min(max(n_cold - oc, 0), (int)Kc),
                                  s_vec, g_vec, acc_s, acc_n);
+                uint32_t mine = 0;                     // lane 1..3: social count of mode lane; lane 5..7: neighbour count
 #pragma unroll
-                for (int m = 1; m < 4; ++m) { cs[m] += (acc_s >> (8 * m)) & 0xFFu; cn[m] += (acc_n >> (8 * m)) & 0xFFu; }
-                blk += (size_t)32 * (K + Kc);
-                done_h += 32u * K; done_c += 32u * Kc;
-            }
-#pragma unroll
-            for (int m = 1; m < 4; ++m) {
-                cs[m] = __reduce_add_sync(0xFFFFFFFFu, cs[m]);
-                cn[m] = __reduce_add_sync(0xFFFFFFFFu, cn[m]);
-            }
-            cs[0] = hd.x + hd.z - cs[1] - cs[2] - cs[3];        // Car = what is left of the list (count_fields)
-            cn[0] = hd.y + hd.w - cn[1] - cn[2] - cn[3];
-            if (lane < 8) {
-                const uint32_t v = lane == 0 ? cs[0] : lane == 1 ? cs[1] : lane == 2 ? cs[2] : lane == 3 ? cs[3]
-                                 : lane == 4 ? cn[0] : lane == 5 ? cn[1] : lane == 6 ? cn[2] : cn[3];
-                r.hub_cnt[(size_t)hub * 8 + lane] = v;
+                for (int m = 1; m < 4; ++m) {
+                    const uint32_t cs_m = __reduce_add_sync(0xFFFFFFFFu, (acc_s >> (8 * m)) & 0xFFu);
+                    const uint32_t cn_m = __reduce_add_sync(0xFFFFFFFFu, (acc_n >> (8 * m)) & 0xFFu);
+                    if (lane == (uint32_t)m) mine = cs_m;
+                    if (lane == (uint32_t)m + 4u) mine = cn_m;
+                }
+                if (mine) atomicAdd(&r.hub_cnt[(size_t)hub * 8 + lane], mine);
             }
         }
         __syncthreads();                              // the hub counts written above are read by other warps below
@@ -439,11 +433,14 @@ day_kernel(const __grid_constant__ RepArray reps, uint32_t R, uint32_t P, uint32
             }
             if (it0 < n_my_hub_slices) {              // finish one hub slice: counts come from the scratch
                 const uint32_t hs = r.hub_begin + p + P * it0, agent = hs * 32 + lane;
-                const uint4 ca = *reinterpret_cast<const uint4*>(r.hub_cnt + (size_t)agent * 8);
-                const uint4 cb = *reinterpret_cast<const uint4*>(r.hub_cnt + (size_t)agent * 8 + 4);
-                const uint32_t hcs[4] = {ca.x, ca.y, ca.z, ca.w}, hcn[4] = {cb.x, cb.y, cb.z, cb.w};
-                const uint32_t stat = r.stat[agent];
+                uint4* cnt = reinterpret_cast<uint4*>(r.hub_cnt + (size_t)agent * 8);
+                const uint4 ca = cnt[0], cb = cnt[1];
+                cnt[0] = make_uint4(0, 0, 0, 0); cnt[1] = make_uint4(0, 0, 0, 0);      // ready for tomorrow
                 const uint4 ad = r.hub_deg[agent];
+                // Car = what is left of each list (count_fields)
+                const uint32_t hcs[4] = {ad.x + ad.z - ca.y - ca.z - ca.w, ca.y, ca.z, ca.w};
+                const uint32_t hcn[4] = {ad.y + ad.w - cb.y - cb.z - cb.w, cb.y, cb.z, cb.w};
+                const uint32_t stat = r.stat[agent];
                 const uint2 own = r.vec[parity][hs];
                 const uint32_t last = ((lane < 16 ? own.x : own.y) >> ((lane & 15u) * 2u)) & 3u;
                 finish_slice<PER_AGENT>(r, hs, lane, false, hcs, ad.x + ad.z, hcn, ad.y + ad.w, stat, r.ws[agent],

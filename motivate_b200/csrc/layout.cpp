@@ -147,8 +147,11 @@ int build_graph_layout(const mvb_population& pop, uint32_t H, uint32_t capacity_
     L.hub_off.assign(n_hub_rows, 0);
     L.hub_deg.assign((size_t)4 * n_hub_rows, 0);
     uint64_t hoff = 0;
+    L.hub_units.clear();
+    L.hub_unit_begin.assign((size_t)L.n_hub_slices + 1, 0);
     for (uint32_t k = 0; k < n_hub_rows; ++k) {
         L.hub_off[k] = hoff;
+        if ((k & 31u) == 0) L.hub_unit_begin[k >> 5] = (uint32_t)(L.hub_units.size() / 2);
         if (k >= hubs.size()) continue;
         const uint32_t e = hubs[k];
         const uint32_t ds = (uint32_t)(srp[e + 1] - srp[e]), dn = (uint32_t)(nrp[e + 1] - nrp[e]);
@@ -158,10 +161,15 @@ int build_graph_layout(const mvb_population& pop, uint32_t H, uint32_t capacity_
         for (uint32_t dh = 0, dc = 0; dh < nh || dc < nc;) {
             uint32_t K, Kc;
             hub_segment(nh - std::min(dh, nh), nc - std::min(dc, nc), K, Kc);
+            L.hub_units.push_back(uint4x{(uint32_t)hoff, (uint32_t)(hoff >> 32), K | Kc << 8, k});
+            L.hub_units.push_back(uint4x{dh, dc, 0, 0});
             hoff += (uint64_t)32 * (K + Kc);
             dh += 32 * K; dc += 32 * Kc;
         }
     }
+    L.hub_unit_begin[L.n_hub_slices] = (uint32_t)(L.hub_units.size() / 2);
+    L.hub_units.push_back(uint4x{0, 0, 0, 0});            // slack: the kernel reads one unit record ahead
+    L.hub_units.push_back(uint4x{0, 0, 0, 0});
     L.hub_codes_len = hoff + 256;                        // + slack for the row prefetch
     // SELL slices
     L.sell_off.assign(L.n_sell_slices, 0);

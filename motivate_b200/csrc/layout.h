@@ -25,8 +25,8 @@
 //   (a wrapping funnel shift uses them directly); code >> 5 is the byte address.
 //
 // Hub slices  (32 hubs, one WARP per hub): the hub's hot and cold lists are cut into 32 contiguous chunks, one
-//   per lane, and stored as blocks of the SELL format below (lane = chunk); a list too long for one block
-//   (more than 252 links per lane, the 8-bit counters' limit) continues in further blocks, see hub_segment().
+//   per lane, and stored as blocks ("units") of the SELL format below (lane = chunk) of at most 1 024 links each,
+//   see hub_segment(); any warp of the block that owns the hub's slice can take a unit.
 // SELL slices (32 agents, one LANE per agent): K = longest hot list, Kc = longest cold list of the slice;
 //   codes stored k-major so that a warp's loads are contiguous: a "body" of floor(K/4) uint4 per lane
 //   (lane's hot links 4q..4q+3), a "tail" of K%4 u32 per lane, then Kc u32 per lane of cold links.
@@ -43,6 +43,8 @@ namespace mvb {
 constexpr uint32_t kHubDegree = 252;        // total links above which an agent is a hub (must be <= 255: 8-bit counters)
 constexpr uint32_t kInvalid = 0xFFFFFFFFu;
 
+constexpr uint32_t kHubUnitRows = 32;       // links per lane in one hub block: a block ("unit") is at most 1 024 links,
+                                            // about one SELL slice of work, so the biggest hubs spread over many warps
 // Lengths (per lane) of the next block of a hub whose lists still have rem_hot / rem_cold links to go.
 // Host (layout.cpp) and device (day_kernels.cuh) walk a hub's blocks with this same rule.
 #if defined(__CUDACC__)
@@ -50,9 +52,9 @@ __host__ __device__
 #endif
 inline void hub_segment(uint32_t rem_hot, uint32_t rem_cold, uint32_t& K, uint32_t& Kc) {
     K = (rem_hot + 31u) / 32u;
-    if (K > 252u) K = 252u;
+    if (K > kHubUnitRows) K = kHubUnitRows;
     Kc = (rem_cold + 31u) / 32u;
-    if (Kc > 252u - K) Kc = 252u - K;
+    if (Kc > kHubUnitRows - K) Kc = kHubUnitRows - K;
 }
 
 struct uint4x { uint32_t x, y, z, w; };   // host-side mirror of CUDA's uint4 (16 bytes)
@@ -80,6 +82,8 @@ struct GraphLayout {
     std::vector<uint64_t> hub_off;         // [n_hub_slices*32] offset of the hub's first block in hub_codes (u32 units)
     std::vector<uint32_t> hub_deg;         // [n_hub_slices*32][4] ds_hot, dn_hot, ds_cold, dn_cold
     uint64_t hub_codes_len = 0;            // u32 entries of the device array hub_codes (incl. prefetch slack)
+    std::vector<uint4x> hub_units;         // 2 records per unit: {off_lo, off_hi, K | Kc << 8, hub} {done_hot, done_cold, 0, 0}
+    std::vector<uint32_t> hub_unit_begin;  // [n_hub_slices + 1] first unit of every hub slice
     // SELL
     std::vector<uint64_t> sell_off;        // [n_sell_slices] offset of the slice in sell_codes (u32 units)
     std::vector<uint32_t> sell_K;          // [n_sell_slices] K | Kc << 16

@@ -6,6 +6,7 @@
 #include <nccl.h>          // types and enums only: the functions are resolved with dlsym (no link-time dependency)
 
 #include <algorithm>
+#include <cmath>
 #include <numeric>
 #include <thread>
 #include <atomic>
@@ -44,7 +45,7 @@ struct DevBuf {                       // owning device allocation
 // (scenario sweeps over one population pass the same graph + neighbourhood arrays).
 struct Graph {
     GraphLayout L;                 // host copy: permutation, sizes (code arrays are released after upload)
-    DevBuf deg, ranges, hub_off, hub_deg, hub_codes, sell_meta, sell_codes, int2ext;
+    DevBuf deg, ranges, hub_off, hub_deg, hub_codes, hub_units, hub_unit_begin, sell_meta, sell_codes, int2ext;
     const void* key[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // caller pointers it was built from
 };
 
@@ -110,7 +111,6 @@ struct mvb_sim {
     std::vector<RepArray> rep_args;      // h_reps cut into kernel-parameter sized pieces
     uint32_t rec_stride = 0;             // u32 per record row (all replicas)
     uint32_t grid = 0;                   // persistent blocks (one per SM)
-    uint32_t threads = 1024;             // block size of the day kernel (MVB_THREADS=512 selects the 128-register variant)
     uint32_t max_npad = 0;
     uint32_t vec_cap_words = 0;          // shared-memory words reserved for the staged mode vector
     size_t smem_bytes = 0, census_smem = 0;
@@ -167,6 +167,29 @@ int launch_census(mvb_sim* s, uint32_t row) {
     return MVB_OK;
 }
 
+// How many parts to cut each of the R replicas of one launch into.  A block takes parts b, b+grid, ... and a part
+// costs a fixed set-up (staging the mode vector, tables, two barriers) plus its slices, 32 at a time (one per warp).
+// Few parts per replica leave blocks idle, many make the set-up and the last, partly filled round of slices dominate
+// (small populations); pick the count with the smallest modelled launch time.
+uint32_t choose_parts(const mvb_sim* s, uint32_t first_rep, uint32_t R) {
+    double slices = 0, vec_bytes = 0;
+    for (uint32_t r = 0; r < R; ++r) {
+        const RepDev& d = s->h_reps[first_rep + r];
+        slices += (d.hub_end - d.hub_begin) * 4.0 + (d.sell_end - d.sell_begin);      // a hub slice is worth a few SELL slices
+        vec_bytes += d.hot_words * 4.0;
+    }
+    slices /= R; vec_bytes /= R;
+    const double t_slice = 7.5, t_fixed = 10.0 + vec_bytes / 150e3;                    // microseconds (calibrated on B200)
+    uint32_t best = 1;
+    double best_t = 1e300;
+    for (uint32_t P = 1; P <= s->grid; ++P) {
+        const double rounds = std::ceil((double)R * P / s->grid);
+        const double t = rounds * (t_fixed + (slices / P / 32.0 + 0.5) * t_slice);        // + half a round: the ragged end
+        if (t < best_t * 0.999) { best_t = t; best = P; }
+    }
+    return best;
+}
+
 int launch_day(mvb_sim* s, uint8_t weather, uint8_t changed) {
     int rc = ensure_rows(s, 1);
     if (rc) return rc;
@@ -179,9 +202,8 @@ int launch_day(mvb_sim* s, uint8_t weather, uint8_t changed) {
         s->rep_args[c], R, P, s->parity, prev, next, weather, changed, uw, s->vec_cap_words)
     for (size_t c = 0; c < s->rep_args.size(); ++c) {
         const uint32_t R = std::min<uint32_t>(kMaxRepsPerLaunch, (uint32_t)s->reps.size() - (uint32_t)c * kMaxRepsPerLaunch);
-        const uint32_t P = s->grid / std::gcd(R, s->grid);      // R*P parts = lcm(R, grid): every block gets the same number
-        if (s->threads == 512) { if (s->any_per_agent) MVB_LAUNCH(true, 512); else MVB_LAUNCH(false, 512); }
-        else                   { if (s->any_per_agent) MVB_LAUNCH(true, 1024); else MVB_LAUNCH(false, 1024); }
+        const uint32_t P = choose_parts(s, (uint32_t)c * kMaxRepsPerLaunch, R);
+        if (s->any_per_agent) MVB_LAUNCH(true, 1024); else MVB_LAUNCH(false, 1024);
         MVB_CUDA(cudaGetLastError());
         s->last_launches++;
     }
@@ -413,7 +435,8 @@ static int create_impl(uint32_t R, const mvb_population* const* pops, const mvb_
             GraphLayout& L = g->L;
             int rc;
             if ((rc = upload(g->ranges, L.ranges, s->stream)) || (rc = upload(g->hub_off, L.hub_off, s->stream)) ||
-                (rc = upload(g->hub_deg, L.hub_deg, s->stream)) || (rc = upload(g->sell_meta, L.sell_meta, s->stream)))
+                (rc = upload(g->hub_deg, L.hub_deg, s->stream)) || (rc = upload(g->sell_meta, L.sell_meta, s->stream)) ||
+                (rc = upload(g->hub_units, L.hub_units, s->stream)) || (rc = upload(g->hub_unit_begin, L.hub_unit_begin, s->stream)))
                 return rc;
             MVB_CUDA(g->deg.alloc(sizeof(uint32_t) * (size_t)L.N_pad));
             MVB_CUDA(g->hub_codes.alloc(sizeof(uint32_t) * L.hub_codes_len));
@@ -519,6 +542,8 @@ static int create_impl(uint32_t R, const mvb_population* const* pops, const mvb_
         d.vec[0] = rp.vec[0].as<uint2>(); d.vec[1] = rp.vec[1].as<uint2>(); d.normvec = rp.normvec.as<uint2>();
         d.deg = g.deg.as<uint32_t>(); d.ranges = g.ranges.as<StageRange>();
         MVB_CUDA(rp.hub_cnt.alloc(sizeof(uint32_t) * 8 * 32 * (size_t)L.n_hub_slices));
+        MVB_CUDA(cudaMemsetAsync(rp.hub_cnt.p, 0, rp.hub_cnt.bytes, s->stream));
+        d.hub_units = g.hub_units.as<uint4>(); d.hub_unit_begin = g.hub_unit_begin.as<uint32_t>();
         d.hub_off = g.hub_off.as<uint64_t>(); d.hub_deg = g.hub_deg.as<uint4>(); d.hub_cnt = rp.hub_cnt.as<uint32_t>();
         d.hub_codes = g.hub_codes.as<uint32_t>();
         d.sell_meta = g.sell_meta.as<uint4>(); d.sell_codes = g.sell_codes.as<uint32_t>();
@@ -527,11 +552,8 @@ static int create_impl(uint32_t R, const mvb_population* const* pops, const mvb_
         d.cong = rp.cong.as<float>();
         if (L.hot_words > s->vec_cap_words) { set_error("internal: staged vector larger than its shared-memory slot"); return MVB_ERR_STATE; }
     }
-    if (const char* t = getenv("MVB_THREADS")) s->threads = atoi(t) == 512 ? 512 : 1024;
     MVB_CUDA(cudaFuncSetAttribute(day_kernel<true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
     MVB_CUDA(cudaFuncSetAttribute(day_kernel<false, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
-    MVB_CUDA(cudaFuncSetAttribute(day_kernel<true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
-    MVB_CUDA(cudaFuncSetAttribute(day_kernel<false, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
     if (s->census_smem > 48 * 1024)
         MVB_CUDA(cudaFuncSetAttribute(census_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->census_smem));
     s->rank = rank; s->world = world;
