@@ -364,6 +364,44 @@ day_kernel(const __grid_constant__ RepArray reps, uint32_t R, uint32_t P, uint32
         for (uint32_t k = tid; k < 4 * S; k += THREADS) s_des[k] = r.desir[k];
         for (uint32_t k = tid; k < rec_width(S, H); k += THREADS) s_rec[k] = 0;
         __syncthreads();
+
+        // While the staging copies are in flight: every warp claims its first two work items (below), reads their slice
+        // records and pulls the first one's link codes and agent state into L2; likewise the first hub unit of the warp.
+        const uint32_t n_own_hub = r.hub_end - r.hub_begin;
+        const uint32_t n_my_hub_slices = n_own_hub > p ? (n_own_hub - p + P - 1) / P : 0;
+        const uint32_t n_sell = r.sell_end - r.sell_begin;
+        const uint32_t n_my_sell = n_sell > p ? (n_sell - p + P - 1) / P : 0;
+        const uint32_t n_items = n_my_hub_slices + n_my_sell;
+        auto next_item = [&]() -> uint32_t {
+            uint32_t q = 0;
+            if (lane == 0) q = atomicAdd(s_next, 1u);
+            return __shfl_sync(0xFFFFFFFFu, q, 0);
+        };
+        auto meta_of = [&](uint32_t item) -> uint4 {   // SELL items only; zero for hub items / past the end
+            if (item < n_my_hub_slices || item >= n_items) return make_uint4(0, 0, 0, 0);
+            return ld_stream_v4(r.sell_meta + (r.sell_begin + p + (uint64_t)P * (item - n_my_hub_slices)));
+        };
+        auto prefetch_item = [&](uint32_t item, const uint4& m) {
+            if (item >= n_items || item < n_my_hub_slices) return;
+            const uint32_t s1 = r.sell_begin + p + P * (item - n_my_hub_slices), a1 = (r.n_hub_slices + s1) * 32;
+            const uint32_t nrow = (m.z & 0xFFFFu) + (m.z >> 16);
+            if (lane == 0 && nrow) prefetch_l2(r.sell_codes + (((uint64_t)m.y << 32) | m.x), nrow * 128u);
+            if (lane == 1) prefetch_l2(r.stat + a1, 128u);
+            if (lane == 2) prefetch_l2(r.deg + a1, 128u);
+            if (lane == 3) prefetch_l2(r.ws + a1, 128u);
+            if (lane == 4) prefetch_l2(r.habit + a1, 512u);
+        };
+        uint32_t it0 = next_item(), it1 = next_item();
+        uint4 meta = meta_of(it0), meta1 = meta_of(it1);
+        prefetch_item(it0, meta);
+        if (n_my_hub_slices) {                         // first hub unit of this warp
+            const uint32_t hs = r.hub_begin + p, u = r.hub_unit_begin[hs] + warp;
+            if (u < r.hub_unit_begin[hs + 1]) {
+                const uint4 ua = ld_stream_v4(r.hub_units + 2 * (size_t)u);
+                const uint32_t rows = (ua.z & 0xFFu) + ((ua.z >> 8) & 0xFFu);
+                if (lane == 0 && rows) prefetch_l2(r.hub_codes + (((uint64_t)ua.y << 32) | ua.x), rows * 128u);
+            }
+        }
         mbar_wait(s_bar, phase);
         phase ^= 1u;
 
@@ -372,8 +410,6 @@ day_kernel(const __grid_constant__ RepArray reps, uint32_t R, uint32_t P, uint32
         // 1 024 links (layout.h); a warp takes a unit, its 32 lanes take 32 contiguous chunks of it, and the unit's
         // counts of modes 1..3 are added to the hub's entry of a small global scratch.  The hub slices are finished
         // below like any other slice, so no warp waits for another here and the biggest hubs spread over many warps.
-        const uint32_t n_own_hub = r.hub_end - r.hub_begin;
-        const uint32_t n_my_hub_slices = n_own_hub > p ? (n_own_hub - p + P - 1) / P : 0;
         for (uint32_t k = 0; k < n_my_hub_slices; ++k) {
             const uint32_t hs = r.hub_begin + p + P * k;
             const uint32_t u_end = r.hub_unit_begin[hs + 1];
@@ -404,33 +440,11 @@ day_kernel(const __grid_constant__ RepArray reps, uint32_t R, uint32_t P, uint32
         // 3. work items handed out by a block-wide counter: first this part's hub slices (finish only), then its
         // SELL slices p + P*k: one lane per agent.  The slice record is read two items ahead, and the next slice is
         // pulled into L2 (its link codes and its agents' state) by TMA prefetches while this one is processed.
-        const uint32_t n_sell = r.sell_end - r.sell_begin;
-        const uint32_t n_my_sell = n_sell > p ? (n_sell - p + P - 1) / P : 0;
-        const uint32_t n_items = n_my_hub_slices + n_my_sell;
-        auto next_item = [&]() -> uint32_t {
-            uint32_t q = 0;
-            if (lane == 0) q = atomicAdd(s_next, 1u);
-            return __shfl_sync(0xFFFFFFFFu, q, 0);
-        };
-        auto meta_of = [&](uint32_t item) -> uint4 {   // SELL items only; zero for hub items / past the end
-            if (item < n_my_hub_slices || item >= n_items) return make_uint4(0, 0, 0, 0);
-            return ld_stream_v4(r.sell_meta + (r.sell_begin + p + (uint64_t)P * (item - n_my_hub_slices)));
-        };
         LaneStats st{0, 0, 0, 0, 0, 0};
-        uint32_t it0 = next_item(), it1 = next_item();
-        uint4 meta = meta_of(it0), meta1 = meta_of(it1);
         while (it0 < n_items) {
             const uint32_t it2 = next_item();
             const uint4 meta2 = meta_of(it2);
-            if (it1 < n_items && it1 >= n_my_hub_slices) {
-                const uint32_t s1 = r.sell_begin + p + P * (it1 - n_my_hub_slices), a1 = (r.n_hub_slices + s1) * 32;
-                const uint32_t nrow = (meta1.z & 0xFFFFu) + (meta1.z >> 16);
-                if (lane == 0 && nrow) prefetch_l2(r.sell_codes + (((uint64_t)meta1.y << 32) | meta1.x), nrow * 128u);
-                if (lane == 1) prefetch_l2(r.stat + a1, 128u);
-                if (lane == 2) prefetch_l2(r.deg + a1, 128u);
-                if (lane == 3) prefetch_l2(r.ws + a1, 128u);
-                if (lane == 4) prefetch_l2(r.habit + a1, 512u);
-            }
+            prefetch_item(it1, meta1);
             if (it0 < n_my_hub_slices) {              // finish one hub slice: counts come from the scratch
                 const uint32_t hs = r.hub_begin + p + P * it0, agent = hs * 32 + lane;
                 uint4* cnt = reinterpret_cast<uint4*>(r.hub_cnt + (size_t)agent * 8);
