@@ -161,3 +161,41 @@ def test_full_size_properties_1m():
     assert not np.any((st["current_mode"] == 2) & (pop["owns_bike"] == 0))
     assert not np.any((st["current_mode"] >= 2) & (pop["commute"] == 2))  # Distant commute: Car / PT only
     g.close()
+
+
+def test_more_replicas_than_one_launch_holds():
+    """70 replicas in one handle: the day kernel takes 64 replica descriptors per launch (kernel parameters), so this
+    steps with two launches per weekday; 6 subcultures exercise the shared-memory-atomic statistics path (S > 4)."""
+    w = mb.weather_pattern(25, seed=8, p_good_given_good=0.6, p_good_given_bad=0.5)
+    pops = [mb.synth_population(400 + 7 * r, 6, 3, 3, 4, seed=100 + r) for r in range(70)]
+    tabs = [mb.synth_tables(6, 3, 400 + 7 * r, seed=100 + r) for r in range(70)]
+    g = mb.Simulation(pops, tabs, PRM)
+    days, rows = g.run(w)
+    ms, launches = g.last_run_stats()
+    assert launches == 2 * (mb.run_rows(25) - 1)
+    for r in (0, 1, 33, 63, 64, 69):
+        o = OracleSimulation(pops[r], tabs[r], PRM)
+        d2, r2 = o.run(w)
+        assert np.array_equal(rows[r], r2), f"replica {r}"
+        assert_state_equal(g.get_state(r), o.get_state(), f"replica {r}")
+    g.close()
+
+
+def test_many_neighbourhoods_and_tiny_groups():
+    """300 neighbourhoods over 3 000 agents: groups of ~10 agents (most slices are padding), neighbourhoods with a single
+    resident or none (no neighbour links, empty lists), a 50-way table in shared memory."""
+    n, S, H = 3000, 5, 300
+    pop = mb.synth_population(n, S, H, 3, 2, seed=13)
+    tab = random_tables(S, H, n, 13)
+    w = mb.weather_pattern(30, seed=13, p_good_given_good=0.5, p_good_given_bad=0.5)
+    lockstep(pop, tab, PRM, w, 30)
+
+
+def test_population_above_shared_memory_capacity():
+    """1.3M agents do not fit the staged vector (914k): a third of the agents are 'cold' and their modes are gathered
+    from L2; 4 weekdays against the oracle, full state."""
+    n = 1_300_000
+    pop = mb.synth_population(n, 4, 10, 5, 10, seed=21)
+    tab = mb.synth_tables(4, 10, n, seed=21)
+    w = np.array([0, 1, 1, 0, 1], np.uint8)
+    lockstep(pop, tab, PRM, w, 5, check_every=2)
