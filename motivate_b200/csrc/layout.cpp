@@ -10,6 +10,19 @@ namespace mvb {
 
 namespace {
 inline uint32_t round_up(uint32_t v, uint32_t m) { return (v + m - 1) / m * m; }
+
+// Stable counting sort of v[b, e) by key DESCENDING (keys <= max_key): elements with equal keys keep their order.
+template <class KeyFn>
+void counting_sort_desc(std::vector<uint32_t>& v, size_t b, size_t e, uint32_t max_key, KeyFn key,
+                        std::vector<uint32_t>& tmp, std::vector<uint32_t>& cnt) {
+    if (e - b < 2) return;
+    cnt.assign((size_t)max_key + 2, 0);
+    for (size_t i = b; i < e; ++i) cnt[max_key - key(v[i]) + 1]++;
+    for (uint32_t k = 0; k <= max_key; ++k) cnt[k + 1] += cnt[k];
+    tmp.resize(e - b);
+    for (size_t i = b; i < e; ++i) tmp[cnt[max_key - key(v[i])]++] = v[i];
+    std::copy(tmp.begin(), tmp.end(), v.begin() + b);
+}
 }  // namespace
 
 int build_graph_layout(const mvb_population& pop, uint32_t H, uint32_t capacity_agents, GraphLayout& L) {
@@ -37,7 +50,9 @@ int build_graph_layout(const mvb_population& pop, uint32_t H, uint32_t capacity_
     }
     auto by_degree = [&](uint32_t a, uint32_t b) { return d[a] != d[b] ? d[a] > d[b] : a < b; };
     std::sort(hubs.begin(), hubs.end(), by_degree);
-    for (auto& g : groups) std::sort(g.begin(), g.end(), by_degree);
+    std::vector<uint32_t> tmp, cnt;
+    // groups hold ids in increasing order and degrees <= kHubDegree: a stable counting sort gives (degree desc, id asc)
+    for (auto& g : groups) counting_sort_desc(g, 0, g.size(), kHubDegree, [&](uint32_t a) { return (uint32_t)d[a]; }, tmp, cnt);
 
     // ---- hot set: all hubs + the highest-degree agents of every group, as many as fit ---------
     const uint32_t hub_pad = round_up((uint32_t)hubs.size(), 64);
@@ -90,15 +105,12 @@ int build_graph_layout(const mvb_population& pop, uint32_t H, uint32_t capacity_
         for (uint64_t x = nrp[i]; x < nrp[i + 1]; ++x) b += is_hot[pop.neighbour_col[x]];
         nsh[i] = a; nnh[i] = b;
     }
-    auto by_lists = [&](uint32_t a, uint32_t b) {
-        const uint64_t ha = nsh[a] + nnh[a], hb = nsh[b] + nnh[b];
-        if (ha != hb) return ha > hb;
-        if (d[a] != d[b]) return d[a] > d[b];
-        return a < b;
-    };
+    // order (hot length desc, degree desc, id asc): the groups are in (degree desc, id asc) order already, so one more
+    // stable pass by hot length does it, separately for the hot part and the cold part of a group
+    auto hot_len = [&](uint32_t a) { return nsh[a] + nnh[a]; };
     for (uint32_t h = 0; h < H; ++h) {
-        std::sort(groups[h].begin(), groups[h].begin() + take[h], by_lists);
-        std::sort(groups[h].begin() + take[h], groups[h].end(), by_lists);
+        counting_sort_desc(groups[h], 0, take[h], kHubDegree, hot_len, tmp, cnt);
+        counting_sort_desc(groups[h], take[h], groups[h].size(), kHubDegree, hot_len, tmp, cnt);
     }
 
     // ---- internal order ----------------------------------------------------------------------
