@@ -252,8 +252,8 @@ def main():
             print(f"bench.py: --gpus {args.gpus} needs torchrun with {args.gpus} ranks", file=sys.stderr)
             sys.exit(2)
     # rank 0 prints exactly one line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION writes it to stdout) out of it
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "WARN"):
+        os.environ["NCCL_DEBUG"] = "NONE"               # NCCL prints the banner at VERSION and at WARN
     import torch
     import torch.distributed as dist
 
