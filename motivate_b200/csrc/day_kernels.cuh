@@ -213,12 +213,18 @@ __device__ __forceinline__ void accumulate_block(const uint32_t* __restrict__ bl
         const uint32_t inc = (1u << ((__funnelshift_l(0u, w1, c1) >> 30) * 8u)) & ~0xFFu;
         if (1 < ds_c) acc_s += inc; else acc_n += inc;
     }
-    for (uint32_t k = 2; k < Kc; ++k) {
-        const uint32_t code = ld_stream_u32(cold + (size_t)k * 32);
-        if ((int)k < d_c) {
-            const uint32_t inc = (1u << ((top2_cold(g_vec, code) >> 30) * 8u)) & ~0xFFu;
-            if ((int)k < ds_c) acc_s += inc; else acc_n += inc;
-        }
+    for (uint32_t k = 2; k < Kc; k += 4) {                      // the rest of the cold list, four links at a time:
+        uint32_t c[4], w[4];                                    // all four codes, then all four gathers, then the counts
+#pragma unroll
+        for (int u = 0; u < 4; ++u) c[u] = k + u < Kc ? ld_stream_u32(cold + (size_t)(k + u) * 32) : 0u;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) w[u] = __ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(g_vec) + (c[u] >> 5)));
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if ((int)(k + u) < d_c) {
+                const uint32_t inc = (1u << ((__funnelshift_l(0u, w[u], c[u]) >> 30) * 8u)) & ~0xFFu;
+                if ((int)(k + u) < ds_c) acc_s += inc; else acc_n += inc;
+            }
     }
 }
 
