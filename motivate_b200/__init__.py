@@ -8,5 +8,6 @@ from .api import (BAD, CAR, CITY_COMMUTE, CYCLE, DEFAULT_GMM, DISTANT_COMMUTE, G
                   PUBLIC_TRANSPORT, STATS_FIXED, WALK, InterventionData, MotivateError, PopulationData,
                   Simulation, TablesData, comm_unique_id, make_params, partition_plan, params_dict, run_rows, synth_population,
                   synth_tables, weather_pattern)
+from .weather import make_pattern
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -237,8 +237,9 @@ def synth_tables(n_subcultures=4, n_neighbourhoods=10, n_agents=1_000_000, seed=
 
 
 def weather_pattern(n_days, seed=0, p_rain_day0=0.14, p_good_given_good=0.886, p_good_given_bad=0.699):
-    """Two-state Markov chain with the matrix of src/main.rs:73-85 (src/weather.rs:19-50), own seeded PRNG
-    (the reference's StdRng/HC-128 stream is not restated — SURVEY.md §8 f3)."""
+    """Two-state Markov chain with the matrix of src/main.rs:73-85 (src/weather.rs:19-50) from numpy's seeded PRNG:
+    benchmarks and tests that want several different sequences.  The rain sequence of a reference run (StdRng =
+    HC-128, zero seed) is `motivate_b200.weather.make_pattern`."""
     rng = np.random.default_rng(seed + 104729)
     u = rng.random(n_days)
     w = np.zeros(n_days, np.uint8)

@@ -3,6 +3,8 @@
 // output/output_{id}.csv) and the same `--generate` flag.  The replicas 1..=number_of_simulations, which the reference
 // spreads over rayon workers, go to the GPU as one batch and are stepped together, one launch per weekday.
 //   motivate_b200_run [--generate] [--dir DIR] [--device N] [--seed S]      (--dump prints the parsed configuration)
+//   motivate_b200_run --weather DAYS      prints the rain sequence `Weather::make_pattern` gives (0 Good / 1 Bad)
+//   motivate_b200_run --keystream N       prints N words of the zero-seed StdRng (HC-128) stream, for the known-answer test
 #include <sys/stat.h>
 
 #include <cstdio>
@@ -28,6 +30,16 @@ int main(int argc, char** argv) {
         else if (!strcmp(argv[i], "--dir") && i + 1 < argc) dir = argv[++i];
         else if (!strcmp(argv[i], "--device") && i + 1 < argc) device = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--seed") && i + 1 < argc) seed = strtoull(argv[++i], nullptr, 10);
+        else if (!strcmp(argv[i], "--weather") && i + 1 < argc) {
+            for (uint8_t w : make_pattern(strtoull(argv[++i], nullptr, 10))) putchar('0' + w);
+            putchar('\n');
+            return 0;
+        } else if (!strcmp(argv[i], "--keystream") && i + 1 < argc) {
+            const uint32_t zero[4] = {0, 0, 0, 0};
+            Hc128 rng(zero, zero);
+            for (unsigned long long k = strtoull(argv[++i], nullptr, 10); k > 0; --k) printf("%08x\n", rng.next_u32());
+            return 0;
+        }
         else { fprintf(stderr, "usage: %s [--generate] [--dir DIR] [--device N] [--seed S]\n", argv[0]); return 2; }
     }
     try {
@@ -76,7 +88,7 @@ int main(int argc, char** argv) {
             }
             fprintf(stderr, "Generating networks complete\n");
         }
-        const std::vector<uint8_t> weather = make_weather_pattern((size_t)365 * prm.total_years, seed);   // main.rs:84-85
+        const std::vector<uint8_t> weather = make_pattern((size_t)365 * prm.total_years);   // main.rs:73-85: the reference's own rain sequence
         std::vector<Prepared> reps;
         for (uint32_t id = 1; id <= prm.number_of_simulations; ++id) {                          // main.rs:89-121
             const std::string n = std::to_string(id);

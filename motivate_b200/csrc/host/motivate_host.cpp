@@ -162,6 +162,58 @@ std::vector<uint8_t> make_weather_pattern(size_t days, uint64_t seed) {
     return w;
 }
 
+// ---- StdRng of rand 0.5.3 = HC-128 (restated from the cipher's specification; see the header) ----------------
+static inline uint32_t rotr32(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
+static inline uint32_t rotl32(uint32_t x, int n) { return (x << n) | (x >> (32 - n)); }
+
+uint32_t Hc128::step() {
+    const uint32_t i = i_, j = i & 511u;
+    i_ = (i + 1) & 1023u;
+    const bool first = (i & 512u) == 0;
+    uint32_t* t = first ? p_ : q_;
+    const uint32_t* o = first ? q_ : p_;
+    const uint32_t a = t[(j - 3) & 511u], b = t[(j - 10) & 511u], c = t[(j - 511) & 511u];
+    const uint32_t g = first ? (rotr32(a, 10) ^ rotr32(c, 23)) + rotr32(b, 8) : (rotl32(a, 10) ^ rotl32(c, 23)) + rotl32(b, 8);
+    t[j] += g;
+    const uint32_t x = t[(j - 12) & 511u];
+    return (o[x & 0xFFu] + o[256 + ((x >> 16) & 0xFFu)]) ^ t[j];
+}
+
+Hc128::Hc128(const uint32_t key[4], const uint32_t iv[4]) {
+    std::vector<uint32_t> w(1280);
+    for (int k = 0; k < 8; ++k) { w[k] = key[k & 3]; w[8 + k] = iv[k & 3]; }
+    for (uint32_t i = 16; i < 1280; ++i) {
+        const uint32_t x = w[i - 2], y = w[i - 15];
+        w[i] = (rotr32(x, 17) ^ rotr32(x, 19) ^ (x >> 10)) + w[i - 7] + (rotr32(y, 7) ^ rotr32(y, 18) ^ (y >> 3)) + w[i - 16] + i;
+    }
+    for (int k = 0; k < 512; ++k) { p_[k] = w[256 + k]; q_[k] = w[768 + k]; }
+    for (uint32_t k = 0; k < 1024; ++k) {                       // outputs of the first 1024 steps replace the table words
+        uint32_t* t = (k & 512u) == 0 ? p_ : q_;
+        const uint32_t s = step();
+        t[k & 511u] = s;
+    }
+    i_ = 0;
+}
+
+static Hc128 hc128_from_seed(const uint8_t seed[32]) {
+    uint32_t w[8];
+    for (int k = 0; k < 8; ++k)
+        w[k] = (uint32_t)seed[4 * k] | (uint32_t)seed[4 * k + 1] << 8 | (uint32_t)seed[4 * k + 2] << 16 | (uint32_t)seed[4 * k + 3] << 24;
+    return Hc128(w, w + 4);
+}
+StdRng::StdRng(const uint8_t seed[32]) : core_(hc128_from_seed(seed)) {}
+
+std::vector<uint8_t> make_pattern(size_t days, double good_given_good, double good_given_bad, double chance_of_rain) {
+    static const uint8_t zero_seed[32] = {0};
+    StdRng rng(zero_seed);                                       // weather.rs:24
+    std::vector<uint8_t> w(days, 0);
+    if (!days) return w;
+    w[0] = rng.gen_f64() > chance_of_rain ? 0 : 1;               // weather.rs:28-32
+    for (size_t i = 1; i < days; ++i)                            // weather.rs:35-48
+        w[i] = rng.gen_f64() < (w[i - 1] == 0 ? good_given_good : good_given_bad) ? 0 : 1;
+    return w;
+}
+
 void read_network(const std::string& path, uint32_t n, std::vector<uint64_t>& rowptr, std::vector<uint32_t>& col) {
     const yaml_lite::Node d = yaml_lite::parse_file(path);                      // HashMap<u32, Vec<u32>>
     std::vector<const yaml_lite::Node*> rows(n, nullptr);

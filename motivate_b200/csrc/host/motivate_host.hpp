@@ -5,7 +5,7 @@
 //   Parameters / Parameters::from_file        src/main.rs:185-228
 //   Scenario / Scenario::from_file             src/scenario.rs:11-45 (+ neighbourhood.rs:13-31, subculture.rs:9-14)
 //   Intervention, NeighbourhoodChange, SubcultureChange      src/intervention.rs:6-52
-//   Weather::make_pattern                      src/weather.rs:19-50 (matrix of src/main.rs:73-85; own seeded PRNG)
+//   Weather::make_pattern                      src/weather.rs:19-50 (matrix of src/main.rs:73-85; StdRng = HC-128 restated)
 //   read_network / write_network               src/main.rs:135-148, 173-179
 //   load_unlinked_agents_from_file / save_agents   src/agent_generation.rs:26-63
 //   link_agents_to_neighbours                  src/simulation.rs:165-189
@@ -85,6 +85,31 @@ struct ResolvedIntervention {                      // tables and ownership that 
     mvb_tables tables() const { return mvb_tables{S, H, supportiveness.data(), capacity.data(), desirability.data()}; }
 };
 
+// `StdRng::from_seed` of rand 0.5.3 (Cargo.lock), which weather.rs:24 draws from: the HC-128 stream cipher, key = seed
+// bytes 0-15, IV = bytes 16-31; `next_u64` = two keystream words, low first; `gen::<f64>()` = (u64 >> 11) * 2^-53.
+// The crate is not under /root/reference: HC-128 is restated from its specification and pinned on the
+// specification's zero key / IV keystream (tests/test_weather.py).
+class Hc128 {
+public:
+    Hc128(const uint32_t key[4], const uint32_t iv[4]);
+    uint32_t next_u32() { return step(); }
+private:
+    uint32_t step();
+    uint32_t p_[512], q_[512], i_ = 0;
+    friend class StdRng;
+};
+class StdRng {
+public:
+    explicit StdRng(const uint8_t seed[32]);
+    uint64_t next_u64() { const uint64_t lo = core_.next_u32(); return lo | (uint64_t)core_.next_u32() << 32; }
+    double gen_f64() { return (double)(next_u64() >> 11) * (1.0 / 9007199254740992.0); }
+private:
+    Hc128 core_;
+};
+// Weather::make_pattern (src/weather.rs:19-50) with the matrix of src/main.rs:73-85: the rain sequence of a reference run.
+std::vector<uint8_t> make_pattern(size_t days, double good_given_good = 0.886, double good_given_bad = 0.699,
+                                  double chance_of_rain = 0.14);
+// Same chain from this repo's own seeded generator (benchmarks and tests that want several different sequences).
 std::vector<uint8_t> make_weather_pattern(size_t days, uint64_t seed = 0);
 void read_network(const std::string& path, uint32_t n_agents, std::vector<uint64_t>& rowptr, std::vector<uint32_t>& col);
 void write_network(const std::string& path, const std::vector<uint64_t>& rowptr, const std::vector<uint32_t>& col);
