@@ -406,7 +406,9 @@ def e2e(args, pops, tabs, prm, w, n_days, local_rank, world, dist, torch):
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     sim = mb.Simulation(pops, tabs, prm, device=local_rank)
+    t1 = time.perf_counter()
     days, rows = sim.run(w, n_days)
+    t2 = time.perf_counter()
     sim.close()
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
@@ -419,6 +421,7 @@ def e2e(args, pops, tabs, prm, w, n_days, local_rank, world, dist, torch):
     return {"value": args.agents * args.replicas * weekdays / dt, "unit": UNIT,
             "h2d_bytes_per_step": h2d / weekdays, "d2h_bytes_per_step": d2h / weekdays,
             "weekdays": weekdays, "seconds": dt,
+            "seconds_rank0": {"create": t1 - t0, "run": t2 - t1, "destroy": t0 + dt - t2},
             "what": "mvb_create_batch (H2D of populations from pinned host memory) + mvb_run (rows D2H) + mvb_destroy"}
 
 

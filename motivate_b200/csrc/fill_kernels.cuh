@@ -22,6 +22,49 @@ struct FillArgs {
     const uint64_t* hub_off; const uint4* hub_deg; uint32_t* hub_codes;
 };
 
+// One warp per agent: how many of its social / neighbour links point at agents whose mode will sit in shared memory
+// (layout.h, layout_count_hot).  This is the one step of the layout that touches every link, so it runs here, on
+// the CSR the fill kernels need anyway.  Also the range check of the link targets: any target >= N sets *bad.
+__global__ void count_hot_kernel(uint32_t N, const uint64_t* __restrict__ s_rowptr, const uint32_t* __restrict__ s_col,
+                                 const uint64_t* __restrict__ n_rowptr, const uint32_t* __restrict__ n_col,
+                                 const uint8_t* __restrict__ is_hot, uint32_t* __restrict__ nsh, uint32_t* __restrict__ nnh,
+                                 uint32_t* __restrict__ bad) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < N; i += warps) {
+        uint32_t a = 0, b = 0, oob = 0;
+        for (uint64_t x = s_rowptr[i] + lane; x < s_rowptr[i + 1]; x += 32) {
+            const uint32_t t = s_col[x];
+            if (t < N) a += is_hot[t]; else oob = 1;
+        }
+        for (uint64_t x = n_rowptr[i] + lane; x < n_rowptr[i + 1]; x += 32) {
+            const uint32_t t = n_col[x];
+            if (t < N) b += is_hot[t]; else oob = 1;
+        }
+        a = __reduce_add_sync(0xFFFFFFFFu, a);
+        b = __reduce_add_sync(0xFFFFFFFFu, b);
+        oob = __reduce_or_sync(0xFFFFFFFFu, oob);
+        if (lane == 0) { nsh[i] = a; nnh[i] = b; if (oob) atomicOr(bad, 1u); }
+    }
+}
+
+// Link code of every possible target (layout.h: word byte offset << 5 | shift, | 1 if hot): a hot agent is addressed
+// by its place in the staged vector (ranges), a cold one by its internal slot.  Same rule as layout_finish.
+__global__ void tcode_kernel(uint32_t N_pad, const uint32_t* __restrict__ int2ext, const StageRange* __restrict__ ranges,
+                             uint32_t n_ranges, const uint8_t* __restrict__ is_hot, uint32_t* __restrict__ tcode) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= N_pad) return;
+    const uint32_t e = int2ext[t];
+    if (e == kInvalid) return;
+    uint32_t pos = t, hot = is_hot[e];
+    if (hot) {
+        uint32_t lo = 0, hi = n_ranges;                       // ranges are in increasing src_word order: last one starting at or before t
+        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (ranges[mid].src_word * 16u <= t) lo = mid; else hi = mid; }
+        pos = ranges[lo].dst_word * 16u + (t - ranges[lo].src_word * 16u);
+    }
+    tcode[e] = ((pos >> 4) << 7 | (30u - 2u * (pos & 15u))) | hot;
+}
+
 __device__ __forceinline__ void put_hot(uint32_t* blk, uint32_t K, uint32_t lane, uint32_t k, uint32_t code) {
     const uint32_t K4 = K >> 2;
     if (k < 4 * K4) blk[(size_t)(k >> 2) * 128 + lane * 4 + (k & 3u)] = code;

@@ -25,25 +25,31 @@ void counting_sort_desc(std::vector<uint32_t>& v, size_t b, size_t e, uint32_t m
 }
 }  // namespace
 
-int build_graph_layout(const mvb_population& pop, uint32_t H, uint32_t capacity_agents, GraphLayout& L) {
+int layout_begin(const mvb_population& pop, uint32_t H, uint32_t capacity_agents, GraphLayout& L, LayoutWork& W) {
     const uint32_t N = pop.n_agents;
     const uint64_t* srp = pop.social_rowptr;
     const uint64_t* nrp = pop.neighbour_rowptr;
     L = GraphLayout();
+    W = LayoutWork();
     L.N = N;
     L.Es = srp[N];
     L.En = nrp[N];
     if (capacity_agents < 64 || capacity_agents % 64) { set_error("internal: bad shared-memory capacity %u", capacity_agents); return MVB_ERR_ARG; }
 
     // ---- degrees, hubs, neighbourhood groups -------------------------------------------------
-    std::vector<uint64_t> d(N);
+    std::vector<uint64_t>& d = W.d;
+    d.resize(N);
+    std::vector<uint32_t> gsize(H, 0);
     for (uint32_t i = 0; i < N; ++i) {
         const uint64_t ds = srp[i + 1] - srp[i], dn = nrp[i + 1] - nrp[i];
         if (ds > 0xFFFFFFFFull || dn > 0xFFFFFFFFull) { set_error("agent %u has more than 2^32 links", i); return MVB_ERR_ARG; }
         d[i] = ds + dn;
+        if (d[i] <= kHubDegree) gsize[pop.neighbourhood[i]]++;
     }
-    std::vector<uint32_t> hubs;
-    std::vector<std::vector<uint32_t>> groups(H);
+    std::vector<uint32_t>& hubs = W.hubs;
+    std::vector<std::vector<uint32_t>>& groups = W.groups;
+    groups.resize(H);
+    for (uint32_t h = 0; h < H; ++h) groups[h].reserve(gsize[h]);
     for (uint32_t i = 0; i < N; ++i) {
         if (d[i] > kHubDegree) hubs.push_back(i);
         else groups[pop.neighbourhood[i]].push_back(i);
@@ -55,14 +61,17 @@ int build_graph_layout(const mvb_population& pop, uint32_t H, uint32_t capacity_
     for (auto& g : groups) counting_sort_desc(g, 0, g.size(), kHubDegree, [&](uint32_t a) { return (uint32_t)d[a]; }, tmp, cnt);
 
     // ---- hot set: all hubs + the highest-degree agents of every group, as many as fit ---------
-    const uint32_t hub_pad = round_up((uint32_t)hubs.size(), 64);
-    std::vector<uint32_t> take(H, 0);                    // hot agents of group h (a prefix in degree order)
-    std::vector<uint32_t> gpad(H);
+    const uint32_t hub_pad = W.hub_pad = round_up((uint32_t)hubs.size(), 64);
+    std::vector<uint32_t>& take = W.take;               // hot agents of group h (a prefix in degree order)
+    std::vector<uint32_t>& gpad = W.gpad;
+    take.assign(H, 0);
+    gpad.resize(H);
     uint64_t total = hub_pad;
     for (uint32_t h = 0; h < H; ++h) { gpad[h] = round_up((uint32_t)groups[h].size(), 64); total += gpad[h]; }
     if (total >= (1ull << 29)) { set_error("too many agents for the word index of a link code"); return MVB_ERR_ARG; }
     L.N_pad = (uint32_t)total;
-    const bool all_hot = L.N_pad <= capacity_agents;
+    const bool all_hot = W.all_hot = L.N_pad <= capacity_agents;
+    W.capacity_agents = capacity_agents;
     if (all_hot) {
         for (uint32_t h = 0; h < H; ++h) take[h] = (uint32_t)groups[h].size();
     } else {
@@ -91,23 +100,49 @@ int build_graph_layout(const mvb_population& pop, uint32_t H, uint32_t capacity_
             take[h] += extra; used += extra;
         }
     }
-    std::vector<uint8_t> is_hot(N, 0);
+    std::vector<uint8_t>& is_hot = W.is_hot;
+    is_hot.assign(N, 0);
     if (all_hot || hub_pad <= capacity_agents) for (uint32_t e : hubs) is_hot[e] = 1;
     else for (uint32_t k = 0; k < std::min<size_t>(hubs.size(), capacity_agents); ++k) is_hot[hubs[k]] = 1;
     for (uint32_t h = 0; h < H; ++h)
         for (uint32_t k = 0; k < take[h]; ++k) is_hot[groups[h][k]] = 1;
+    return MVB_OK;
+}
 
-    // hot / cold link counts per agent; order each group's hot part and cold part by (hot, cold) length
-    std::vector<uint32_t> nsh(N, 0), nnh(N, 0);          // social / neighbour links whose target is hot
+void layout_count_hot(const mvb_population& pop, LayoutWork& W) {
+    const uint32_t N = pop.n_agents;
+    W.nsh_own.assign(N, 0);
+    W.nnh_own.assign(N, 0);
     for (uint32_t i = 0; i < N; ++i) {
         uint32_t a = 0, b = 0;
-        for (uint64_t x = srp[i]; x < srp[i + 1]; ++x) a += is_hot[pop.social_col[x]];
-        for (uint64_t x = nrp[i]; x < nrp[i + 1]; ++x) b += is_hot[pop.neighbour_col[x]];
-        nsh[i] = a; nnh[i] = b;
+        for (uint64_t x = pop.social_rowptr[i]; x < pop.social_rowptr[i + 1]; ++x) a += W.is_hot[pop.social_col[x]];
+        for (uint64_t x = pop.neighbour_rowptr[i]; x < pop.neighbour_rowptr[i + 1]; ++x) b += W.is_hot[pop.neighbour_col[x]];
+        W.nsh_own[i] = a; W.nnh_own[i] = b;
     }
+    W.nsh = W.nsh_own.data();
+    W.nnh = W.nnh_own.data();
+}
+
+int layout_finish(const mvb_population& pop, LayoutWork& W, GraphLayout& L, bool want_tcode) {
+    const uint32_t N = pop.n_agents, H = (uint32_t)W.groups.size();
+    const uint64_t* srp = pop.social_rowptr;
+    const uint64_t* nrp = pop.neighbour_rowptr;
+    const uint32_t* nsh = W.nsh;
+    const uint32_t* nnh = W.nnh;
+    std::vector<uint64_t>& d = W.d;
+    std::vector<uint32_t>& hubs = W.hubs;
+    std::vector<std::vector<uint32_t>>& groups = W.groups;
+    const std::vector<uint32_t>& take = W.take;
+    const uint32_t hub_pad = W.hub_pad;
+
+    // hot | cold << 16 list lengths of the agents that are not hubs (both <= kHubDegree)
+    std::vector<uint32_t> hc(N, 0);
+    for (uint32_t i = 0; i < N; ++i)
+        if (d[i] <= kHubDegree) { const uint32_t hl = nsh[i] + nnh[i]; hc[i] = hl | ((uint32_t)d[i] - hl) << 16; }
     // order (hot length desc, degree desc, id asc): the groups are in (degree desc, id asc) order already, so one more
     // stable pass by hot length does it, separately for the hot part and the cold part of a group
-    auto hot_len = [&](uint32_t a) { return nsh[a] + nnh[a]; };
+    std::vector<uint32_t> tmp, cnt;
+    auto hot_len = [&](uint32_t a) { return hc[a] & 0xFFFFu; };
     for (uint32_t h = 0; h < H; ++h) {
         counting_sort_desc(groups[h], 0, take[h], kHubDegree, hot_len, tmp, cnt);
         counting_sort_desc(groups[h], take[h], groups[h].size(), kHubDegree, hot_len, tmp, cnt);
@@ -117,42 +152,46 @@ int build_graph_layout(const mvb_population& pop, uint32_t H, uint32_t capacity_
     std::vector<uint32_t> gstart(H);
     {
         uint64_t at = hub_pad;
-        for (uint32_t h = 0; h < H; ++h) { gstart[h] = (uint32_t)at; at += gpad[h]; }
+        for (uint32_t h = 0; h < H; ++h) { gstart[h] = (uint32_t)at; at += W.gpad[h]; }
     }
     L.n_hub_slices = hub_pad / 32;
     L.n_sell_slices = (L.N_pad - hub_pad) / 32;
     L.int2ext.assign(L.N_pad, kInvalid);
-    L.ext2int.assign(N, kInvalid);
     for (uint32_t k = 0; k < hubs.size(); ++k) L.int2ext[k] = hubs[k];
-    for (uint32_t h = 0; h < H; ++h)
-        for (uint32_t k = 0; k < groups[h].size(); ++k) L.int2ext[gstart[h] + k] = groups[h][k];
-    for (uint32_t s = 0; s < L.N_pad; ++s)
-        if (L.int2ext[s] != kInvalid) L.ext2int[L.int2ext[s]] = s;
+    for (uint32_t h = 0; h < H; ++h) std::copy(groups[h].begin(), groups[h].end(), L.int2ext.begin() + gstart[h]);
 
-    // ---- staged ranges: position of an internal slot in the shared-memory vector, or kInvalid if cold
-    std::vector<uint32_t> hot_pos(L.N_pad, kInvalid);
+    // ---- staged ranges: which pieces of the packed vector go to shared memory, and where
     uint32_t staged = 0;
     auto add_range = [&](uint32_t start, uint32_t count) {       // both multiples of 64
         if (!count) return;
         L.ranges.push_back(StageRange{start / 16, count / 16, staged / 16, 0});
-        for (uint32_t k = 0; k < count; ++k) hot_pos[start + k] = staged + k;
         staged += count;
     };
-    if (all_hot) {
+    if (W.all_hot) {
         add_range(0, L.N_pad);
     } else {
-        add_range(0, std::min(hub_pad, capacity_agents));
+        add_range(0, std::min(hub_pad, W.capacity_agents));
         for (uint32_t h = 0; h < H; ++h) add_range(gstart[h], take[h]);     // take[h] is a multiple of 64 here
     }
     L.hot_words = staged / 16;
 
     // ---- link codes ---------------------------------------------------------------------------
-    // code of every possible target, computed once; the arrays of codes are filled on the device (fill_kernels.cuh)
-    L.tcode.resize(N);
-    for (uint32_t e = 0; e < N; ++e) {
-        const uint32_t t = L.ext2int[e];
-        const uint32_t pos = is_hot[e] ? hot_pos[t] : t;
-        L.tcode[e] = ((pos >> 4) << 7 | (30u - 2u * (pos & 15u))) | (is_hot[e] ? 1u : 0u);
+    // code of every possible target; the arrays of codes are filled on the device (fill_kernels.cuh).  With
+    // want_tcode == false the caller computes this table on the device as well (tcode_kernel, same rule).
+    if (want_tcode) {
+        L.tcode.resize(N);
+        for (const StageRange& r : L.ranges)
+            for (uint32_t t = r.src_word * 16; t < (r.src_word + r.n_words) * 16; ++t) {
+                const uint32_t e = L.int2ext[t];
+                if (e == kInvalid || !W.is_hot[e]) continue;
+                const uint32_t pos = r.dst_word * 16 + (t - r.src_word * 16);
+                L.tcode[e] = ((pos >> 4) << 7 | (30u - 2u * (pos & 15u))) | 1u;
+            }
+        for (uint32_t t = 0; t < L.N_pad; ++t) {
+            const uint32_t e = L.int2ext[t];
+            if (e == kInvalid || W.is_hot[e]) continue;
+            L.tcode[e] = (t >> 4) << 7 | (30u - 2u * (t & 15u));
+        }
     }
     // hub blocks: lane l of a block holds links [l*K, (l+1)*K) of what is left of the list
     const uint32_t n_hub_rows = L.n_hub_slices * 32;
@@ -193,9 +232,8 @@ int build_graph_layout(const mvb_population& pop, uint32_t H, uint32_t capacity_
         for (uint32_t l = 0; l < 32; ++l) {
             const uint32_t e = L.int2ext[base + l];
             if (e == kInvalid) continue;
-            const uint32_t nh = nsh[e] + nnh[e];
-            K = std::max(K, nh);
-            Kc = std::max<uint32_t>(Kc, (uint32_t)d[e] - nh);
+            K = std::max(K, hc[e] & 0xFFFFu);
+            Kc = std::max(Kc, hc[e] >> 16);
         }
         L.sell_off[s] = off;
         L.sell_K[s] = K | Kc << 16;
@@ -207,6 +245,13 @@ int build_graph_layout(const mvb_population& pop, uint32_t H, uint32_t capacity_
     for (uint32_t s = 0; s < L.n_sell_slices; ++s)
         L.sell_meta[s] = uint4x{(uint32_t)L.sell_off[s], (uint32_t)(L.sell_off[s] >> 32), L.sell_K[s], 0};
     return MVB_OK;
+}
+
+int build_graph_layout(const mvb_population& pop, uint32_t H, uint32_t capacity_agents, GraphLayout& L) {
+    LayoutWork W;
+    if (int rc = layout_begin(pop, H, capacity_agents, L, W)) return rc;
+    layout_count_hot(pop, W);
+    return layout_finish(pop, W, L, true);
 }
 
 void partition_slices(const GraphLayout& L, uint32_t world, std::vector<uint32_t>& bounds) {

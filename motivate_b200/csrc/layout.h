@@ -74,9 +74,9 @@ struct GraphLayout {
     uint32_t hot_words = 0;        // staged vector size in u32 words
     uint64_t Es = 0, En = 0;       // link counts of the source graph
     std::vector<uint32_t> int2ext; // [N_pad] internal slot -> caller's agent id, kInvalid for padding
-    std::vector<uint32_t> ext2int; // [N]
     std::vector<uint32_t> tcode;   // [N] link code of every possible target (caller's id) | 1 if the target is hot
-                                   // (the low bit is free: the shift field of a code is even); input of the fill kernels
+                                   // (the low bit is free: the shift field of a code is even); input of the fill kernels.
+                                   // Only filled by build_graph_layout: mvb_create* makes it on the device (tcode_kernel)
     std::vector<StageRange> ranges;
     // hubs
     std::vector<uint64_t> hub_off;         // [n_hub_slices*32] offset of the hub's first block in hub_codes (u32 units)
@@ -95,6 +95,28 @@ struct GraphLayout {
 // and the per-agent length words (deg) are written on the device by fill_kernels.cuh from the caller's CSR.
 // capacity_agents: how many agents of the mode vector fit in shared memory (multiple of 64, >= 64).
 // Returns MVB_OK or an error code (message via set_error).
+//
+// The work comes in three steps so that mvb_create* can hand the middle one, the only one that touches every link,
+// to the GPU (count_hot_kernel) while host threads do the other two for many graphs at once:
+//   layout_begin      O(N): degrees, hubs, neighbourhood groups in degree order, which agents are hot
+//   layout_count_hot  O(E): per agent, how many of its social / neighbour links point at hot agents
+//   layout_finish     O(N): final order, slices, offsets, hub blocks
+struct LayoutWork {                        // what layout_begin leaves for the later steps
+    std::vector<uint64_t> d;               // [N] total links
+    std::vector<uint32_t> hubs;            // hub ids, (degree desc, id asc)
+    std::vector<std::vector<uint32_t>> groups;   // per neighbourhood: ids of the other agents, (degree desc, id asc)
+    std::vector<uint32_t> take, gpad;      // per group: hot agents (a prefix), size rounded up to 64
+    uint32_t hub_pad = 0, capacity_agents = 0;
+    bool all_hot = false;
+    std::vector<uint8_t> is_hot;           // [N]
+    const uint32_t* nsh = nullptr;         // [N] social links with a hot target   (set by layout_count_hot, or by the
+    const uint32_t* nnh = nullptr;         // [N] neighbour links with a hot target  caller from the device's counts)
+    std::vector<uint32_t> nsh_own, nnh_own;
+};
+int layout_begin(const mvb_population& pop, uint32_t n_neighbourhoods, uint32_t capacity_agents, GraphLayout& out, LayoutWork& work);
+void layout_count_hot(const mvb_population& pop, LayoutWork& work);
+int layout_finish(const mvb_population& pop, LayoutWork& work, GraphLayout& out, bool want_tcode);
+// all three on the host (mvb_partition_plan, mvb_create_partitioned)
 int build_graph_layout(const mvb_population& pop, uint32_t n_neighbourhoods, uint32_t capacity_agents,
                        GraphLayout& out);
 

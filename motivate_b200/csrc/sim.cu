@@ -10,8 +10,12 @@
 #include <numeric>
 #include <thread>
 #include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <mutex>
 #include <cstdlib>
 #include <cstring>
+#include <list>
 #include <memory>
 #include <new>
 #include <vector>
@@ -25,21 +29,51 @@ using namespace mvb;
 
 namespace {
 
-struct DevBuf {                       // owning device allocation
+struct DevBuf {                       // device memory: its own allocation, or a piece of an Arena
     void* p = nullptr;
     size_t bytes = 0;
+    bool owned = true;
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
-    DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes) { o.p = nullptr; o.bytes = 0; }
-    ~DevBuf() { if (p) cudaFree(p); }
+    DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes), owned(o.owned) { o.p = nullptr; o.bytes = 0; }
+    ~DevBuf() { if (p && owned) cudaFree(p); }
     cudaError_t alloc(size_t n) {
-        if (p) { cudaFree(p); p = nullptr; }
+        if (p && owned) cudaFree(p);
+        p = nullptr; owned = true;
         bytes = n;
         return cudaMalloc(&p, n ? n : 1);
     }
+    void view(void* ptr, size_t n) {
+        if (p && owned) cudaFree(p);
+        p = ptr; bytes = n; owned = false;
+    }
     template <class T> T* as() const { return (T*)p; }
 };
+
+// Device memory of a handle: a few large allocations cut into 256-byte-aligned pieces.  On a B200 box one 10 GB
+// cudaMalloc + cudaFree costs about 5 ms, the same memory as 128 separate buffers 100-300 ms
+// (tools/microbench_alloc.cu), and tear-down of many replicas was dominated by it.
+struct Arena {
+    std::vector<DevBuf> chunks;
+    size_t used = 0, chunk_bytes = 256u << 20;                 // size of the next chunk (a request larger than it gets its own)
+    static size_t piece(size_t n) { return (n + 255) & ~(size_t)255; }
+    cudaError_t carve(DevBuf& b, size_t n) {
+        const size_t need = piece(n);
+        if (chunks.empty() || used + need > chunks.back().bytes) {
+            DevBuf c;
+            cudaError_t e = c.alloc(std::max(chunk_bytes, need));
+            if (e != cudaSuccess) return e;
+            chunks.push_back(std::move(c));
+            used = 0;
+            if (chunks.size() == 1) chunk_bytes = std::max<size_t>(256u << 20, chunk_bytes / 8);   // an estimate that fell short grows in steps
+        }
+        b.view((char*)chunks.back().p + used, n);
+        used += need;
+        return cudaSuccess;
+    }
+};
+#define MVB_CARVE(arena, buf, n) MVB_CUDA((arena).carve((buf), (n)))
 
 // The link graph of one population in device layout (layout.h), shareable between replicas
 // (scenario sweeps over one population pass the same graph + neighbourhood arrays).
@@ -105,6 +139,7 @@ struct mvb_sim {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     mvb_params prm{};
+    Arena mem;                           // device memory of the graphs and replicas
     std::vector<Replica> reps;
     DevBuf d_reps;                       // RepDev[R]
     std::vector<RepDev> h_reps;
@@ -238,6 +273,120 @@ int upload(DevBuf& b, const std::vector<T>& v, cudaStream_t st) {
     return MVB_OK;
 }
 
+// Device scratch of the create path: comes from the device's stream-ordered pool and goes back to it in stream
+// order, so releasing it never waits for the device.
+struct TmpBuf {
+    void* p = nullptr;
+    cudaStream_t st = nullptr;
+    TmpBuf() = default;
+    TmpBuf(const TmpBuf&) = delete;
+    TmpBuf& operator=(const TmpBuf&) = delete;
+    ~TmpBuf() { release(); }
+    void release() { if (p) cudaFreeAsync(p, st); p = nullptr; }
+    cudaError_t alloc(size_t n, cudaStream_t stream) {
+        release();
+        st = stream;
+        return cudaMallocAsync(&p, n ? n : 1, stream);
+    }
+    template <class T> T* as() const { return (T*)p; }
+};
+
+// Pinned host buffers are slow to make (about 15 ms for 9 MB on the B200 boxes), so the few that set-up needs are
+// kept for the next handle of the process (at most 8; never returned to the driver before exit).
+struct PinnedCache {
+    std::mutex m;
+    std::vector<std::pair<char*, size_t>> idle;
+    cudaError_t get(size_t bytes, char** out, size_t* cap) {
+        {
+            std::lock_guard<std::mutex> lk(m);
+            for (size_t k = 0; k < idle.size(); ++k)
+                if (idle[k].second >= bytes) { *out = idle[k].first; *cap = idle[k].second; idle.erase(idle.begin() + k); return cudaSuccess; }
+        }
+        *cap = bytes + bytes / 8;
+        return cudaHostAlloc((void**)out, *cap, cudaHostAllocDefault);
+    }
+    void put(char* p, size_t cap) {
+        if (!p) return;
+        std::lock_guard<std::mutex> lk(m);
+        if (idle.size() < 8) idle.emplace_back(p, cap); else cudaFreeHost(p);
+    }
+};
+static PinnedCache& pinned_cache() { static PinnedCache* c = new PinnedCache(); return *c; }
+
+// Two pinned staging slots for the arrays the layout builder leaves in pageable vectors: a copy out of pageable
+// memory would make the host wait for everything queued on the stream; out of a slot it is asynchronous.  A slot is
+// reused once the copies issued from it have finished (event).
+struct PinnedRing {
+    char* base[2] = {nullptr, nullptr};
+    size_t cap[2] = {0, 0}, used = 0;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    int cur = 1;
+    ~PinnedRing() {
+        for (int k = 0; k < 2; ++k) { if (ev[k]) { cudaEventSynchronize(ev[k]); cudaEventDestroy(ev[k]); } pinned_cache().put(base[k], cap[k]); }
+    }
+    cudaError_t begin(size_t bytes) {                         // next slot, at least `bytes` large
+        cur ^= 1; used = 0;
+        cudaError_t e;
+        if (!ev[cur]) { if ((e = cudaEventCreateWithFlags(&ev[cur], cudaEventDisableTiming)) != cudaSuccess) return e; }
+        else if ((e = cudaEventSynchronize(ev[cur])) != cudaSuccess) return e;
+        if (bytes > cap[cur]) {
+            pinned_cache().put(base[cur], cap[cur]);
+            base[cur] = nullptr; cap[cur] = 0;
+            if ((e = pinned_cache().get(bytes, &base[cur], &cap[cur])) != cudaSuccess) { base[cur] = nullptr; cap[cur] = 0; return e; }
+        }
+        return cudaSuccess;
+    }
+    template <class T> const T* put(const std::vector<T>& v) {
+        char* dst = base[cur] + used;
+        memcpy(dst, v.data(), sizeof(T) * v.size());
+        used += (sizeof(T) * v.size() + 255) & ~(size_t)255;
+        return reinterpret_cast<const T*>(dst);
+    }
+    template <class T> static size_t need(const std::vector<T>& v) { return (sizeof(T) * v.size() + 255) & ~(size_t)255; }
+    cudaError_t end(cudaStream_t st) { return cudaEventRecord(ev[cur], st); }
+};
+
+template <class T>
+int upload_staged(Arena& mem, DevBuf& b, const std::vector<T>& v, PinnedRing& ring, cudaStream_t st) {
+    MVB_CARVE(mem, b, sizeof(T) * v.size());
+    if (!v.empty()) MVB_CUDA(cudaMemcpyAsync(b.p, ring.put(v), sizeof(T) * v.size(), cudaMemcpyHostToDevice, st));
+    return MVB_OK;
+}
+
+// Host threads that run `job(i)` for i = 0..n-1 in index order while the caller consumes the results as they come:
+// wait(i) blocks until job i is done.  The destructor stops handing out jobs and joins.
+class Crew {
+public:
+    template <class F>
+    Crew(uint32_t n, F job) : n_(n), done_(n, 0) {
+        const uint32_t nt = std::max(1u, std::min(n, std::thread::hardware_concurrency()));
+        for (uint32_t t = 0; t < nt; ++t)
+            th_.emplace_back([this, job] {
+                for (uint32_t i; !stop_.load() && (i = next_.fetch_add(1)) < n_;) {
+                    job(i);
+                    { std::lock_guard<std::mutex> lk(m_); done_[i] = 1; }
+                    cv_.notify_all();
+                }
+            });
+    }
+    void wait(uint32_t i) {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_.wait(lk, [&] { return done_[i] != 0; });
+    }
+    ~Crew() {
+        stop_.store(true);
+        for (auto& t : th_) t.join();
+    }
+private:
+    uint32_t n_;
+    std::vector<char> done_;
+    std::atomic<uint32_t> next_{0};
+    std::atomic<bool> stop_{false};
+    std::mutex m_;
+    std::condition_variable cv_;
+    std::vector<std::thread> th_;
+};
+
 // the u64 of one slice (lanes 0-15 in .x, 16-31 in .y, as finish_slice packs them) -> 32 two-bit values
 void unpack_slices(const std::vector<uint32_t>& int2ext, const std::vector<uint2>& in, uint8_t* values) {
     for (size_t i = 0; i < int2ext.size(); ++i) {
@@ -278,13 +427,22 @@ int upload_tables(mvb_sim* s, Replica& r, const mvb_tables* t) {
     return MVB_OK;
 }
 
-int validate_population(const mvb_population* p, const mvb_tables* t) {
+int check_population_arrays(const mvb_population* p) {          // O(1): what must hold before anything is read
     if (!p || p->n_agents == 0 || !p->subculture || !p->neighbourhood || !p->commute || !p->owns_car ||
         !p->owns_bike || !p->weather_sensitivity || !p->habit || !p->current_mode || !p->norm ||
         !p->social_rowptr || !p->neighbour_rowptr) {
         set_error("population has null arrays or zero agents");
         return MVB_ERR_ARG;
     }
+    const uint64_t es = p->social_rowptr[p->n_agents], en = p->neighbour_rowptr[p->n_agents];
+    if ((es && !p->social_col) || (en && !p->neighbour_col)) { set_error("null column array"); return MVB_ERR_ARG; }
+    if (es >= (1ull << 40) || en >= (1ull << 40)) { set_error("rowptr[n_agents] is not a plausible link count"); return MVB_ERR_ARG; }
+    return MVB_OK;
+}
+
+// O(N), or O(N + E) with check_cols: every index in range.  mvb_create* leaves the link targets to count_hot_kernel.
+int validate_population(const mvb_population* p, const mvb_tables* t, bool check_cols) {
+    if (int rc = check_population_arrays(p)) return rc;
     const uint32_t N = p->n_agents;
     for (uint32_t i = 0; i < N; ++i) {
         if (p->subculture[i] >= t->n_subcultures) { set_error("agent %u: subculture index %u out of range (\"Subculture not found\")", i, p->subculture[i]); return MVB_ERR_ARG; }
@@ -298,7 +456,7 @@ int validate_population(const mvb_population* p, const mvb_tables* t) {
         for (uint32_t i = 0; i < N; ++i)
             if (rp[i + 1] < rp[i]) { set_error("rowptr not monotone at %u", i); return MVB_ERR_ARG; }
         if (rp[N] && !cl) { set_error("null column array"); return MVB_ERR_ARG; }
-        for (uint64_t e = 0; e < rp[N]; ++e)
+        for (uint64_t e = 0; check_cols && e < rp[N]; ++e)
             if (cl[e] >= N) { set_error("link target %u out of range", cl[e]); return MVB_ERR_ARG; }
     }
     return MVB_OK;
@@ -322,13 +480,22 @@ uint32_t mvb_run_rows(uint32_t n_days) {
 
 void mvb_destroy(mvb_sim* s) {
     if (!s) return;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
+    const double t1 = now();
     if (s->comm && nccl()) nccl()->CommDestroy(s->comm);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->stream) cudaStreamDestroy(s->stream);
+    const double t2 = now();
+    s->mem.chunks.clear();
+    const double t3 = now();
     delete s;
+    if (getenv("MVB_TIMING"))
+        fprintf(stderr, "mvb_destroy: stream sync %.3f s, events/stream %.3f s, device memory %.3f s, host memory %.3f s\n",
+                t1 - t0, t2 - t1, t3 - t2, now() - t3);
 }
 
 static int create_impl(uint32_t R, const mvb_population* const* pops, const mvb_tables* const* tabs,
@@ -343,16 +510,14 @@ static int create_impl(uint32_t R, const mvb_population* const* pops, const mvb_
         int rc = check_tables(tabs[r]);
         if (rc) return rc;
     }
-    {   // validate the populations on all host cores (each walks every link once)
-        std::vector<int> rcs(R, MVB_OK);
-        std::vector<std::string> msgs(R);
-        parallel_for(R, [&](uint32_t r) {
-            rcs[r] = validate_population(pops[r], tabs[r]);
-            if (rcs[r]) msgs[r] = mvb_last_error();
-        });
-        for (uint32_t r = 0; r < R; ++r)
-            if (rcs[r]) { set_error("replica %u: %s", r, msgs[r].c_str()); return rcs[r]; }
-    }
+    // MVB_TIMING=1 prints where the set-up time went (stderr)
+    const bool timing = getenv("MVB_TIMING") != nullptr;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double tm0 = now();
+    double tm_wait = 0, tm_graph = 0, tm_state = 0;
+    for (uint32_t r = 0; r < R; ++r)
+        if (int rc = check_population_arrays(pops[r])) return rc;
+    const double tm1 = now();
     MVB_CUDA(cudaSetDevice(device));
     std::unique_ptr<mvb_sim, void (*)(mvb_sim*)> sp(new (std::nothrow) mvb_sim(), mvb_destroy);
     mvb_sim* s = sp.get();
@@ -408,18 +573,161 @@ static int create_impl(uint32_t R, const mvb_population* const* pops, const mvb_
         }
         graph_of[r] = g;
     }
+    {   // first chunk of device memory: an estimate of everything the graphs and replicas will need (link codes ~ the
+        // caller's CSR columns + slice padding, 12 B per agent of graph arrays, 27-47 B per agent of state)
+        size_t est = 64u << 20;
+        for (uint32_t g = 0; g < graphs.size(); ++g) {
+            const mvb_population* p = pops[first_rep[g]];
+            const size_t e = p->social_rowptr[p->n_agents] + p->neighbour_rowptr[p->n_agents];
+            est += 4 * e + e / 4 + 16 * (size_t)p->n_agents + (1u << 20);
+        }
+        for (uint32_t r = 0; r < R; ++r) est += 48 * (size_t)pops[r]->n_agents + (1u << 16);
+        size_t free_b = 0, total_b = 0;
+        MVB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        s->mem.chunk_bytes = std::max<size_t>(256u << 20, std::min(est, free_b / 2));
+    }
+    // Set-up is a pipeline between host threads (the crew) and the device, driven by this thread:
+    //   A(r)  crew: range checks of replica r's arrays, residents per neighbourhood, and, if r is the first replica
+    //         of its graph g, layout_begin (degree order, hot set)
+    //   S1(g) this thread: the caller's CSR goes up as it is; once A is done, is_hot goes up, count_hot_kernel counts
+    //         the hot links of every agent (and range-checks the targets), the counts come back to pinned memory
+    //   F(g)  crew: waits for the counts, layout_finish (final order, slices, offsets)
+    //   S2(g) this thread: layout arrays up, tcode + fill kernels, then the state of the replicas that use g
+    // S1 runs kLook graphs ahead of S2 so that the copies of later graphs hide the host work of earlier ones.
+    constexpr uint32_t kLook = 2, kSlots = kLook + 2;
+    const uint32_t G = (uint32_t)graphs.size();
+    struct GraphWork {
+        LayoutWork W;
+        TmpBuf srp, scol, nrp, ncol, is_hot, counts, flag;
+        uint32_t* h_counts = nullptr;                            // pinned: nsh[N] | nnh[N] | bad flag
+    };
+    std::vector<GraphWork> work(G);
+    struct Slots {                                               // pinned buffers the counts come back into
+        char* base[kSlots] = {};
+        size_t cap[kSlots] = {};
+        cudaEvent_t ev[kSlots] = {};
+        ~Slots() { for (uint32_t k = 0; k < kSlots; ++k) { if (ev[k]) { cudaEventSynchronize(ev[k]); cudaEventDestroy(ev[k]); } pinned_cache().put(base[k], cap[k]); } }
+    } slots;
     {
-        std::vector<int> rcs(graphs.size(), MVB_OK);
-        std::vector<std::string> msgs(graphs.size());
-        parallel_for((uint32_t)graphs.size(), [&](uint32_t g) {
-            rcs[g] = build_graph_layout(*pops[first_rep[g]], tabs[first_rep[g]]->n_neighbourhoods, capacity_agents, graphs[g]->L);
-            if (rcs[g]) msgs[g] = mvb_last_error();
-        });
-        for (size_t g = 0; g < graphs.size(); ++g)
-            if (rcs[g]) { set_error("%s", msgs[g].c_str()); return rcs[g]; }
+        size_t slot_bytes = 0;
+        for (uint32_t g = 0; g < G; ++g) slot_bytes = std::max(slot_bytes, 9 * (size_t)pops[first_rep[g]]->n_agents + 64);
+        for (uint32_t k = 0; k < std::min(kSlots, G); ++k) {
+            MVB_CUDA(pinned_cache().get(slot_bytes, &slots.base[k], &slots.cap[k]));
+            MVB_CUDA(cudaEventCreateWithFlags(&slots.ev[k], cudaEventDisableTiming));
+        }
+    }
+    struct Signals {                                             // S1(g) queued -> F(g) may wait for its event
+        std::mutex m;
+        std::condition_variable cv;
+        std::vector<char> queued;
+        bool abort = false;
+    } sig;
+    sig.queued.assign(G, 0);
+    // crew job list: A(r) in replica order; F(g) follows the A of graph g + kLook
+    std::vector<std::pair<char, uint32_t>> jobs;
+    std::vector<uint32_t> job_a(R), job_f(G);
+    for (uint32_t r = 0; r < R; ++r) {
+        job_a[r] = (uint32_t)jobs.size();
+        jobs.emplace_back('A', r);
+        const uint32_t g = graph_of[r];
+        if (first_rep[g] == r && g >= kLook) { job_f[g - kLook] = (uint32_t)jobs.size(); jobs.emplace_back('F', g - kLook); }
+    }
+    for (uint32_t g = G > kLook ? G - kLook : 0; g < G; ++g) { job_f[g] = (uint32_t)jobs.size(); jobs.emplace_back('F', g); }
+    std::vector<int> job_rc(jobs.size(), MVB_OK);
+    std::vector<std::string> job_msg(jobs.size());
+    std::vector<std::vector<uint32_t>> nres_all(R);
+    Crew crew((uint32_t)jobs.size(), [&](uint32_t j) {
+        auto fail = [&](int rc) { job_rc[j] = rc; job_msg[j] = mvb_last_error(); };
+        if (jobs[j].first == 'A') {
+            const uint32_t r = jobs[j].second, g = graph_of[r];
+            if (int rc = validate_population(pops[r], tabs[r], false)) return fail(rc);
+            nres_all[r].assign(tabs[r]->n_neighbourhoods, 0u);
+            for (uint32_t i = 0; i < pops[r]->n_agents; ++i) nres_all[r][pops[r]->neighbourhood[i]]++;
+            if (first_rep[g] != r) return;
+            if (int rc = layout_begin(*pops[r], tabs[r]->n_neighbourhoods, capacity_agents, graphs[g]->L, work[g].W)) return fail(rc);
+        } else {
+            const uint32_t g = jobs[j].second;
+            {
+                std::unique_lock<std::mutex> lk(sig.m);
+                sig.cv.wait(lk, [&] { return sig.queued[g] || sig.abort; });
+                if (sig.abort) return;
+            }
+            cudaSetDevice(device);
+            if (cudaEventSynchronize(slots.ev[g % kSlots]) != cudaSuccess) { set_error("waiting for the device failed"); return fail(MVB_ERR_CUDA); }
+            GraphWork& w = work[g];
+            const uint32_t N = pops[first_rep[g]]->n_agents;
+            if (w.h_counts[2 * (size_t)N]) { set_error("a link target is out of range"); return fail(MVB_ERR_ARG); }
+            w.W.nsh = w.h_counts;
+            w.W.nnh = w.h_counts + N;
+            if (int rc = layout_finish(*pops[first_rep[g]], w.W, graphs[g]->L, false)) return fail(rc);
+            LayoutWork done;                                     // only is_hot's device copy is still needed
+            std::swap(done, w.W);
+        }
+    });
+    struct Abort {                                               // declared after the crew: runs before it joins
+        Signals& sig;
+        ~Abort() { { std::lock_guard<std::mutex> lk(sig.m); sig.abort = true; } sig.cv.notify_all(); }
+    } abort_guard{sig};
+    auto wait_job = [&](uint32_t j, const char* what, uint32_t idx) -> int {
+        crew.wait(j);
+        if (job_rc[j]) { set_error("%s %u: %s", what, idx, job_msg[j].c_str()); return job_rc[j]; }
+        return MVB_OK;
+    };
+    uint32_t csr_issued = 0, s1_done = 0;                        // graphs [0, x) have their CSR copies / their S1 queued
+    auto issue_csr = [&](uint32_t upto) -> int {
+        for (; csr_issued < std::min(upto, G); ++csr_issued) {
+            const mvb_population* p = pops[first_rep[csr_issued]];
+            const size_t nb_rp = 8 * ((size_t)p->n_agents + 1), es = p->social_rowptr[p->n_agents], en = p->neighbour_rowptr[p->n_agents];
+            GraphWork& c = work[csr_issued];
+            MVB_CUDA(c.srp.alloc(nb_rp, s->stream)); MVB_CUDA(c.nrp.alloc(nb_rp, s->stream));
+            MVB_CUDA(c.scol.alloc(4 * es, s->stream)); MVB_CUDA(c.ncol.alloc(4 * en, s->stream));
+            MVB_CUDA(cudaMemcpyAsync(c.srp.p, p->social_rowptr, nb_rp, cudaMemcpyHostToDevice, s->stream));
+            MVB_CUDA(cudaMemcpyAsync(c.nrp.p, p->neighbour_rowptr, nb_rp, cudaMemcpyHostToDevice, s->stream));
+            if (es) MVB_CUDA(cudaMemcpyAsync(c.scol.p, p->social_col, 4 * es, cudaMemcpyHostToDevice, s->stream));
+            if (en) MVB_CUDA(cudaMemcpyAsync(c.ncol.p, p->neighbour_col, 4 * en, cudaMemcpyHostToDevice, s->stream));
+        }
+        return MVB_OK;
+    };
+    auto stage1 = [&](uint32_t upto) -> int {
+        for (; s1_done < std::min(upto, G); ++s1_done) {
+            const uint32_t g = s1_done, r0 = first_rep[g], N = pops[r0]->n_agents;
+            if (int rc = issue_csr(g + 1)) return rc;
+            const double tw = now();
+            if (int rc = wait_job(job_a[r0], "replica", r0)) return rc;
+            tm_wait += now() - tw;
+            GraphWork& w = work[g];
+            char* slot = slots.base[g % kSlots];
+            w.h_counts = reinterpret_cast<uint32_t*>(slot);
+            uint8_t* h_hot = reinterpret_cast<uint8_t*>(slot) + 8 * (size_t)N + 64;
+            memcpy(h_hot, w.W.is_hot.data(), N);
+            MVB_CUDA(w.is_hot.alloc(N, s->stream));
+            MVB_CUDA(w.counts.alloc(8 * (size_t)N + 4, s->stream));
+            MVB_CUDA(cudaMemcpyAsync(w.is_hot.p, h_hot, N, cudaMemcpyHostToDevice, s->stream));
+            uint32_t* d_bad = w.counts.as<uint32_t>() + 2 * (size_t)N;
+            MVB_CUDA(cudaMemsetAsync(d_bad, 0, 4, s->stream));
+            count_hot_kernel<<<(unsigned)std::min<uint64_t>(((uint64_t)N * 32 + 255) / 256, (uint64_t)sms * 32), 256, 0, s->stream>>>(
+                N, w.srp.as<uint64_t>(), w.scol.as<uint32_t>(), w.nrp.as<uint64_t>(), w.ncol.as<uint32_t>(), w.is_hot.as<uint8_t>(),
+                w.counts.as<uint32_t>(), w.counts.as<uint32_t>() + N, d_bad);
+            MVB_CUDA(cudaGetLastError());
+            MVB_CUDA(cudaMemcpyAsync(w.h_counts, w.counts.p, 8 * (size_t)N + 4, cudaMemcpyDeviceToHost, s->stream));
+            MVB_CUDA(cudaEventRecord(slots.ev[g % kSlots], s->stream));
+            { std::lock_guard<std::mutex> lk(sig.m); sig.queued[g] = 1; }
+            sig.cv.notify_all();
+        }
+        return MVB_OK;
+    };
+    PinnedRing ring;
+    {   // scratch buffers come from the device's stream-ordered pool; let it keep what it has between replicas
+        cudaMemPool_t pool;
+        MVB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+        uint64_t keep = ~0ull;
+        MVB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
     }
     std::vector<char> uploaded(graphs.size(), 0);
+    std::list<std::vector<float>> host_f;
+    const double tm2 = now();
     for (uint32_t r = 0; r < R; ++r) {
+        const double tr = now();
         const mvb_population* p = pops[r];
         const mvb_tables* t = tabs[r];
         Replica& rp = s->reps[r];
@@ -429,31 +737,43 @@ static int create_impl(uint32_t R, const mvb_population* const* pops, const mvb_
         rp.rec_off = s->rec_stride;
         s->rec_stride += rp.rec_width;
         rp.graph = graphs[graph_of[r]];
+        if (int rc = stage1(graph_of[r] + 1 + kLook)) return rc;
+        if (int rc = issue_csr(graph_of[r] + 2 + kLook)) return rc;
+        {
+            const double tw = now();
+            if (int rc = wait_job(job_a[r], "replica", r)) return rc;
+            if (!uploaded[graph_of[r]])
+                if (int rc = wait_job(job_f[graph_of[r]], "replica", r)) return rc;
+            tm_wait += now() - tw;
+        }
         if (!uploaded[graph_of[r]]) {
             uploaded[graph_of[r]] = 1;
             Graph* g = rp.graph.get();
             GraphLayout& L = g->L;
             int rc;
-            if ((rc = upload(g->ranges, L.ranges, s->stream)) || (rc = upload(g->hub_off, L.hub_off, s->stream)) ||
-                (rc = upload(g->hub_deg, L.hub_deg, s->stream)) || (rc = upload(g->sell_meta, L.sell_meta, s->stream)) ||
-                (rc = upload(g->hub_units, L.hub_units, s->stream)) || (rc = upload(g->hub_unit_begin, L.hub_unit_begin, s->stream)))
+            MVB_CUDA(ring.begin(PinnedRing::need(L.ranges) + PinnedRing::need(L.hub_off) + PinnedRing::need(L.hub_deg) +
+                                PinnedRing::need(L.sell_meta) + PinnedRing::need(L.hub_units) + PinnedRing::need(L.hub_unit_begin) +
+                                PinnedRing::need(L.int2ext)));
+            if ((rc = upload_staged(s->mem, g->ranges, L.ranges, ring, s->stream)) || (rc = upload_staged(s->mem, g->hub_off, L.hub_off, ring, s->stream)) ||
+                (rc = upload_staged(s->mem, g->hub_deg, L.hub_deg, ring, s->stream)) || (rc = upload_staged(s->mem, g->sell_meta, L.sell_meta, ring, s->stream)) ||
+                (rc = upload_staged(s->mem, g->hub_units, L.hub_units, ring, s->stream)) ||
+                (rc = upload_staged(s->mem, g->hub_unit_begin, L.hub_unit_begin, ring, s->stream)) ||
+                (rc = upload_staged(s->mem, g->int2ext, L.int2ext, ring, s->stream)))
                 return rc;
-            MVB_CUDA(g->deg.alloc(sizeof(uint32_t) * (size_t)L.N_pad));
-            MVB_CUDA(g->hub_codes.alloc(sizeof(uint32_t) * L.hub_codes_len));
-            MVB_CUDA(g->sell_codes.alloc(sizeof(uint32_t) * L.sell_codes_len));
+            MVB_CARVE(s->mem, g->deg, sizeof(uint32_t) * (size_t)L.N_pad);
+            MVB_CARVE(s->mem, g->hub_codes, sizeof(uint32_t) * L.hub_codes_len);
+            MVB_CARVE(s->mem, g->sell_codes, sizeof(uint32_t) * L.sell_codes_len);
             MVB_CUDA(cudaMemsetAsync(g->hub_codes.p, 0, g->hub_codes.bytes, s->stream));      // padding = code 0
             MVB_CUDA(cudaMemsetAsync(g->sell_codes.p, 0, g->sell_codes.bytes, s->stream));
-            // the caller's CSR goes to the device as it is; the fill kernels re-encode it there, then it is dropped
-            DevBuf t_srp, t_scol, t_nrp, t_ncol, t_tcode;
-            const size_t nb_rp = 8 * ((size_t)N + 1);
-            MVB_CUDA(t_srp.alloc(nb_rp)); MVB_CUDA(t_nrp.alloc(nb_rp));
-            MVB_CUDA(t_scol.alloc(4 * L.Es)); MVB_CUDA(t_ncol.alloc(4 * L.En));
-            MVB_CUDA(cudaMemcpyAsync(t_srp.p, p->social_rowptr, nb_rp, cudaMemcpyHostToDevice, s->stream));
-            MVB_CUDA(cudaMemcpyAsync(t_nrp.p, p->neighbour_rowptr, nb_rp, cudaMemcpyHostToDevice, s->stream));
-            if (L.Es) MVB_CUDA(cudaMemcpyAsync(t_scol.p, p->social_col, 4 * L.Es, cudaMemcpyHostToDevice, s->stream));
-            if (L.En) MVB_CUDA(cudaMemcpyAsync(t_ncol.p, p->neighbour_col, 4 * L.En, cudaMemcpyHostToDevice, s->stream));
-            if ((rc = upload(t_tcode, L.tcode, s->stream)) || (rc = upload(g->int2ext, L.int2ext, s->stream))) return rc;
-            FillArgs fa{t_srp.as<uint64_t>(), t_scol.as<uint32_t>(), t_nrp.as<uint64_t>(), t_ncol.as<uint32_t>(),
+            // the caller's CSR went to the device as it is (issue_csr); the fill kernels re-encode it there, then it is dropped
+            GraphWork& c = work[graph_of[r]];
+            TmpBuf t_tcode;
+            MVB_CUDA(t_tcode.alloc(4 * (size_t)N, s->stream));
+            MVB_CUDA(ring.end(s->stream));
+            tcode_kernel<<<(L.N_pad + 255) / 256, 256, 0, s->stream>>>(L.N_pad, g->int2ext.as<uint32_t>(), g->ranges.as<StageRange>(),
+                                                                     (uint32_t)L.ranges.size(), c.is_hot.as<uint8_t>(), t_tcode.as<uint32_t>());
+            MVB_CUDA(cudaGetLastError());
+            FillArgs fa{c.srp.as<uint64_t>(), c.scol.as<uint32_t>(), c.nrp.as<uint64_t>(), c.ncol.as<uint32_t>(),
                         t_tcode.as<uint32_t>(), g->int2ext.as<uint32_t>(), L.n_hub_slices, L.n_sell_slices,
                         g->sell_meta.as<uint4>(), g->sell_codes.as<uint32_t>(), g->deg.as<uint32_t>(),
                         g->hub_off.as<uint64_t>(), g->hub_deg.as<uint4>(), g->hub_codes.as<uint32_t>()};
@@ -466,13 +786,14 @@ static int create_impl(uint32_t R, const mvb_population* const* pops, const mvb_
                 fill_hub_kernel<<<(L.n_hub_slices * 32 * 32 + 255) / 256, 256, 0, s->stream>>>(fa, L.n_hub_slices * 32);
                 MVB_CUDA(cudaGetLastError());
             }
-            MVB_CUDA(cudaStreamSynchronize(s->stream));          // temporaries are freed when they go out of scope
-            std::vector<uint32_t>().swap(L.tcode);
+            c.srp.release(); c.scol.release(); c.nrp.release(); c.ncol.release(); c.is_hot.release(); c.counts.release();   // back to the pool, in stream order
             std::vector<uint4x>().swap(L.sell_meta);
         }
         const GraphLayout& L = rp.graph->L;
         const uint32_t NP = L.N_pad;
         s->max_npad = std::max(s->max_npad, NP);
+        const double ts = now();
+        tm_graph += ts - tr;
         // per-agent state: the caller's arrays go up as they are, a kernel permutes them into internal slot order
         const float* pa_src[5] = {p->consistency, p->social_connectivity, p->subculture_connectivity,
                                   p->neighbourhood_connectivity, p->average_weight};
@@ -482,12 +803,17 @@ static int create_impl(uint32_t R, const mvb_population* const* pops, const mvb_
         for (int k = 0; k < 5; ++k) rp.per_agent |= (pa_src[k] != nullptr);
         if (rp.per_agent) s->any_per_agent = true;
         {
-            MVB_CUDA(rp.stat.alloc(4 * (size_t)NP)); MVB_CUDA(rp.ws.alloc(4 * (size_t)NP)); MVB_CUDA(rp.habit.alloc(16 * (size_t)NP));
-            MVB_CUDA(rp.vec[0].alloc(NP / 4)); MVB_CUDA(rp.vec[1].alloc(NP / 4)); MVB_CUDA(rp.normvec.alloc(NP / 4));
-            if (rp.per_agent) MVB_CUDA(rp.pa.alloc(20 * (size_t)NP));
-            DevBuf t[14];
-            auto up = [&](DevBuf& b, const void* src, size_t bytes) -> int {
-                MVB_CUDA(b.alloc(bytes));
+            const size_t hub_cnt_bytes = sizeof(uint32_t) * 8 * 32 * (size_t)L.n_hub_slices;
+            MVB_CARVE(s->mem, rp.stat, 4 * (size_t)NP); MVB_CARVE(s->mem, rp.ws, 4 * (size_t)NP); MVB_CARVE(s->mem, rp.habit, 16 * (size_t)NP);
+            MVB_CARVE(s->mem, rp.vec[0], NP / 4); MVB_CARVE(s->mem, rp.vec[1], NP / 4); MVB_CARVE(s->mem, rp.normvec, NP / 4);
+            if (rp.per_agent) MVB_CARVE(s->mem, rp.pa, 20 * (size_t)NP);
+            MVB_CARVE(s->mem, rp.tables_f, sizeof(float) * 4 * (rp.H + rp.S));
+            MVB_CARVE(s->mem, rp.tables_u, sizeof(uint32_t) * 5 * rp.H);
+            MVB_CARVE(s->mem, rp.cong, sizeof(float) * 4 * rp.H);
+            MVB_CARVE(s->mem, rp.hub_cnt, hub_cnt_bytes);
+            TmpBuf t[14];
+            auto up = [&](TmpBuf& b, const void* src, size_t bytes) -> int {
+                MVB_CUDA(b.alloc(bytes, s->stream));
                 MVB_CUDA(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, s->stream));
                 return MVB_OK;
             };
@@ -510,20 +836,13 @@ static int create_impl(uint32_t R, const mvb_population* const* pops, const mvb_
             ia.pa_out = rp.per_agent ? rp.pa.as<float>() : nullptr;
             ia.vec0 = rp.vec[0].as<uint2>(); ia.vec1 = rp.vec[1].as<uint2>(); ia.normvec = rp.normvec.as<uint2>();
             init_state_kernel<<<(NP + 255) / 256, 256, 0, s->stream>>>(ia);
-            MVB_CUDA(cudaGetLastError());
-            MVB_CUDA(cudaStreamSynchronize(s->stream));          // temporaries are freed on scope exit
+            MVB_CUDA(cudaGetLastError());                        // the scratch goes back to the pool in stream order
         }
         // tables + residents
-        MVB_CUDA(rp.tables_f.alloc(sizeof(float) * 4 * (rp.H + rp.S)));
-        MVB_CUDA(rp.tables_u.alloc(sizeof(uint32_t) * 5 * rp.H));
-        MVB_CUDA(rp.cong.alloc(sizeof(float) * 4 * rp.H));
         if (int rc = upload_tables(s, rp, t)) return rc;
-        std::vector<uint32_t> nres(rp.H, 0);
-        for (uint32_t i = 0; i < N; ++i) nres[p->neighbourhood[i]]++;
-        MVB_CUDA(cudaMemcpyAsync(rp.tables_u.as<uint32_t>() + 4 * rp.H, nres.data(), 4 * rp.H, cudaMemcpyHostToDevice, s->stream));
-        std::vector<float> ones(4 * rp.H, 1.0f);      // default_congestion_modifier, neighbourhood.rs:34-41
-        MVB_CUDA(cudaMemcpyAsync(rp.cong.p, ones.data(), 16 * rp.H, cudaMemcpyHostToDevice, s->stream));
-        MVB_CUDA(cudaStreamSynchronize(s->stream));   // the host staging vectors above go out of scope
+        MVB_CUDA(cudaMemcpyAsync(rp.tables_u.as<uint32_t>() + 4 * rp.H, nres_all[r].data(), 4 * rp.H, cudaMemcpyHostToDevice, s->stream));
+        host_f.emplace_back(4 * rp.H, 1.0f);          // default_congestion_modifier, neighbourhood.rs:34-41; lives until the final synchronize
+        MVB_CUDA(cudaMemcpyAsync(rp.cong.p, host_f.back().data(), 16 * rp.H, cudaMemcpyHostToDevice, s->stream));
 
         Graph& g = *rp.graph;
         RepDev& d = s->h_reps[r];
@@ -541,8 +860,7 @@ static int create_impl(uint32_t R, const mvb_population* const* pops, const mvb_
         d.pa = rp.per_agent ? rp.pa.as<float>() : nullptr;
         d.vec[0] = rp.vec[0].as<uint2>(); d.vec[1] = rp.vec[1].as<uint2>(); d.normvec = rp.normvec.as<uint2>();
         d.deg = g.deg.as<uint32_t>(); d.ranges = g.ranges.as<StageRange>();
-        MVB_CUDA(rp.hub_cnt.alloc(sizeof(uint32_t) * 8 * 32 * (size_t)L.n_hub_slices));
-        MVB_CUDA(cudaMemsetAsync(rp.hub_cnt.p, 0, rp.hub_cnt.bytes, s->stream));
+        if (rp.hub_cnt.bytes) MVB_CUDA(cudaMemsetAsync(rp.hub_cnt.p, 0, rp.hub_cnt.bytes, s->stream));
         d.hub_units = g.hub_units.as<uint4>(); d.hub_unit_begin = g.hub_unit_begin.as<uint32_t>();
         d.hub_off = g.hub_off.as<uint64_t>(); d.hub_deg = g.hub_deg.as<uint4>(); d.hub_cnt = rp.hub_cnt.as<uint32_t>();
         d.hub_codes = g.hub_codes.as<uint32_t>();
@@ -551,7 +869,9 @@ static int create_impl(uint32_t R, const mvb_population* const* pops, const mvb_
         d.cap = rp.tables_u.as<uint32_t>(); d.nres = rp.tables_u.as<uint32_t>() + 4 * rp.H;
         d.cong = rp.cong.as<float>();
         if (L.hot_words > s->vec_cap_words) { set_error("internal: staged vector larger than its shared-memory slot"); return MVB_ERR_STATE; }
+        tm_state += now() - ts;
     }
+    const double tm3 = now();
     MVB_CUDA(cudaFuncSetAttribute(day_kernel<true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
     MVB_CUDA(cudaFuncSetAttribute(day_kernel<false, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
     if (s->census_smem > 48 * 1024)
@@ -576,6 +896,16 @@ static int create_impl(uint32_t R, const mvb_population* const* pops, const mvb_
     rc = launch_census(s, 0);
     if (rc) return rc;
     MVB_CUDA(cudaStreamSynchronize(s->stream));
+    if (timing)
+        fprintf(stderr, "mvb_create: checks %.3f s, set-up %.3f s, replicas %.3f s (waiting for host threads %.3f, graph enqueue %.3f, "
+                "state enqueue %.3f), drain %.3f s\n", tm1 - tm0, tm2 - tm1, tm3 - tm2, tm_wait, tm_graph - tm_wait, tm_state, now() - tm3);
+    {   // hand the scratch memory back
+        cudaMemPool_t pool;
+        MVB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+        uint64_t keep = 0;
+        MVB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        MVB_CUDA(cudaMemPoolTrimTo(pool, 0));
+    }
     *out = sp.release();
     return MVB_OK;
 }

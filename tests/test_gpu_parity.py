@@ -199,3 +199,23 @@ def test_population_above_shared_memory_capacity():
     tab = mb.synth_tables(4, 10, n, seed=21)
     w = np.array([0, 1, 1, 0, 1], np.uint8)
     lockstep(pop, tab, PRM, w, 5, check_every=2)
+
+
+@pytest.mark.gpu
+def test_create_rejects_bad_indices():
+    """What panics in the reference (indexing past the agent list, "Subculture not found") is an error return here; the
+    link targets are range-checked on the device (count_hot_kernel), everything else by the host threads."""
+    tab = mb.synth_tables(3, 4, 3000, seed=1)
+    for what in ("social_col", "neighbour_col", "subculture", "neighbourhood", "current_mode"):
+        pop = mb.synth_population(3000, 3, 4, seed=21)
+        a = pop.arrays[what]
+        a[len(a) // 2] = 3000 if what.endswith("col") else 200
+        with pytest.raises(mb.MotivateError):
+            mb.Simulation(pop, tab, mb.make_params())
+    # and a good population next to a bad one: the error names the replica
+    good, bad = mb.synth_population(3000, 3, 4, seed=22), mb.synth_population(3000, 3, 4, seed=23)
+    bad.arrays["social_col"][7] = 1 << 31
+    with pytest.raises(mb.MotivateError, match="replica 1"):
+        mb.Simulation([good, bad], [tab, tab], mb.make_params())
+    with mb.Simulation([good, good], [tab, tab], mb.make_params()) as sim:      # the handle machinery still works afterwards
+        assert sim.n_replicas == 2
