@@ -44,7 +44,7 @@ def parse():
                     help="BASELINE config 5: --replicas scenario variants (tables + ownership differ) over ONE shared population")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-baseline-days", type=int, default=8)
+    ap.add_argument("--cpu-baseline-days", type=int, default=100)
     return ap.parse_args()
 
 
