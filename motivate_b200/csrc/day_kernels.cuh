@@ -113,6 +113,17 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// Shared-memory atomics issued by ONE lane of a warp.  Plain atomicAdd makes the compiler wrap the instruction in its
+// warp-aggregation sequence (vote, find-leader, popc, shuffle: ~12 instructions) because it cannot know that.
+__device__ __forceinline__ uint32_t smem_fetch_add(uint32_t* p, uint32_t v) {
+    uint32_t old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(p)), "r"(v));
+    return old;
+}
+__device__ __forceinline__ void smem_add(uint32_t* p, uint32_t v) {
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v));
+}
+
 // ---- gathering yesterday's modes ---------------------------------------------------------------
 // Link code (layout.h): code >> 5 = byte offset of the target's word, low 5 bits = left shift that brings the
 // target's 2 bits to bits 31:30.  __funnelshift_l wraps the shift amount, so the code is used as it is.
@@ -138,16 +149,21 @@ __device__ __forceinline__ uint32_t top_fields(int n) {      // mask of the low 
 }
 
 // `bits` holds 16 gathered modes, link number base+e in field 15-e (the first link pushed ends up highest), of a
-// list whose first `ds` links are social and the following neighbour links, `d` in total (fields at or past d are
-// padding).  Adds the counts of modes 1..3 to bits 8-31 of the packed 8-bit accumulators; the Car count (mode 0) is
-// what is left of the list length (car_counts).  count_in_subgroup's grouping, agent.rs:325-329.
-__device__ __forceinline__ void count_fields(uint32_t bits, int base, int ds, int d, uint32_t& acc_s, uint32_t& acc_n) {
-    const uint32_t vmask = top_fields(min(max(d - base, 0), 16)), smask = top_fields(min(max(ds - base, 0), 16));
-    const uint32_t lo = bits & vmask, hi = (bits >> 1) & vmask;          // padding fields drop out here
+// list whose first `ds` links are social and the rest neighbour links.  Fields past the end of the list hold 0: the
+// padding codes of a block point at a shared-memory word that is always zero (kPadWord, layout.h), and 0 is Car,
+// which is not counted here but derived from the list length (car_counts).  Adds the counts of modes 1..3 to bits
+// 8-31 of the packed 8-bit accumulators: acc_t over the whole group, acc_s over its social links
+// (count_in_subgroup's grouping, agent.rs:325-329).
+__device__ __forceinline__ void count_fields(uint32_t bits, int base, int ds, uint32_t& acc_s, uint32_t& acc_t) {
+    const uint32_t smask = top_fields(min(max(ds - base, 0), 16));
+    const uint32_t lo = bits & 0x55555555u, hi = (bits >> 1) & 0x55555555u;
     const uint32_t m3 = hi & lo, m2 = hi & ~lo, m1 = ~hi & lo;
-    const uint32_t s1 = __popc(m1 & smask), s2 = __popc(m2 & smask), s3 = __popc(m3 & smask);
-    acc_s += s1 << 8 | s2 << 16 | s3 << 24;
-    acc_n += (__popc(m1) - s1) << 8 | (__popc(m2) - s2) << 16 | (__popc(m3) - s3) << 24;
+    acc_s += __popc(m1 & smask) << 8;
+    acc_s += __popc(m2 & smask) << 16;
+    acc_s += __popc(m3 & smask) << 24;
+    acc_t += __popc(m1) << 8;
+    acc_t += __popc(m2) << 16;
+    acc_t += __popc(m3) << 24;
 }
 // Fill in the Car count of a list of n links whose other three counts sit in bits 8-31 of acc.
 __device__ __forceinline__ uint32_t car_counts(uint32_t acc, uint32_t n) {
@@ -155,12 +171,14 @@ __device__ __forceinline__ uint32_t car_counts(uint32_t acc, uint32_t n) {
 }
 
 // One lane's part of a block of link codes laid out k-major for the warp (layout.h): K hot codes per lane
-// (floor(K/4) uint4 rows, then K%4 u32 rows) followed by Kc cold codes per lane.  The lane's hot list has d_h
-// links of which the first ds_h are social; likewise d_c / ds_c for the cold list.  Per-mode counts are added to
-// acc_s / acc_n (8 bits per mode: the caller keeps every list below 256 links).
+// (floor(K/4) uint4 rows, then K%4 u32 rows) followed by Kc cold codes per lane.  The first ds_h links of the lane's
+// hot list are social (its end needs no bound: padding gathers 0, see count_fields); the cold list has d_c links of
+// which the first ds_c are social.  Per-mode counts are added to acc_s / acc_n (8 bits per mode: the caller keeps
+// every list below 256 links).
 __device__ __forceinline__ void accumulate_block(const uint32_t* __restrict__ blk, uint32_t K, uint32_t Kc, uint32_t lane,
-                                                 int ds_h, int d_h, int ds_c, int d_c, const uint32_t* s_vec,
+                                                 int ds_h, int ds_c, int d_c, const uint32_t* s_vec,
                                                  const uint32_t* __restrict__ g_vec, uint32_t& acc_s, uint32_t& acc_n) {
+    uint32_t hs = 0, ht = 0;                                    // hot list: social / all
     const uint32_t K4 = K >> 2, Kt = K & 3u;
     const uint4* body = reinterpret_cast<const uint4*>(blk) + lane;
     const uint32_t* tail = blk + (size_t)K4 * 128 + lane;
@@ -190,7 +208,7 @@ __device__ __forceinline__ void accumulate_block(const uint32_t* __restrict__ bl
         bits = push_row(s_vec, bits, r2);
         if (q + 5 < K4) r1 = ld_stream_v4(body + (size_t)(q + 5) * 32);
         bits = push_row(s_vec, bits, r3);
-        count_fields(bits, (int)(q * 4), ds_h, d_h, acc_s, acc_n);
+        count_fields(bits, (int)(q * 4), ds_h, hs, ht);
         bits = 0;
     }
     const uint32_t rem = K4 - q;                                // 0..3 rows left, then the tail
@@ -203,8 +221,10 @@ __device__ __forceinline__ void accumulate_block(const uint32_t* __restrict__ bl
         if (Kt > 1) bits = push2(bits, top2_hot(s_vec, t1));
         if (Kt > 2) bits = push2(bits, top2_hot(s_vec, t2));
         bits <<= 2u * (16u - (rem * 4u + Kt));                  // first link of the group back to field 15
-        count_fields(bits, (int)(q * 4), ds_h, d_h, acc_s, acc_n);
+        count_fields(bits, (int)(q * 4), ds_h, hs, ht);
     }
+    acc_s += hs;
+    acc_n += ht - hs;                                           // byte-wise: every count of ht is >= that of hs
     if (0 < d_c) {
         const uint32_t inc = (1u << ((__funnelshift_l(0u, w0, c0) >> 30) * 8u)) & ~0xFFu;      // Car is derived, see count_fields
         if (0 < ds_c) acc_s += inc; else acc_n += inc;
@@ -213,14 +233,14 @@ __device__ __forceinline__ void accumulate_block(const uint32_t* __restrict__ bl
         const uint32_t inc = (1u << ((__funnelshift_l(0u, w1, c1) >> 30) * 8u)) & ~0xFFu;
         if (1 < ds_c) acc_s += inc; else acc_n += inc;
     }
-    for (uint32_t k = 2; k < Kc; k += 4) {                      // the rest of the cold list, four links at a time:
-        uint32_t c[4], w[4];                                    // all four codes, then all four gathers, then the counts
+    for (uint32_t k = 2; k < Kc; k += 8) {                      // the rest of the cold list, eight links at a time:
+        uint32_t c[8], w[8];                                    // all eight codes, then all eight gathers, then the counts
 #pragma unroll
-        for (int u = 0; u < 4; ++u) c[u] = k + u < Kc ? ld_stream_u32(cold + (size_t)(k + u) * 32) : 0u;
+        for (int u = 0; u < 8; ++u) c[u] = k + u < Kc ? ld_stream_u32(cold + (size_t)(k + u) * 32) : 0u;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) w[u] = __ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(g_vec) + (c[u] >> 5)));
+        for (int u = 0; u < 8; ++u) w[u] = __ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(g_vec) + (c[u] >> 5)));
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < 8; ++u)
             if ((int)(k + u) < d_c) {
                 const uint32_t inc = (1u << ((__funnelshift_l(0u, w[u], c[u]) >> 30) * 8u)) & ~0xFFu;
                 if ((int)(k + u) < ds_c) acc_s += inc; else acc_n += inc;
@@ -323,7 +343,7 @@ day_kernel(const __grid_constant__ RepArray reps, uint32_t R, uint32_t P, uint32
     uint32_t* s_next = s_tail + 2;                    // work-item counter of the current part
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 
-    if (tid == 0) mbar_init(s_bar, 1);
+    if (tid == 0) { mbar_init(s_bar, 1); s_vec[vec_cap_words - 1] = 0; }   // the word padding codes point at (pad_code)
     uint32_t phase = 0;
 
     for (uint32_t part = blockIdx.x; part < R * P; part += gridDim.x) {
@@ -425,9 +445,9 @@ day_kernel(const __grid_constant__ RepArray reps, uint32_t R, uint32_t P, uint32
                 const uint4 hd = ld_stream_v4(reinterpret_cast<const uint4*>(r.hub_deg) + hub);   // ds_hot, dn_hot, ds_cold, dn_cold
                 const uint32_t* blk = r.hub_codes + (((uint64_t)ua.y << 32) | ua.x);
                 const int oh = (int)(ub.x + lane * K), oc = (int)(ub.y + lane * Kc);
-                const int n_hot = (int)(hd.x + hd.y), n_cold = (int)(hd.z + hd.w);
+                const int n_cold = (int)(hd.z + hd.w);
                 uint32_t acc_s = 0, acc_n = 0;
-                accumulate_block(blk, K, Kc, lane, min(max((int)hd.x - oh, 0), (int)K), min(max(n_hot - oh, 0), (int)K),
+                accumulate_block(blk, K, Kc, lane, min(max((int)hd.x - oh, 0), (int)K),
                                  min(max((int)hd.z - oc, 0), (int)Kc), min(max(n_cold - oc, 0), (int)Kc),
                                  s_vec, g_vec, acc_s, acc_n);
                 uint32_t mine = 0;                     // lane 1..3: social count of mode lane; lane 5..7: neighbour count
@@ -480,7 +500,7 @@ day_kernel(const __grid_constant__ RepArray reps, uint32_t R, uint32_t P, uint32
             const uint2 own = ld_stream_v2(r.vec[parity] + slice);
             const int ds_h = (int)(dg & 0xFFu), dn_h = (int)((dg >> 8) & 0xFFu), ds_c = (int)((dg >> 16) & 0xFFu), dn_c = (int)(dg >> 24);
             uint32_t acc_s = 0, acc_n = 0;
-            accumulate_block(blk, KK & 0xFFFFu, KK >> 16, lane, ds_h, ds_h + dn_h, ds_c, ds_c + dn_c, s_vec, g_vec, acc_s, acc_n);
+            accumulate_block(blk, KK & 0xFFFFu, KK >> 16, lane, ds_h, ds_c, ds_c + dn_c, s_vec, g_vec, acc_s, acc_n);
             acc_s = car_counts(acc_s, (uint32_t)(ds_h + ds_c));
             acc_n = car_counts(acc_n, (uint32_t)(dn_h + dn_c));
             uint32_t cs[4], cn[4];

@@ -22,6 +22,10 @@ struct FillArgs {
     const uint64_t* hub_off; const uint4* hub_deg; uint32_t* hub_codes;
 };
 
+__global__ void fill_u32_kernel(uint32_t* __restrict__ p, uint64_t n, uint32_t v) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
 // One warp per agent: how many of its social / neighbour links point at agents whose mode will sit in shared memory
 // (layout.h, layout_count_hot).  This is the one step of the layout that touches every link, so it runs here, on
 // the CSR the fill kernels need anyway.  Also the range check of the link targets: any target >= N sets *bad.

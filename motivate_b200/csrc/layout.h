@@ -57,6 +57,13 @@ inline void hub_segment(uint32_t rem_hot, uint32_t rem_cold, uint32_t& K, uint32
     if (Kc > kHubUnitRows - K) Kc = kHubUnitRows - K;
 }
 
+// Shared memory holds `vec_cap_words` words of the staged mode vector; the last four are never staged into and the
+// very last one is kept zero by the day kernel.  Unused entries of the link-code arrays ("padding": lanes whose list
+// is shorter than their slice's) hold a code that points there, so they gather mode 0 (Car), which the kernel does
+// not count but derives from the list lengths: no per-link bound check.
+inline uint32_t staged_capacity_agents(uint32_t vec_cap_words) { return (vec_cap_words - 4u) * 16u / 64u * 64u; }
+inline uint32_t pad_code(uint32_t vec_cap_words) { return ((vec_cap_words - 1u) * 4u) << 5; }
+
 struct uint4x { uint32_t x, y, z, w; };   // host-side mirror of CUDA's uint4 (16 bytes)
 
 struct StageRange {                // one contiguous piece of the mode vector staged in shared memory

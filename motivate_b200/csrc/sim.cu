@@ -551,7 +551,7 @@ static int create_impl(uint32_t R, const mvb_population* const* pops, const mvb_
     s->smem_bytes = (size_t)smem_optin;
     s->vec_cap_words = ((uint32_t)smem_optin / 4 - tail_max) & ~3u;
     s->census_smem = sizeof(uint32_t) * census_words;
-    const uint32_t capacity_agents = s->vec_cap_words * 16u / 64u * 64u;
+    const uint32_t capacity_agents = staged_capacity_agents(s->vec_cap_words);
     s->grid = (uint32_t)sms;
 
     s->reps.resize(R);
@@ -763,8 +763,10 @@ static int create_impl(uint32_t R, const mvb_population* const* pops, const mvb_
             MVB_CARVE(s->mem, g->deg, sizeof(uint32_t) * (size_t)L.N_pad);
             MVB_CARVE(s->mem, g->hub_codes, sizeof(uint32_t) * L.hub_codes_len);
             MVB_CARVE(s->mem, g->sell_codes, sizeof(uint32_t) * L.sell_codes_len);
-            MVB_CUDA(cudaMemsetAsync(g->hub_codes.p, 0, g->hub_codes.bytes, s->stream));      // padding = code 0
-            MVB_CUDA(cudaMemsetAsync(g->sell_codes.p, 0, g->sell_codes.bytes, s->stream));
+            // unused entries = the code of the always-zero shared-memory word (layout.h)
+            fill_u32_kernel<<<sms * 8, 256, 0, s->stream>>>(g->hub_codes.as<uint32_t>(), L.hub_codes_len, pad_code(s->vec_cap_words));
+            fill_u32_kernel<<<sms * 8, 256, 0, s->stream>>>(g->sell_codes.as<uint32_t>(), L.sell_codes_len, pad_code(s->vec_cap_words));
+            MVB_CUDA(cudaGetLastError());
             // the caller's CSR went to the device as it is (issue_csr); the fill kernels re-encode it there, then it is dropped
             GraphWork& c = work[graph_of[r]];
             TmpBuf t_tcode;
@@ -805,7 +807,9 @@ static int create_impl(uint32_t R, const mvb_population* const* pops, const mvb_
         {
             const size_t hub_cnt_bytes = sizeof(uint32_t) * 8 * 32 * (size_t)L.n_hub_slices;
             MVB_CARVE(s->mem, rp.stat, 4 * (size_t)NP); MVB_CARVE(s->mem, rp.ws, 4 * (size_t)NP); MVB_CARVE(s->mem, rp.habit, 16 * (size_t)NP);
-            MVB_CARVE(s->mem, rp.vec[0], NP / 4); MVB_CARVE(s->mem, rp.vec[1], NP / 4); MVB_CARVE(s->mem, rp.normvec, NP / 4);
+            // + 64 bytes: the early gather of a padded cold-list entry reads the word a padding code names (at most
+            // 16 bytes past a vector that only just exceeds the shared-memory capacity); its value is never used
+            MVB_CARVE(s->mem, rp.vec[0], NP / 4 + 64); MVB_CARVE(s->mem, rp.vec[1], NP / 4 + 64); MVB_CARVE(s->mem, rp.normvec, NP / 4);
             if (rp.per_agent) MVB_CARVE(s->mem, rp.pa, 20 * (size_t)NP);
             MVB_CARVE(s->mem, rp.tables_f, sizeof(float) * 4 * (rp.H + rp.S));
             MVB_CARVE(s->mem, rp.tables_u, sizeof(uint32_t) * 5 * rp.H);
@@ -868,7 +872,7 @@ static int create_impl(uint32_t R, const mvb_population* const* pops, const mvb_
         d.supp = rp.tables_f.as<float>(); d.desir = rp.tables_f.as<float>() + 4 * rp.H;
         d.cap = rp.tables_u.as<uint32_t>(); d.nres = rp.tables_u.as<uint32_t>() + 4 * rp.H;
         d.cong = rp.cong.as<float>();
-        if (L.hot_words > s->vec_cap_words) { set_error("internal: staged vector larger than its shared-memory slot"); return MVB_ERR_STATE; }
+        if (L.hot_words + 4 > s->vec_cap_words) { set_error("internal: staged vector larger than its shared-memory slot"); return MVB_ERR_STATE; }
         tm_state += now() - ts;
     }
     const double tm3 = now();
@@ -957,7 +961,7 @@ int mvb_partition_plan(const mvb_population* pop, uint32_t S, uint32_t H, uint32
     // same shared-memory capacity as mvb_create* computes on a B200 (227 KB opt-in limit), so the plan is the
     // split a B200 handle really uses
     const uint32_t tail = (tail_words(S, H) + 3u) & ~3u;
-    const uint32_t capacity = ((232448u / 4u - tail) & ~3u) * 16u / 64u * 64u;
+    const uint32_t capacity = staged_capacity_agents((232448u / 4u - tail) & ~3u);
     int rc = build_graph_layout(*pop, H, capacity, L);
     if (rc) return rc;
     std::vector<uint32_t> bounds;
