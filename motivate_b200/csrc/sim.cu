@@ -501,8 +501,8 @@ void mvb_destroy(mvb_sim* s) {
 static int create_impl(uint32_t R, const mvb_population* const* pops, const mvb_tables* const* tabs,
                        const mvb_params* prm, int device, uint32_t rank, uint32_t world, const void* unique_id,
                        mvb_sim** out) {
+    if (out) *out = nullptr;
     if (!out || !pops || !tabs || !prm || R == 0) { set_error("null argument or zero replicas"); return MVB_ERR_ARG; }
-    *out = nullptr;
     int ndev = mvb_device_count();
     if (ndev <= 0) { set_error("no CUDA device available (this library has no CPU path)"); return MVB_ERR_CUDA; }
     if (device < 0 || device >= ndev) { set_error("device %d out of range (have %d)", device, ndev); return MVB_ERR_ARG; }

@@ -72,3 +72,19 @@ def test_product_package_does_not_import_the_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", "Makefile")):
                 assert not pat.search(open(os.path.join(root, f)).read()), (root, f)
+
+
+def test_plain_c_consumer(tmp_path):
+    """include/motivate_b200.h compiles as C99 and a C program linked against the library runs (host-only calls)."""
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    exe = str(tmp_path / "abi_consumer")
+    libdir = os.path.dirname(_ffi.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "c", "abi_consumer.c"), "-o", exe, "-L", libdir, "-lmotivate_b200",
+                    f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.startswith("ok 5000 ")
