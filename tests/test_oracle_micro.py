@@ -131,9 +131,68 @@ def case_duplicate_links_count_twice():
     return pop, tab, GOOD, 0, dict(norm0=WALK)
 
 
+def _resolve_population():
+    pop = tiny_population([WALK], social=[[]], neighbours=[[]], ws=[.2])
+    tab = tables([[.5, .5, .6, .6]], [[BIG] * 4], [[.5, .5, .5, .5]])
+    return pop, tab
+
+
+def case_bad_weather_unchanged_keeps_walker_walking():
+    """Local commute, supportiveness [.5,.5,.6,.6] -> base cost (.2+(1-s))/2 = [.35,.35,.3,.3]; sensitivity 0.2.
+    Bad again today (no change) and the agent walked: resolve -0.1 (agent.rs:205-212) -> mod = (1+.2)-.1 = 1.1 ->
+    Cycle/Walk cost .33 < .35 -> cost ranks Cycle0 Walk1 Car2 PT3.
+    No links, des .5: avg = [.0625,.0625,.0625,(.25+1)/4]; budget ranks Walk0 Car1 PT2 Cycle3.
+    sums Car3 PT5 Cycle3 Walk1 -> Walk.  norm: t all .25 -> last maximum -> Walk.
+    """
+    pop, tab = _resolve_population()
+    return pop, tab, BAD, 0, dict(mode=[WALK], norm=[WALK], row=[1, 1, 0, 0, 1, 0, 0, 1, 1])
+
+
+def case_bad_weather_changed_has_no_resolve():
+    """Same agent, but the weather CHANGED to Bad today: resolve 0.0 (agent.rs:213-215) -> mod = 1.2 -> Cycle/Walk
+    cost .36 > .35 -> cost ranks Car0 PT1 Cycle2 Walk3; budget ranks as above Walk0 Car1 PT2 Cycle3.
+    sums Car1 PT3 Cycle5 Walk3 -> Car.  Row: inactive mode against an active norm.
+    """
+    pop, tab = _resolve_population()
+    return pop, tab, BAD, 1, dict(mode=[CAR], norm=[WALK], row=[0, 1, 0, 1, 0, 0, 0, 0, 0])
+
+
+def case_ownership_limits_budget_and_choice():
+    """Three agents, all PT yesterday, no links, des .5, Local, supportiveness [.3,.3,.9,.9]
+    -> cost [.45,.45,.15,.15] -> ranks Cycle0 Walk1 Car2 PT3 (agent.rs:224-232).
+    avg = [.0625, .3125, .0625, .0625]; ownership multiplies Car / Cycle by 0 or 1 (agent.rs:150-153) and removes
+    them from the choice set (agent.rs:274-285).
+    Agent 0 (car, bike):    budget ranks PT0 Car1 Cycle2 Walk3 -> sums Car3 PT3 Cycle2 Walk4 -> Cycle.
+    Agent 1 (car, no bike): b = [.0625,.3125,0,.0625] -> PT0 Car1 Walk2 Cycle3; allowed {Car,PT,Walk}:
+                            sums Car3 PT3 Walk3 -> three-way tie -> best budget rank -> PT.
+    Agent 2 (neither):      b = [0,.3125,0,.0625] -> PT0 Walk1 Car2 Cycle3; allowed {PT,Walk}: PT3 Walk2 -> Walk.
+    """
+    pop = tiny_population([PT, PT, PT], social=[[]] * 3, neighbours=[[]] * 3, car=[1, 1, 0], bike=[1, 0, 0])
+    tab = tables([[.3, .3, .9, .9]], [[BIG] * 4], [[.5, .5, .5, .5]])
+    return pop, tab, GOOD, 0, dict(mode=[CYCLE, PT, WALK], norm=[WALK] * 3, row=[2, 3, 0, 1, 2, 0, 0, 2, 2])
+
+
+def case_two_neighbourhoods_two_subcultures():
+    """Congestion and the statistics columns are per neighbourhood / per subculture (neighbourhood.rs:57-89,
+    statistics.rs:62-93).  Everybody drove yesterday.  Neighbourhood 0: Car capacity 1 for 2 residents -> modifier
+    1-(2-1)/(2-1) = 0, supportiveness [.5,.5,.5,.9] -> cost [.35,.35,.35,.15] -> ranks Walk0 Car1 PT2 Cycle3.
+    Neighbourhood 1: uncongested, supportiveness .5 -> cost ranks Car0 PT1 Cycle2 Walk3.
+    Subculture 0 des .5 -> sub .25; subculture 1 des [.1,.1,.1,.9] -> sub [.05,.05,.05,.45].
+    A0 (n0,s0): b = [0,.0625,.0625,.0625] -> PT0 Cycle1 Walk2 Car3 -> sums Car4 PT2 Cycle4 Walk2 -> tie -> PT.
+    A1 (n0,s1): avg = [.2625,.0125,.0125,.1125], b = [0,.0125,.0125,.1125] -> Walk0 PT1 Cycle2 Car3 -> Walk sum 0 -> Walk.
+    A2 (n1,s0), A3 (n1,s1): Car has budget rank 0 and cost rank 0 -> Car.
+    """
+    pop = tiny_population([CAR] * 4, social=[[]] * 4, neighbours=[[]] * 4, nbhd=[0, 0, 1, 1], sub=[0, 1, 0, 1])
+    tab = tables([[.5, .5, .5, .9], [.5, .5, .5, .5]], [[1, BIG, BIG, BIG], [BIG] * 4], [[.5, .5, .5, .5], [.1, .1, .1, .9]])
+    return pop, tab, GOOD, 0, dict(mode=[PT, WALK, CAR, CAR], norm=[WALK] * 4, row=[1, 4, 0, 3, 1, 0, 0, 0, 1, 1, 0],
+                                   cong=[[0.0, 1.0, 1.0, 1.0], [1.0, 1.0, 1.0, 1.0]])
+
+
 CASES = [case_social_pull_and_rank_ties, case_norm_tie_takes_last_maximum, case_sum_tie_resolved_by_budget_rank,
          case_distant_commute_key_set, case_congestion_over_capacity, case_partial_congestion_value,
-         case_bad_weather_resolve, case_bad_weather_flips_cost_order, case_duplicate_links_count_twice]
+         case_bad_weather_resolve, case_bad_weather_flips_cost_order, case_duplicate_links_count_twice,
+         case_bad_weather_unchanged_keeps_walker_walking, case_bad_weather_changed_has_no_resolve,
+         case_ownership_limits_budget_and_choice, case_two_neighbourhoods_two_subcultures]
 
 
 def check_case(case, cls):
