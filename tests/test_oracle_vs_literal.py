@@ -97,3 +97,23 @@ def test_map_order_only_matters_on_exact_ties():
         a = a_can[i]
         assert (not a.owns_car) or (not a.owns_bike) or a.commute_length == 0 or len(a.habit) < 4, i
     assert len(diff) < n // 2
+
+
+def test_micro_cases_on_the_literal_model():
+    """The hand-derived expectations of tests/test_oracle_micro.py hold for the HashMap-structured model too."""
+    from test_oracle_micro import CASES, PRM
+    for case in CASES:
+        pop, tab, weather, changed, exp = case()
+        w = np.array([weather ^ 1 if changed else weather, weather], np.uint8)      # day 1 is a weekday
+        days, rows, snaps = literal_states(pop, tab, PRM, w, 2)
+        st = snaps[1]
+        if "mode" in exp:
+            assert st["current_mode"].tolist() == exp["mode"], case.__name__
+        if "norm" in exp:
+            assert st["norm"].tolist() == exp["norm"], case.__name__
+        if "norm0" in exp:
+            assert st["norm"][0] == exp["norm0"], case.__name__
+        if "row" in exp:
+            assert rows[1].tolist() == exp["row"], case.__name__
+        if "cong" in exp:
+            assert np.array_equal(st["congestion"], np.array(exp["cong"], np.float32)), case.__name__
