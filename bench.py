@@ -359,8 +359,12 @@ def run_partitioned(args, rank, local_rank, world, torch, dist, mb):
     ms, launches = sim.last_run_stats()
     clocks = sampler.stop()
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    per_rank = [torch.zeros_like(t) for _ in range(world)]
     if world > 1:
+        dist.all_gather(per_rank, t)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    else:
+        per_rank = [t]
     max_ms = float(t.item())
     days, rows = sim.fetch_rows()
     sim.close()
@@ -377,7 +381,8 @@ def run_partitioned(args, rank, local_rank, world, torch, dist, mb):
            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes / world,
                         "kernel": "day kernel + NCCL exchange, per rank"},
-           "clocks": clocks, "active_mode_last_row": int(rows[0][-1, 0])}
+           "clocks": clocks, "active_mode_last_row": int(rows[0][-1, 0]),
+           "ms_per_step_by_rank": [float(x.item()) / args.steps for x in per_rank]}
     if rank == 0:
         print(json.dumps(out))
     if world > 1:

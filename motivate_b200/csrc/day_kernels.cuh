@@ -420,14 +420,33 @@ day_kernel(const __grid_constant__ RepArray reps, uint32_t R, uint32_t P, uint32
         uint32_t it0 = next_item(), it1 = next_item();
         uint4 meta = meta_of(it0), meta1 = meta_of(it1);
         prefetch_item(it0, meta);
-        if (n_my_hub_slices) {                         // first hub unit of this warp
-            const uint32_t hs = r.hub_begin + p, u = r.hub_unit_begin[hs] + warp;
-            if (u < r.hub_unit_begin[hs + 1]) {
-                const uint4 ua = ld_stream_v4(r.hub_units + 2 * (size_t)u);
-                const uint32_t rows = (ua.z & 0xFFu) + ((ua.z >> 8) & 0xFFu);
-                if (lane == 0 && rows) prefetch_l2(r.hub_codes + (((uint64_t)ua.y << 32) | ua.x), rows * 128u);
+        // this warp's hub units of the part: unit records are read two units ahead, a unit's link codes are pulled
+        // into L2 one unit ahead (the first two records and the first prefetch go out while the staging copies fly)
+        uint32_t hk = 0, hu = 0, hu_end = 0;
+        auto seek_unit = [&] {                         // (hk, hu) -> this warp's next unit at or after it, or hk == n_my_hub_slices
+            while (hk < n_my_hub_slices && hu >= hu_end) {
+                if (++hk < n_my_hub_slices) {
+                    const uint32_t hs = r.hub_begin + p + P * hk;
+                    hu = r.hub_unit_begin[hs] + warp; hu_end = r.hub_unit_begin[hs + 1];
+                }
             }
+        };
+        auto load_unit = [&]() -> uint4 {              // record of the unit at the cursor (zero = none left), cursor moves on
+            uint4 rec = make_uint4(0, 0, 0, 0);
+            if (hk < n_my_hub_slices) { rec = ld_stream_v4(r.hub_units + hu); hu += THREADS / 32; seek_unit(); }
+            return rec;
+        };
+        auto prefetch_unit = [&](const uint4& rec) {
+            const uint32_t rows = (rec.z & 0xFFu) + ((rec.z >> 8) & 0xFFu);
+            if (lane == 0 && rows) prefetch_l2(r.hub_codes + (uint64_t)rec.x * 32, rows * 128u);
+        };
+        if (n_my_hub_slices) {
+            const uint32_t hs = r.hub_begin + p;
+            hu = r.hub_unit_begin[hs] + warp; hu_end = r.hub_unit_begin[hs + 1];
+            seek_unit();
         }
+        uint4 unit0 = load_unit(), unit1 = load_unit();
+        prefetch_unit(unit0);
         mbar_wait(s_bar, phase);
         phase ^= 1u;
 
@@ -436,30 +455,27 @@ day_kernel(const __grid_constant__ RepArray reps, uint32_t R, uint32_t P, uint32
         // 1 024 links (layout.h); a warp takes a unit, its 32 lanes take 32 contiguous chunks of it, and the unit's
         // counts of modes 1..3 are added to the hub's entry of a small global scratch.  The hub slices are finished
         // below like any other slice, so no warp waits for another here and the biggest hubs spread over many warps.
-        for (uint32_t k = 0; k < n_my_hub_slices; ++k) {
-            const uint32_t hs = r.hub_begin + p + P * k;
-            const uint32_t u_end = r.hub_unit_begin[hs + 1];
-            for (uint32_t u = r.hub_unit_begin[hs] + warp; u < u_end; u += THREADS / 32) {
-                const uint4 ua = ld_stream_v4(r.hub_units + 2 * (size_t)u), ub = ld_stream_v4(r.hub_units + 2 * (size_t)u + 1);
-                const uint32_t K = ua.z & 0xFFu, Kc = (ua.z >> 8) & 0xFFu, hub = ua.w;
-                const uint4 hd = ld_stream_v4(reinterpret_cast<const uint4*>(r.hub_deg) + hub);   // ds_hot, dn_hot, ds_cold, dn_cold
-                const uint32_t* blk = r.hub_codes + (((uint64_t)ua.y << 32) | ua.x);
-                const int oh = (int)(ub.x + lane * K), oc = (int)(ub.y + lane * Kc);
-                const int n_cold = (int)(hd.z + hd.w);
-                uint32_t acc_s = 0, acc_n = 0;
-                accumulate_block(blk, K, Kc, lane, min(max((int)hd.x - oh, 0), (int)K),
-                                 min(max((int)hd.z - oc, 0), (int)Kc), min(max(n_cold - oc, 0), (int)Kc),
-                                 s_vec, g_vec, acc_s, acc_n);
-                uint32_t mine = 0;                     // lane 1..3: social count of mode lane; lane 5..7: neighbour count
+        while (unit0.z) {
+            const uint4 unit2 = load_unit();
+            prefetch_unit(unit1);
+            const uint32_t K = unit0.z & 0xFFu, Kc = (unit0.z >> 8) & 0xFFu, hub = unit0.y;
+            const uint32_t* blk = r.hub_codes + (uint64_t)unit0.x * 32;
+            // social hot / social cold / cold links left at the start of the unit -> this lane's chunk of them
+            const int oh = (int)(lane * K), oc = (int)(lane * Kc);
+            uint32_t acc_s = 0, acc_n = 0;
+            accumulate_block(blk, K, Kc, lane, min(max((int)(unit0.z >> 16) - oh, 0), (int)K),
+                             min(max((int)(unit0.w & 0xFFFFu) - oc, 0), (int)Kc), min(max((int)(unit0.w >> 16) - oc, 0), (int)Kc),
+                             s_vec, g_vec, acc_s, acc_n);
+            uint32_t mine = 0;                         // lane 1..3: social count of mode lane; lane 5..7: neighbour count
 #pragma unroll
-                for (int m = 1; m < 4; ++m) {
-                    const uint32_t cs_m = __reduce_add_sync(0xFFFFFFFFu, (acc_s >> (8 * m)) & 0xFFu);
-                    const uint32_t cn_m = __reduce_add_sync(0xFFFFFFFFu, (acc_n >> (8 * m)) & 0xFFu);
-                    if (lane == (uint32_t)m) mine = cs_m;
-                    if (lane == (uint32_t)m + 4u) mine = cn_m;
-                }
-                if (mine) atomicAdd(&r.hub_cnt[(size_t)hub * 8 + lane], mine);
+            for (int m = 1; m < 4; ++m) {
+                const uint32_t cs_m = __reduce_add_sync(0xFFFFFFFFu, (acc_s >> (8 * m)) & 0xFFu);
+                const uint32_t cn_m = __reduce_add_sync(0xFFFFFFFFu, (acc_n >> (8 * m)) & 0xFFu);
+                if (lane == (uint32_t)m) mine = cs_m;
+                if (lane == (uint32_t)m + 4u) mine = cn_m;
             }
+            if (mine) atomicAdd(&r.hub_cnt[(size_t)hub * 8 + lane], mine);
+            unit0 = unit1; unit1 = unit2;
         }
         __syncthreads();                              // the hub counts written above are read by other warps below
 

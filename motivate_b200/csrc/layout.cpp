@@ -202,25 +202,26 @@ int layout_finish(const mvb_population& pop, LayoutWork& W, GraphLayout& L, bool
     L.hub_unit_begin.assign((size_t)L.n_hub_slices + 1, 0);
     for (uint32_t k = 0; k < n_hub_rows; ++k) {
         L.hub_off[k] = hoff;
-        if ((k & 31u) == 0) L.hub_unit_begin[k >> 5] = (uint32_t)(L.hub_units.size() / 2);
+        if ((k & 31u) == 0) L.hub_unit_begin[k >> 5] = (uint32_t)L.hub_units.size();
         if (k >= hubs.size()) continue;
         const uint32_t e = hubs[k];
         const uint32_t ds = (uint32_t)(srp[e + 1] - srp[e]), dn = (uint32_t)(nrp[e + 1] - nrp[e]);
         uint32_t* dg = &L.hub_deg[(size_t)4 * k];
         dg[0] = nsh[e]; dg[1] = nnh[e]; dg[2] = ds - nsh[e]; dg[3] = dn - nnh[e];
         const uint32_t nh = nsh[e] + nnh[e], nc = (uint32_t)d[e] - nh;
+        // what is left of a list at the start of a unit, as far as one unit can see (32 lanes x 32 rows)
+        auto left = [](uint32_t total, uint32_t done) { return total > done ? std::min(total - done, 1024u) : 0u; };
         for (uint32_t dh = 0, dc = 0; dh < nh || dc < nc;) {
             uint32_t K, Kc;
             hub_segment(nh - std::min(dh, nh), nc - std::min(dc, nc), K, Kc);
-            L.hub_units.push_back(uint4x{(uint32_t)hoff, (uint32_t)(hoff >> 32), K | Kc << 8, k});
-            L.hub_units.push_back(uint4x{dh, dc, 0, 0});
+            L.hub_units.push_back(uint4x{(uint32_t)(hoff / 32), k, K | Kc << 8 | left(dg[0], dh) << 16, left(dg[2], dc) | left(nc, dc) << 16});
             hoff += (uint64_t)32 * (K + Kc);
             dh += 32 * K; dc += 32 * Kc;
         }
     }
-    L.hub_unit_begin[L.n_hub_slices] = (uint32_t)(L.hub_units.size() / 2);
-    L.hub_units.push_back(uint4x{0, 0, 0, 0});            // slack: the kernel reads one unit record ahead
-    L.hub_units.push_back(uint4x{0, 0, 0, 0});
+    L.hub_unit_begin[L.n_hub_slices] = (uint32_t)L.hub_units.size();
+    L.hub_units.push_back(uint4x{0, 0, 0, 0});            // slack
+    if (hoff / 32 >= (1ull << 32)) { set_error("hub link lists too long for a 32-bit row offset"); return MVB_ERR_ARG; }
     L.hub_codes_len = hoff + 256;                        // + slack for the row prefetch
     // SELL slices
     L.sell_off.assign(L.n_sell_slices, 0);

@@ -89,7 +89,9 @@ struct GraphLayout {
     std::vector<uint64_t> hub_off;         // [n_hub_slices*32] offset of the hub's first block in hub_codes (u32 units)
     std::vector<uint32_t> hub_deg;         // [n_hub_slices*32][4] ds_hot, dn_hot, ds_cold, dn_cold
     uint64_t hub_codes_len = 0;            // u32 entries of the device array hub_codes (incl. prefetch slack)
-    std::vector<uint4x> hub_units;         // 2 records per unit: {off_lo, off_hi, K | Kc << 8, hub} {done_hot, done_cold, 0, 0}
+    std::vector<uint4x> hub_units;         // one record per unit: {offset in hub_codes / 32, hub (row of hub_deg),
+                                           //  K | Kc << 8 | social hot links left << 16, social cold links left | cold links left << 16},
+                                           //  "left" = at the start of the unit, capped at 1 024
     std::vector<uint32_t> hub_unit_begin;  // [n_hub_slices + 1] first unit of every hub slice
     // SELL
     std::vector<uint64_t> sell_off;        // [n_sell_slices] offset of the slice in sell_codes (u32 units)
