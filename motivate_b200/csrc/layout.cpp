@@ -56,12 +56,20 @@ int layout_begin(const mvb_population& pop, uint32_t H, uint32_t capacity_agents
     }
     auto by_degree = [&](uint32_t a, uint32_t b) { return d[a] != d[b] ? d[a] > d[b] : a < b; };
     std::sort(hubs.begin(), hubs.end(), by_degree);
+    const uint32_t hub_pad = W.hub_pad = round_up((uint32_t)hubs.size(), 64);
+    {   // Deal the hubs (biggest first) round the hub slices like cards, so that every slice - the unit in which hub
+        // work is handed to the parts of a launch - holds about the same number of links.  With the 32 biggest hubs
+        // in one slice, the part that drew it was the straggler of every launch with few replicas.
+        const uint32_t n_hs = hub_pad / 32;
+        std::vector<uint32_t> dealt(hub_pad, kInvalid);
+        for (uint32_t j = 0; j < hubs.size(); ++j) dealt[(j % n_hs) * 32 + j / n_hs] = hubs[j];
+        hubs.swap(dealt);                               // from here on: hubs[slot], kInvalid where a slice has a free place
+    }
     std::vector<uint32_t> tmp, cnt;
     // groups hold ids in increasing order and degrees <= kHubDegree: a stable counting sort gives (degree desc, id asc)
     for (auto& g : groups) counting_sort_desc(g, 0, g.size(), kHubDegree, [&](uint32_t a) { return (uint32_t)d[a]; }, tmp, cnt);
 
     // ---- hot set: all hubs + the highest-degree agents of every group, as many as fit ---------
-    const uint32_t hub_pad = W.hub_pad = round_up((uint32_t)hubs.size(), 64);
     std::vector<uint32_t>& take = W.take;               // hot agents of group h (a prefix in degree order)
     std::vector<uint32_t>& gpad = W.gpad;
     take.assign(H, 0);
@@ -102,8 +110,8 @@ int layout_begin(const mvb_population& pop, uint32_t H, uint32_t capacity_agents
     }
     std::vector<uint8_t>& is_hot = W.is_hot;
     is_hot.assign(N, 0);
-    if (all_hot || hub_pad <= capacity_agents) for (uint32_t e : hubs) is_hot[e] = 1;
-    else for (uint32_t k = 0; k < std::min<size_t>(hubs.size(), capacity_agents); ++k) is_hot[hubs[k]] = 1;
+    for (uint32_t k = 0; k < (all_hot ? hub_pad : std::min(hub_pad, capacity_agents)); ++k)     // hub slots that get staged
+        if (hubs[k] != kInvalid) is_hot[hubs[k]] = 1;
     for (uint32_t h = 0; h < H; ++h)
         for (uint32_t k = 0; k < take[h]; ++k) is_hot[groups[h][k]] = 1;
     return MVB_OK;
@@ -157,7 +165,7 @@ int layout_finish(const mvb_population& pop, LayoutWork& W, GraphLayout& L, bool
     L.n_hub_slices = hub_pad / 32;
     L.n_sell_slices = (L.N_pad - hub_pad) / 32;
     L.int2ext.assign(L.N_pad, kInvalid);
-    for (uint32_t k = 0; k < hubs.size(); ++k) L.int2ext[k] = hubs[k];
+    for (uint32_t k = 0; k < hubs.size(); ++k) L.int2ext[k] = hubs[k];            // hub_pad entries, kInvalid = free place
     for (uint32_t h = 0; h < H; ++h) std::copy(groups[h].begin(), groups[h].end(), L.int2ext.begin() + gstart[h]);
 
     // ---- staged ranges: which pieces of the packed vector go to shared memory, and where
@@ -203,7 +211,7 @@ int layout_finish(const mvb_population& pop, LayoutWork& W, GraphLayout& L, bool
     for (uint32_t k = 0; k < n_hub_rows; ++k) {
         L.hub_off[k] = hoff;
         if ((k & 31u) == 0) L.hub_unit_begin[k >> 5] = (uint32_t)L.hub_units.size();
-        if (k >= hubs.size()) continue;
+        if (hubs[k] == kInvalid) continue;
         const uint32_t e = hubs[k];
         const uint32_t ds = (uint32_t)(srp[e + 1] - srp[e]), dn = (uint32_t)(nrp[e + 1] - nrp[e]);
         uint32_t* dg = &L.hub_deg[(size_t)4 * k];

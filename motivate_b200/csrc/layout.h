@@ -4,7 +4,8 @@
 // link lists of every agent are re-encoded once, at create time, for the day kernel:
 //
 // Internal agent order ("slots"): [ hub agents | neighbourhood 0 | neighbourhood 1 | ... ],
-//   hubs   = agents with more than kHubDegree links, by degree descending
+//   hubs   = agents with more than kHubDegree links, dealt by descending degree round the hub slices (slice j % n,
+//            place j / n), so that every hub slice holds about the same number of links
 //   groups = the remaining residents of one neighbourhood, by degree descending
 //   every region is padded to a multiple of 64 agents with invalid agents, so every
 //   32-agent slice outside the hub region holds residents of ONE neighbourhood and every
@@ -112,7 +113,7 @@ struct GraphLayout {
 //   layout_finish     O(N): final order, slices, offsets, hub blocks
 struct LayoutWork {                        // what layout_begin leaves for the later steps
     std::vector<uint64_t> d;               // [N] total links
-    std::vector<uint32_t> hubs;            // hub ids, (degree desc, id asc)
+    std::vector<uint32_t> hubs;            // [hub_pad] hub id per hub slot (kInvalid = free place), see layout.h on the order
     std::vector<std::vector<uint32_t>> groups;   // per neighbourhood: ids of the other agents, (degree desc, id asc)
     std::vector<uint32_t> take, gpad;      // per group: hot agents (a prefix), size rounded up to 64
     uint32_t hub_pad = 0, capacity_agents = 0;
