@@ -270,7 +270,9 @@ void partition_slices(const GraphLayout& L, uint32_t world, std::vector<uint32_t
         uint64_t w = 0;
         for (uint32_t k = 0; k < 32; ++k) {
             const uint32_t* dg = &L.hub_deg[(size_t)4 * (hs * 32 + k)];
-            w += (uint64_t)dg[0] + dg[1] + 2ull * (dg[2] + dg[3]) + 64;     // cold links cost about twice; + per-agent work
+            // cold links cost about twice a hot one; + per-agent work; x 2.5 because a hub's links are walked in a
+            // phase of their own, between two block barriers (calibrated on 8M agents over 2 B200s)
+            w += 5ull * ((uint64_t)dg[0] + dg[1] + 2ull * (dg[2] + dg[3])) / 2 + 64;
         }
         work[hs] = w;
     }

@@ -250,18 +250,15 @@ int launch_day(mvb_sim* s, uint8_t weather, uint8_t changed) {
         Nccl* n = nccl();
         uint2* vec_next = rp.vec[s->parity ^ 1u].as<uint2>();
         uint2* normvec = rp.normvec.as<uint2>();
-        static const int xchg = getenv("MVB_XCHG") ? atoi(getenv("MVB_XCHG")) : 2;      // TEMP experiment knob
-        if (xchg > 0) {
         MVB_NCCL(n->GroupStart());
         for (uint32_t r = 0; r < s->world; ++r) {
             const size_t b = s->bounds[r], cnt = (size_t)s->bounds[r + 1] - b;
             if (!cnt) continue;
             MVB_NCCL(n->Broadcast(vec_next + b, vec_next + b, cnt * 8, ncclUint8, (int)r, s->comm, s->stream));
-            if (xchg > 1) MVB_NCCL(n->Broadcast(normvec + b, normvec + b, cnt * 8, ncclUint8, (int)r, s->comm, s->stream));
+            MVB_NCCL(n->Broadcast(normvec + b, normvec + b, cnt * 8, ncclUint8, (int)r, s->comm, s->stream));
         }
         MVB_NCCL(n->AllReduce(next, next, s->rec_stride, ncclUint32, ncclSum, s->comm, s->stream));
         MVB_NCCL(n->GroupEnd());
-        }
     }
     s->cursor++;
     s->parity ^= 1u;

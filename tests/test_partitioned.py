@@ -37,7 +37,8 @@ def test_partition_plan_is_balanced_partition():
     for world in (1, 2, 3, 8):
         owner = mb.partition_plan(pop, S, H, world)
         assert owner.min() == 0 and owner.max() == world - 1           # everyone is owned, every rank owns someone
-        links = np.bincount(owner, weights=deg + 64, minlength=world)   # the plan's work measure: links + per-agent work
+        # the plan's work measure: links (a hub's links count 2.5 times, layout.cpp) + per-agent work
+        links = np.bincount(owner, weights=np.where(deg > 252, 2.5 * deg, deg) + 64, minlength=world)
         if world <= 3:                                                  # (slice granularity: 6 000 agents are 190 slices,
             assert links.max() / links.mean() < 1.15, (world, links)    #  the first of them all hubs)
     assert np.array_equal(mb.partition_plan(pop, S, H, 2), mb.partition_plan(pop, S, H, 2))
