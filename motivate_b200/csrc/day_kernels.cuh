@@ -43,13 +43,11 @@ struct RepDev {                     // device-side descriptor of one replica
     uint32_t N, N_pad, S, H, rec_off;
     uint32_t n_hub_slices, n_sell_slices, n_ranges, hot_words;
     uint32_t hub_begin, hub_end, sell_begin, sell_end;   // slices this rank updates (everything unless agent-partitioned)
-    const uint32_t* stat;           // [N_pad] packed static word (decide.cuh) | kStatValid
-    const float* ws;                // [N_pad] weather_sensitivity
-    float4* habit;                  // [N_pad] dense habit, updated in place
+    uint32_t* state;                // [N_pad / 32] slice records (layout.h: static word, list lengths, weather
+                                    // sensitivity, habit of the slice's 32 agents), the habit updated in place
     const float* pa;                // per-agent weights [5][N_pad] or nullptr (uniform)
     uint2* vec[2];                  // [N_pad/32] packed current_mode per slice, double buffered by day parity
     uint2* normvec;                 // [N_pad/32] packed norm per slice
-    const uint32_t* deg;            // [N_pad] SELL agents: ds_hot | dn_hot<<8 | ds_cold<<16 | dn_cold<<24
     const StageRange* ranges;
     const uint64_t* hub_off; const uint4* hub_deg; const uint32_t* hub_codes;   // per hub: block offset, (ds_hot, dn_hot, ds_cold, dn_cold)
     const uint4* hub_units; const uint32_t* hub_unit_begin;   // units (<= 1 024 links) of every hub slice, layout.h
@@ -305,7 +303,7 @@ __device__ __forceinline__ void finish_slice(const RepDev& r, uint32_t slice, ui
     decide<!PER_AGENT>(cs, ds, cn, dn, w, h, s_des + 4 * st_sub(stat), s_cong + 4 * nb, s_cost + 12 * nb + 4 * cm,
                        s_crank[3 * nb + cm], cm, st_car(stat), st_bike(stat), wsv, last, weather, changed, mode, norm);
     if (!valid) { mode = 0; norm = 0; }
-    if (valid) r.habit[agent] = make_float4(h[0], h[1], h[2], h[3]);
+    if (valid) reinterpret_cast<float4*>(r.state + (size_t)slice * kRecWords + kRecHabit)[lane] = make_float4(h[0], h[1], h[2], h[3]);
     // 32 agents x 2 bits -> one u64 (lanes 0-15 in .x, 16-31 in .y)
     const uint32_t sh = (lane & 15u) * 2u;
     const uint32_t mlo = __reduce_or_sync(0xFFFFFFFFu, lane < 16 ? mode << sh : 0u);
@@ -409,13 +407,10 @@ day_kernel(const __grid_constant__ RepArray reps, uint32_t R, uint32_t P, uint32
         };
         auto prefetch_item = [&](uint32_t item, const uint4& m) {
             if (item >= n_items || item < n_my_hub_slices) return;
-            const uint32_t s1 = r.sell_begin + p + P * (item - n_my_hub_slices), a1 = (r.n_hub_slices + s1) * 32;
+            const uint32_t s1 = r.sell_begin + p + P * (item - n_my_hub_slices);
             const uint32_t nrow = (m.z & 0xFFFFu) + (m.z >> 16);
             if (lane == 0 && nrow) prefetch_l2(r.sell_codes + (((uint64_t)m.y << 32) | m.x), nrow * 128u);
-            if (lane == 1) prefetch_l2(r.stat + a1, 128u);
-            if (lane == 2) prefetch_l2(r.deg + a1, 128u);
-            if (lane == 3) prefetch_l2(r.ws + a1, 128u);
-            if (lane == 4) prefetch_l2(r.habit + a1, 512u);
+            if (lane == 1) prefetch_l2(r.state + (size_t)(r.n_hub_slices + s1) * kRecWords, kRecWords * 4u);
         };
         uint32_t it0 = next_item(), it1 = next_item();
         uint4 meta = meta_of(it0), meta1 = meta_of(it1);
@@ -496,11 +491,12 @@ day_kernel(const __grid_constant__ RepArray reps, uint32_t R, uint32_t P, uint32
                 // Car = what is left of each list (count_fields)
                 const uint32_t hcs[4] = {ad.x + ad.z - ca.y - ca.z - ca.w, ca.y, ca.z, ca.w};
                 const uint32_t hcn[4] = {ad.y + ad.w - cb.y - cb.z - cb.w, cb.y, cb.z, cb.w};
-                const uint32_t stat = r.stat[agent];
+                const uint32_t* rec = r.state + (size_t)hs * kRecWords;
+                const uint32_t stat = rec[kRecStat + lane];
                 const uint2 own = r.vec[parity][hs];
                 const uint32_t last = ((lane < 16 ? own.x : own.y) >> ((lane & 15u) * 2u)) & 3u;
-                finish_slice<PER_AGENT>(r, hs, lane, false, hcs, ad.x + ad.z, hcn, ad.y + ad.w, stat, r.ws[agent],
-                                        r.habit[agent], last, uw, s_cong, s_cost, s_crank, s_des, s_rec, weather, changed, parity, st);
+                finish_slice<PER_AGENT>(r, hs, lane, false, hcs, ad.x + ad.z, hcn, ad.y + ad.w, stat, __uint_as_float(rec[kRecWs + lane]),
+                                        reinterpret_cast<const float4*>(rec + kRecHabit)[lane], last, uw, s_cong, s_cost, s_crank, s_des, s_rec, weather, changed, parity, st);
             } else {
             const uint32_t s = r.sell_begin + p + P * (it0 - n_my_hub_slices);
             const uint32_t slice = r.n_hub_slices + s, agent = slice * 32 + lane;
@@ -508,10 +504,11 @@ day_kernel(const __grid_constant__ RepArray reps, uint32_t R, uint32_t P, uint32
             const uint32_t* blk = r.sell_codes + (((uint64_t)meta.y << 32) | meta.x);
             // the agent's own state goes out with the first rows of link codes
             // (all streaming loads bypass L1, which is left to the cold part of the mode vector)
-            const uint32_t stat = ld_stream_u32(r.stat + agent);
-            const uint32_t dg = ld_stream_u32(r.deg + agent);
-            const float wsv = ld_stream_f32(r.ws + agent);
-            const uint4 hraw = ld_stream_v4(reinterpret_cast<const uint4*>(r.habit + agent));
+            const uint32_t* rec = r.state + (size_t)slice * kRecWords + lane;
+            const uint32_t stat = ld_stream_u32(rec + kRecStat);
+            const uint32_t dg = ld_stream_u32(rec + kRecLens);
+            const float wsv = __uint_as_float(ld_stream_u32(rec + kRecWs));
+            const uint4 hraw = ld_stream_v4(reinterpret_cast<const uint4*>(rec + kRecHabit - lane) + lane);
             const float4 hv = make_float4(__uint_as_float(hraw.x), __uint_as_float(hraw.y), __uint_as_float(hraw.z), __uint_as_float(hraw.w));
             const uint2 own = ld_stream_v2(r.vec[parity] + slice);
             const int ds_h = (int)(dg & 0xFFu), dn_h = (int)((dg >> 8) & 0xFFu), ds_c = (int)((dg >> 16) & 0xFFu), dn_c = (int)(dg >> 24);
@@ -544,7 +541,7 @@ __global__ void census_kernel(const RepDev* reps, uint32_t parity, uint32_t* rec
     for (uint32_t k = threadIdx.x; k < W; k += blockDim.x) s_rec[k] = 0;
     __syncthreads();
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t stat = i < r.N_pad ? r.stat[i] : 0u;
+    const uint32_t stat = i < r.N_pad ? r.state[rec_word(i, kRecStat)] : 0u;
     if (stat & kStatValid) {
         const uint2 mv = r.vec[parity][i >> 5], nv = r.normvec[i >> 5];
         const uint32_t l = i & 31u, sh = (l & 15u) * 2u;

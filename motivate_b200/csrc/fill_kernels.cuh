@@ -158,7 +158,8 @@ struct InitArgs {
     const uint8_t* sub; const uint16_t* nbhd; const uint8_t* commute; const uint8_t* car; const uint8_t* bike;
     const float* ws; const float4* habit; const uint8_t* mode; const uint8_t* norm;
     const float* pa_src[5]; float pa_def[5];              // per-agent weights (nullptr = uniform default), agent.rs:44-57
-    uint32_t* stat; float* ws_out; float4* habit_out; float* pa_out;
+    const uint32_t* lens;                                 // [N_pad] list lengths of the SELL agents (written by fill_sell_kernel)
+    uint32_t* state; float* pa_out;                       // slice records (layout.h)
     uint2* vec0; uint2* vec1; uint2* normvec;
 };
 __global__ void init_state_kernel(InitArgs a) {
@@ -167,13 +168,15 @@ __global__ void init_state_kernel(InitArgs a) {
     const uint32_t e = a.int2ext[i];
     const bool valid = e != kInvalid;
     uint32_t mode = 0, norm = 0;
+    float4* habit_out = reinterpret_cast<float4*>(a.state + rec_habit_word(i));
+    a.state[rec_word(i, kRecLens)] = a.lens[i];
     if (valid) {
-        a.stat[i] = 0x80000000u | pack_static(a.nbhd[e], a.sub[e], a.commute[e], a.car[e] != 0, a.bike[e] != 0);
-        a.ws_out[i] = a.ws[e];
-        a.habit_out[i] = a.habit[e];
+        a.state[rec_word(i, kRecStat)] = 0x80000000u | pack_static(a.nbhd[e], a.sub[e], a.commute[e], a.car[e] != 0, a.bike[e] != 0);
+        a.state[rec_word(i, kRecWs)] = __float_as_uint(a.ws[e]);
+        *habit_out = a.habit[e];
         mode = a.mode[e] & 3u; norm = a.norm[e] & 3u;
     } else {
-        a.stat[i] = 0; a.ws_out[i] = 0.f; a.habit_out[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        a.state[rec_word(i, kRecStat)] = 0; a.state[rec_word(i, kRecWs)] = 0; *habit_out = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     if (a.pa_out)
         for (int k = 0; k < 5; ++k)
@@ -187,15 +190,15 @@ __global__ void init_state_kernel(InitArgs a) {
 }
 
 // Ownership part of `intervene` (simulation.rs:383-463): rewrite the car / bike bits of the static words.
-__global__ void set_ownership_kernel(const uint32_t* int2ext, uint32_t N_pad, const uint8_t* car, const uint8_t* bike, uint32_t* stat) {
+__global__ void set_ownership_kernel(const uint32_t* int2ext, uint32_t N_pad, const uint8_t* car, const uint8_t* bike, uint32_t* state) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N_pad) return;
     const uint32_t e = int2ext[i];
     if (e == kInvalid) return;
-    uint32_t w = stat[i];
+    uint32_t w = state[rec_word(i, kRecStat)];
     if (car)  w = (w & ~(1u << 26)) | ((car[e] ? 1u : 0u) << 26);
     if (bike) w = (w & ~(1u << 27)) | ((bike[e] ? 1u : 0u) << 27);
-    stat[i] = w;
+    state[rec_word(i, kRecStat)] = w;
 }
 
 }  // namespace mvb

@@ -65,6 +65,22 @@ inline void hub_segment(uint32_t rem_hot, uint32_t rem_cold, uint32_t& K, uint32
 inline uint32_t staged_capacity_agents(uint32_t vec_cap_words) { return (vec_cap_words - 4u) * 16u / 64u * 64u; }
 inline uint32_t pad_code(uint32_t vec_cap_words) { return ((vec_cap_words - 1u) * 4u) << 5; }
 
+// Per-slice state record: what the 32 agents of a slice read (and, for the habit, write) every weekday sits in one
+// contiguous 896-byte block (7 lines), so a slice needs one base address and one L2 prefetch for all of it:
+//   words [0, 32)    packed static word of agent `lane` (decide.cuh) | kStatValid
+//   words [32, 64)   list lengths of a SELL agent: ds_hot | dn_hot << 8 | ds_cold << 16 | dn_cold << 24
+//   words [64, 96)   weather_sensitivity
+//   words [96, 224)  dense habit, float4 per agent, updated in place
+constexpr uint32_t kRecWords = 224, kRecStat = 0, kRecLens = 32, kRecWs = 64, kRecHabit = 96;
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline size_t rec_word(uint32_t slot, uint32_t field) { return (size_t)(slot >> 5) * kRecWords + field + (slot & 31u); }
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline size_t rec_habit_word(uint32_t slot) { return (size_t)(slot >> 5) * kRecWords + kRecHabit + 4u * (slot & 31u); }
+
 struct uint4x { uint32_t x, y, z, w; };   // host-side mirror of CUDA's uint4 (16 bytes)
 
 struct StageRange {                // one contiguous piece of the mode vector staged in shared memory

@@ -87,7 +87,7 @@ struct Replica {
     uint32_t N = 0, S = 0, H = 0;
     uint32_t rec_width = 0, rec_off = 0;
     std::shared_ptr<Graph> graph;
-    DevBuf stat, ws, habit, vec[2], normvec, pa, tables_f, tables_u, cong, hub_cnt;
+    DevBuf state, vec[2], normvec, pa, tables_f, tables_u, cong, hub_cnt;     // state = slice records (layout.h)
     bool per_agent = false;
 };
 
@@ -806,7 +806,7 @@ static int create_impl(uint32_t R, const mvb_population* const* pops, const mvb_
         if (rp.per_agent) s->any_per_agent = true;
         {
             const size_t hub_cnt_bytes = sizeof(uint32_t) * 8 * 32 * (size_t)L.n_hub_slices;
-            MVB_CARVE(s->mem, rp.stat, 4 * (size_t)NP); MVB_CARVE(s->mem, rp.ws, 4 * (size_t)NP); MVB_CARVE(s->mem, rp.habit, 16 * (size_t)NP);
+            MVB_CARVE(s->mem, rp.state, (size_t)(NP / 32) * kRecWords * 4);
             // + 64 bytes: the early gather of a padded cold-list entry reads the word a padding code names (at most
             // 16 bytes past a vector that only just exceeds the shared-memory capacity); its value is never used
             MVB_CARVE(s->mem, rp.vec[0], NP / 4 + 64); MVB_CARVE(s->mem, rp.vec[1], NP / 4 + 64); MVB_CARVE(s->mem, rp.normvec, NP / 4);
@@ -836,7 +836,7 @@ static int create_impl(uint32_t R, const mvb_population* const* pops, const mvb_
                 ia.pa_src[k] = nullptr; ia.pa_def[k] = pa_def[k];
                 if (rp.per_agent && pa_src[k]) { if ((rc = up(t[9 + k], pa_src[k], 4 * (size_t)N))) return rc; ia.pa_src[k] = t[9 + k].as<float>(); }
             }
-            ia.stat = rp.stat.as<uint32_t>(); ia.ws_out = rp.ws.as<float>(); ia.habit_out = rp.habit.as<float4>();
+            ia.lens = rp.graph->deg.as<uint32_t>(); ia.state = rp.state.as<uint32_t>();
             ia.pa_out = rp.per_agent ? rp.pa.as<float>() : nullptr;
             ia.vec0 = rp.vec[0].as<uint2>(); ia.vec1 = rp.vec[1].as<uint2>(); ia.normvec = rp.normvec.as<uint2>();
             init_state_kernel<<<(NP + 255) / 256, 256, 0, s->stream>>>(ia);
@@ -860,10 +860,10 @@ static int create_impl(uint32_t R, const mvb_population* const* pops, const mvb_
             d.hub_begin = std::min(b, nh); d.hub_end = std::min(e, nh);
             d.sell_begin = std::max(b, nh) - nh; d.sell_end = std::max(e, nh) - nh;
         }
-        d.stat = rp.stat.as<uint32_t>(); d.ws = rp.ws.as<float>(); d.habit = rp.habit.as<float4>();
+        d.state = rp.state.as<uint32_t>();
         d.pa = rp.per_agent ? rp.pa.as<float>() : nullptr;
         d.vec[0] = rp.vec[0].as<uint2>(); d.vec[1] = rp.vec[1].as<uint2>(); d.normvec = rp.normvec.as<uint2>();
-        d.deg = g.deg.as<uint32_t>(); d.ranges = g.ranges.as<StageRange>();
+        d.ranges = g.ranges.as<StageRange>();
         if (rp.hub_cnt.bytes) MVB_CUDA(cudaMemsetAsync(rp.hub_cnt.p, 0, rp.hub_cnt.bytes, s->stream));
         d.hub_units = g.hub_units.as<uint4>(); d.hub_unit_begin = g.hub_unit_begin.as<uint32_t>();
         d.hub_off = g.hub_off.as<uint64_t>(); d.hub_deg = g.hub_deg.as<uint4>(); d.hub_cnt = rp.hub_cnt.as<uint32_t>();
@@ -1015,7 +1015,7 @@ int mvb_set_ownership(mvb_sim* s, uint32_t r, const uint8_t* car, const uint8_t*
     if (bike) { MVB_CUDA(tb.alloc(rp.N)); MVB_CUDA(cudaMemcpyAsync(tb.p, bike, rp.N, cudaMemcpyHostToDevice, s->stream)); }
     set_ownership_kernel<<<(NP + 255) / 256, 256, 0, s->stream>>>(rp.graph->int2ext.as<uint32_t>(), NP,
                                                                   car ? tc.as<uint8_t>() : nullptr, bike ? tb.as<uint8_t>() : nullptr,
-                                                                  rp.stat.as<uint32_t>());
+                                                                  rp.state.as<uint32_t>());
     MVB_CUDA(cudaGetLastError());
     MVB_CUDA(cudaStreamSynchronize(s->stream));   // the caller's buffers and the temporaries are released on return
     return MVB_OK;
@@ -1159,10 +1159,10 @@ int mvb_get_state(mvb_sim* s, uint32_t r, float* habit, uint8_t* cur, uint8_t* l
     const std::vector<uint32_t>& int2ext = rp.graph->L.int2ext;
     const size_t NP = int2ext.size();
     if (habit) {
-        std::vector<float> h(4 * NP);
-        MVB_CUDA(cudaMemcpy(h.data(), rp.habit.p, 16 * NP, cudaMemcpyDeviceToHost));
+        std::vector<uint32_t> recs(NP / 32 * kRecWords);
+        MVB_CUDA(cudaMemcpy(recs.data(), rp.state.p, 4 * recs.size(), cudaMemcpyDeviceToHost));
         for (size_t i = 0; i < NP; ++i)
-            if (int2ext[i] != kInvalid) memcpy(habit + (size_t)4 * int2ext[i], &h[4 * i], 16);
+            if (int2ext[i] != kInvalid) memcpy(habit + (size_t)4 * int2ext[i], &recs[rec_habit_word((uint32_t)i)], 16);
     }
     std::vector<uint2> v(NP / 32);
     if (cur) {
