@@ -396,10 +396,14 @@ day_kernel(const __grid_constant__ RepArray reps, uint32_t R, uint32_t P, uint32
         const uint32_t n_sell = r.sell_end - r.sell_begin;
         const uint32_t n_my_sell = n_sell > p ? (n_sell - p + P - 1) / P : 0;
         const uint32_t n_items = n_my_hub_slices + n_my_sell;
+        uint32_t claim = 0;                            // items are claimed two at a time: bit 0 = the second one is still to come
         auto next_item = [&]() -> uint32_t {
+            if (claim & 1u) { claim ^= 1u; return (claim >> 1) + 1u; }
             uint32_t q = 0;
-            if (lane == 0) q = atomicAdd(s_next, 1u);
-            return __shfl_sync(0xFFFFFFFFu, q, 0);
+            if (lane == 0) q = atomicAdd(s_next, 2u);
+            q = __shfl_sync(0xFFFFFFFFu, q, 0);
+            claim = q << 1 | 1u;
+            return q;
         };
         auto meta_of = [&](uint32_t item) -> uint4 {   // SELL items only; zero for hub items / past the end
             if (item < n_my_hub_slices || item >= n_items) return make_uint4(0, 0, 0, 0);
