@@ -165,7 +165,7 @@ __device__ __forceinline__ void count_fields(uint32_t bits, int base, int ds, ui
 }
 // Fill in the Car count of a list of n links whose other three counts sit in bits 8-31 of acc.
 __device__ __forceinline__ uint32_t car_counts(uint32_t acc, uint32_t n) {
-    return acc | (n - ((acc >> 8) & 0xFFu) - ((acc >> 16) & 0xFFu) - (acc >> 24));
+    return acc | (n - __dp4a(acc, 0x01010100u, 0u));            // n minus the sum of bytes 1..3
 }
 
 // One lane's part of a block of link codes laid out k-major for the warp (layout.h): K hot codes per lane
@@ -329,7 +329,7 @@ __device__ __forceinline__ void finish_slice(const RepDev& r, uint32_t slice, ui
 }
 
 // ---- the weekday kernel ----------------------------------------------------------------------------
-template <bool PER_AGENT, int THREADS>
+template <bool PER_AGENT, int THREADS, uint32_t G>
 __global__ void __launch_bounds__(THREADS, 1)
 day_kernel(const __grid_constant__ RepArray reps, uint32_t R, uint32_t P, uint32_t parity,
            const uint32_t* __restrict__ rec_prev, uint32_t* __restrict__ rec_next, uint32_t weather,
@@ -396,13 +396,16 @@ day_kernel(const __grid_constant__ RepArray reps, uint32_t R, uint32_t P, uint32
         const uint32_t n_sell = r.sell_end - r.sell_begin;
         const uint32_t n_my_sell = n_sell > p ? (n_sell - p + P - 1) / P : 0;
         const uint32_t n_items = n_my_hub_slices + n_my_sell;
-        uint32_t claim = 0;                            // items are claimed two at a time: bit 0 = the second one is still to come
+        // Items are claimed in groups of G consecutive ones (one shared-memory atomic and one shuffle per group: the
+        // claim sits on the critical path of every slice it is made for).  G is a compile-time constant (a run-time
+        // one costs more than it saves); the host picks the instantiation: 4 when a warp gets many items, else 2.
+        uint32_t claim = 0;                            // first item of the group (a multiple of G) | items of it still to come
         auto next_item = [&]() -> uint32_t {
-            if (claim & 1u) { claim ^= 1u; return (claim >> 1) + 1u; }
+            if (claim & (G - 1u)) { const uint32_t it = (claim & ~(G - 1u)) + G - (claim & (G - 1u)); --claim; return it; }
             uint32_t q = 0;
-            if (lane == 0) q = atomicAdd(s_next, 2u);
+            if (lane == 0) q = atomicAdd(s_next, G);
             q = __shfl_sync(0xFFFFFFFFu, q, 0);
-            claim = q << 1 | 1u;
+            claim = q | (G - 1u);
             return q;
         };
         auto meta_of = [&](uint32_t item) -> uint4 {   // SELL items only; zero for hub items / past the end

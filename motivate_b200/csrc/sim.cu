@@ -233,12 +233,17 @@ int launch_day(mvb_sim* s, uint8_t weather, uint8_t changed) {
     AgentWeights uw{s->prm.consistency, s->prm.social_connectivity, s->prm.subculture_connectivity,
                     s->prm.neighbourhood_connectivity, s->prm.average_weight};
     // replica descriptors travel as kernel parameters, kMaxRepsPerLaunch at a time
-#define MVB_LAUNCH(PA, T) day_kernel<PA, T><<<s->grid, T, s->smem_bytes, s->stream>>>( \
+#define MVB_LAUNCH(PA, T, G) day_kernel<PA, T, G><<<s->grid, T, s->smem_bytes, s->stream>>>( \
         s->rep_args[c], R, P, s->parity, prev, next, weather, changed, uw, s->vec_cap_words)
     for (size_t c = 0; c < s->rep_args.size(); ++c) {
         const uint32_t R = std::min<uint32_t>(kMaxRepsPerLaunch, (uint32_t)s->reps.size() - (uint32_t)c * kMaxRepsPerLaunch);
         const uint32_t P = choose_parts(s, (uint32_t)c * kMaxRepsPerLaunch, R);
-        if (s->any_per_agent) MVB_LAUNCH(true, 1024); else MVB_LAUNCH(false, 1024);
+        // work items (slices) a warp of a part gets: with many, they are claimed four at a time, else two (day_kernels.cuh)
+        const RepDev& r0 = s->h_reps[c * kMaxRepsPerLaunch];
+        const uint32_t per_warp = ((r0.hub_end - r0.hub_begin) + (r0.sell_end - r0.sell_begin)) / P / 32;
+        const bool many = per_warp >= 32;
+        if (s->any_per_agent) { if (many) MVB_LAUNCH(true, 1024, 4); else MVB_LAUNCH(true, 1024, 2); }
+        else                  { if (many) MVB_LAUNCH(false, 1024, 4); else MVB_LAUNCH(false, 1024, 2); }
         MVB_CUDA(cudaGetLastError());
         s->last_launches++;
     }
@@ -876,8 +881,10 @@ static int create_impl(uint32_t R, const mvb_population* const* pops, const mvb_
         tm_state += now() - ts;
     }
     const double tm3 = now();
-    MVB_CUDA(cudaFuncSetAttribute(day_kernel<true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
-    MVB_CUDA(cudaFuncSetAttribute(day_kernel<false, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
+    MVB_CUDA(cudaFuncSetAttribute(day_kernel<true, 1024, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
+    MVB_CUDA(cudaFuncSetAttribute(day_kernel<true, 1024, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
+    MVB_CUDA(cudaFuncSetAttribute(day_kernel<false, 1024, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
+    MVB_CUDA(cudaFuncSetAttribute(day_kernel<false, 1024, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
     if (s->census_smem > 48 * 1024)
         MVB_CUDA(cudaFuncSetAttribute(census_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->census_smem));
     s->rank = rank; s->world = world;
