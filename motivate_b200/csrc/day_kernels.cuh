@@ -506,7 +506,7 @@ day_kernel(const __grid_constant__ RepArray reps, uint32_t R, uint32_t P, uint32
                                         reinterpret_cast<const float4*>(rec + kRecHabit)[lane], last, uw, s_cong, s_cost, s_crank, s_des, s_rec, weather, changed, parity, st);
             } else {
             const uint32_t s = r.sell_begin + p + P * (it0 - n_my_hub_slices);
-            const uint32_t slice = r.n_hub_slices + s, agent = slice * 32 + lane;
+            const uint32_t slice = r.n_hub_slices + s;
             const uint32_t KK = meta.z;
             const uint32_t* blk = r.sell_codes + (((uint64_t)meta.y << 32) | meta.x);
             // the agent's own state goes out with the first rows of link codes

@@ -271,13 +271,6 @@ int launch_day(mvb_sim* s, uint8_t weather, uint8_t changed) {
     return MVB_OK;
 }
 
-template <class T>
-int upload(DevBuf& b, const std::vector<T>& v, cudaStream_t st) {
-    MVB_CUDA(b.alloc(sizeof(T) * v.size()));
-    if (!v.empty()) MVB_CUDA(cudaMemcpyAsync(b.p, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice, st));
-    return MVB_OK;
-}
-
 // Device scratch of the create path: comes from the device's stream-ordered pool and goes back to it in stream
 // order, so releasing it never waits for the device.
 struct TmpBuf {
@@ -403,17 +396,6 @@ void unpack_slices(const std::vector<uint32_t>& int2ext, const std::vector<uint2
 }
 
 // Run f(0..n-1) on up to hardware_concurrency host threads (setup only: validation, layout builds).
-template <class F>
-void parallel_for(uint32_t n, F f) {
-    const uint32_t nt = std::max(1u, std::min(n, std::thread::hardware_concurrency()));
-    if (nt <= 1) { for (uint32_t i = 0; i < n; ++i) f(i); return; }
-    std::atomic<uint32_t> next{0};
-    std::vector<std::thread> th;
-    for (uint32_t t = 0; t < nt; ++t)
-        th.emplace_back([&] { for (uint32_t i; (i = next.fetch_add(1)) < n;) f(i); });
-    for (auto& t : th) t.join();
-}
-
 int check_tables(const mvb_tables* t) {
     if (!t || !t->supportiveness || !t->capacity || !t->desirability || t->n_subcultures == 0 ||
         t->n_subcultures > 256 || t->n_neighbourhoods == 0 || t->n_neighbourhoods > 65536) {
