@@ -147,15 +147,6 @@ int layout_finish(const mvb_population& pop, LayoutWork& W, GraphLayout& L, bool
     std::vector<uint32_t> hc(N, 0);
     for (uint32_t i = 0; i < N; ++i)
         if (d[i] <= kHubDegree) { const uint32_t hl = nsh[i] + nnh[i]; hc[i] = hl | ((uint32_t)d[i] - hl) << 16; }
-    // order (hot length desc, degree desc, id asc): the groups are in (degree desc, id asc) order already, so one more
-    // stable pass by hot length does it, separately for the hot part and the cold part of a group
-    std::vector<uint32_t> tmp, cnt;
-    auto hot_len = [&](uint32_t a) { return hc[a] & 0xFFFFu; };
-    for (uint32_t h = 0; h < H; ++h) {
-        counting_sort_desc(groups[h], 0, take[h], kHubDegree, hot_len, tmp, cnt);
-        counting_sort_desc(groups[h], take[h], groups[h].size(), kHubDegree, hot_len, tmp, cnt);
-    }
-
     // ---- internal order ----------------------------------------------------------------------
     std::vector<uint32_t> gstart(H);
     {
@@ -166,7 +157,46 @@ int layout_finish(const mvb_population& pop, LayoutWork& W, GraphLayout& L, bool
     L.n_sell_slices = (L.N_pad - hub_pad) / 32;
     L.int2ext.assign(L.N_pad, kInvalid);
     for (uint32_t k = 0; k < hubs.size(); ++k) L.int2ext[k] = hubs[k];            // hub_pad entries, kInvalid = free place
-    for (uint32_t h = 0; h < H; ++h) std::copy(groups[h].begin(), groups[h].end(), L.int2ext.begin() + gstart[h]);
+    // Group by group: order (hot length desc, degree desc, id asc) — the groups are in (degree desc, id asc) order
+    // already, so one more stable pass by hot length does it, separately for the hot part and the cold part — then
+    // the group's SELL slices.  The list lengths travel with the ids through the sort (high half of a u64), so the
+    // only random reads are one gather per agent; one group's worth of scratch is reused for all groups.
+    L.sell_off.assign(L.n_sell_slices, 0);
+    L.sell_K.assign(L.n_sell_slices, 0);
+    uint64_t off = 0;
+    {
+        std::vector<uint64_t> kv, tmp;
+        std::vector<uint32_t> cnt;
+        uint32_t s = 0;
+        for (uint32_t h = 0; h < H; ++h) {
+            const std::vector<uint32_t>& g = groups[h];
+            kv.resize(g.size());
+            for (size_t i = 0; i < g.size(); ++i) kv[i] = (uint64_t)hc[g[i]] << 32 | g[i];
+            auto sort_part = [&](size_t b, size_t e) {          // stable counting sort by hot length, descending
+                if (e - b < 2) return;
+                cnt.assign(kHubDegree + 2, 0);
+                for (size_t i = b; i < e; ++i) cnt[kHubDegree - (uint32_t)((kv[i] >> 32) & 0xFFFFu) + 1]++;
+                for (uint32_t k = 0; k <= kHubDegree; ++k) cnt[k + 1] += cnt[k];
+                tmp.resize(e - b);
+                for (size_t i = b; i < e; ++i) tmp[cnt[kHubDegree - (uint32_t)((kv[i] >> 32) & 0xFFFFu)]++] = kv[i];
+                std::copy(tmp.begin(), tmp.end(), kv.begin() + b);
+            };
+            sort_part(0, take[h]);
+            sort_part(take[h], g.size());
+            for (size_t i = 0; i < kv.size(); ++i) L.int2ext[gstart[h] + i] = (uint32_t)kv[i];
+            for (size_t b = 0; b < W.gpad[h]; b += 32, ++s) {   // the group's slices: its agents, 32 at a time, then padding
+                uint32_t K = 0, Kc = 0;
+                for (size_t i = b; i < std::min(b + 32, kv.size()); ++i) {
+                    const uint32_t key = (uint32_t)(kv[i] >> 32);
+                    K = std::max(K, key & 0xFFFFu);
+                    Kc = std::max(Kc, key >> 16);
+                }
+                L.sell_off[s] = off;
+                L.sell_K[s] = K | Kc << 16;
+                off += (uint64_t)32 * (K + Kc);
+            }
+        }
+    }
 
     // ---- staged ranges: which pieces of the packed vector go to shared memory, and where
     uint32_t staged = 0;
@@ -231,23 +261,6 @@ int layout_finish(const mvb_population& pop, LayoutWork& W, GraphLayout& L, bool
     L.hub_units.push_back(uint4x{0, 0, 0, 0});            // slack
     if (hoff / 32 >= (1ull << 32)) { set_error("hub link lists too long for a 32-bit row offset"); return MVB_ERR_ARG; }
     L.hub_codes_len = hoff + 256;                        // + slack for the row prefetch
-    // SELL slices
-    L.sell_off.assign(L.n_sell_slices, 0);
-    L.sell_K.assign(L.n_sell_slices, 0);
-    uint64_t off = 0;
-    for (uint32_t s = 0; s < L.n_sell_slices; ++s) {
-        const uint32_t base = hub_pad + s * 32;
-        uint32_t K = 0, Kc = 0;
-        for (uint32_t l = 0; l < 32; ++l) {
-            const uint32_t e = L.int2ext[base + l];
-            if (e == kInvalid) continue;
-            K = std::max(K, hc[e] & 0xFFFFu);
-            Kc = std::max(Kc, hc[e] >> 16);
-        }
-        L.sell_off[s] = off;
-        L.sell_K[s] = K | Kc << 16;
-        off += (uint64_t)32 * (K + Kc);
-    }
     L.sell_codes_len = off + 256;                        // + slack: the kernel's row prefetch may run 2 rows past a slice
     // one 16-byte record per slice; 64 zero records of slack let the kernel prefetch past the end
     L.sell_meta.assign((size_t)L.n_sell_slices + 64, uint4x{0, 0, 0, 0});
