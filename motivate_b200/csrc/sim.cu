@@ -241,7 +241,8 @@ int launch_day(mvb_sim* s, uint8_t weather, uint8_t changed) {
         // work items (slices) a warp of a part gets: with many, they are claimed four at a time, else two (day_kernels.cuh)
         const RepDev& r0 = s->h_reps[c * kMaxRepsPerLaunch];
         const uint32_t per_warp = ((r0.hub_end - r0.hub_begin) + (r0.sell_end - r0.sell_begin)) / P / 32;
-        const bool many = per_warp >= 32;
+        const char* force = getenv("MVB_CLAIM_GROUP");          // tests pin the instantiation: "2" or "4"
+        const bool many = force ? atoi(force) >= 4 : per_warp >= 32;
         if (s->any_per_agent) { if (many) MVB_LAUNCH(true, 1024, 4); else MVB_LAUNCH(true, 1024, 2); }
         else                  { if (many) MVB_LAUNCH(false, 1024, 4); else MVB_LAUNCH(false, 1024, 2); }
         MVB_CUDA(cudaGetLastError());

@@ -219,3 +219,24 @@ def test_create_rejects_bad_indices():
         mb.Simulation([good, bad], [tab, tab], mb.make_params())
     with mb.Simulation([good, good], [tab, tab], mb.make_params()) as sim:      # the handle machinery still works afterwards
         assert sim.n_replicas == 2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("group", ["2", "4"])
+def test_both_claim_group_instantiations(group, monkeypatch):
+    """The day kernel exists in two instantiations (work items claimed two or four at a time); the host picks by the
+    number of slices a warp gets, which small test populations never make large.  MVB_CLAIM_GROUP pins the choice, so
+    both are compared with the oracle here: several replicas, hubs, cold links, an intervention."""
+    monkeypatch.setenv("MVB_CLAIM_GROUP", group)
+    n, S, H, n_days = 40000, 4, 6, 20
+    pops = [mb.synth_population(n, S, H, 5, 10, seed=40 + r) for r in range(3)]
+    tabs = [mb.synth_tables(S, H, n, seed=40 + r) for r in range(3)]
+    w = mb.weather_pattern(n_days, seed=21, p_good_given_good=0.6, p_good_given_bad=0.5)
+    with mb.Simulation(pops, tabs, mb.make_params()) as sim:
+        days, rows = sim.run(w, n_days)
+        states = [sim.get_state(r) for r in range(3)]
+    for r in range(3):
+        o = OracleSimulation(pops[r], tabs[r], mb.make_params())
+        odays, orows = o.run(w, n_days)
+        assert np.array_equal(days, odays) and np.array_equal(rows[r], orows), (group, r)
+        assert_state_equal(states[r], o.get_state(), f"group {group} replica {r}")
