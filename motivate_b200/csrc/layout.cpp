@@ -39,20 +39,42 @@ int layout_begin(const mvb_population& pop, uint32_t H, uint32_t capacity_agents
     // ---- degrees, hubs, neighbourhood groups -------------------------------------------------
     std::vector<uint64_t>& d = W.d;
     d.resize(N);
-    std::vector<uint32_t> gsize(H, 0);
+    // Non-hub agents are bucketed by (neighbourhood, degree): one counting pass, one scatter pass in id order, and every
+    // group comes out in (degree desc, id asc) order.  With very many neighbourhoods the bucket table would not stay
+    // in cache; then the groups are filled in id order and sorted one by one.
+    const bool bucketed = (uint64_t)H * (kHubDegree + 1) <= (1u << 18);
+    std::vector<uint32_t> bucket(bucketed ? (size_t)H * (kHubDegree + 1) : 0, 0), gsize(H, 0);
     for (uint32_t i = 0; i < N; ++i) {
         const uint64_t ds = srp[i + 1] - srp[i], dn = nrp[i + 1] - nrp[i];
         if (ds > 0xFFFFFFFFull || dn > 0xFFFFFFFFull) { set_error("agent %u has more than 2^32 links", i); return MVB_ERR_ARG; }
         d[i] = ds + dn;
-        if (d[i] <= kHubDegree) gsize[pop.neighbourhood[i]]++;
+        if (d[i] <= kHubDegree) {
+            gsize[pop.neighbourhood[i]]++;
+            if (bucketed) bucket[(size_t)pop.neighbourhood[i] * (kHubDegree + 1) + (kHubDegree - (uint32_t)d[i])]++;
+        }
     }
     std::vector<uint32_t>& hubs = W.hubs;
     std::vector<std::vector<uint32_t>>& groups = W.groups;
     groups.resize(H);
-    for (uint32_t h = 0; h < H; ++h) groups[h].reserve(gsize[h]);
-    for (uint32_t i = 0; i < N; ++i) {
-        if (d[i] > kHubDegree) hubs.push_back(i);
-        else groups[pop.neighbourhood[i]].push_back(i);
+    if (bucketed) {
+        for (uint32_t h = 0; h < H; ++h) {               // bucket counts -> first position of the bucket in its group
+            groups[h].resize(gsize[h]);
+            uint32_t at = 0;
+            for (uint32_t k = 0; k <= kHubDegree; ++k) { uint32_t& b = bucket[(size_t)h * (kHubDegree + 1) + k]; const uint32_t c = b; b = at; at += c; }
+        }
+        for (uint32_t i = 0; i < N; ++i) {
+            if (d[i] > kHubDegree) hubs.push_back(i);
+            else { const uint32_t h = pop.neighbourhood[i]; groups[h][bucket[(size_t)h * (kHubDegree + 1) + (kHubDegree - (uint32_t)d[i])]++] = i; }
+        }
+    } else {
+        for (uint32_t h = 0; h < H; ++h) groups[h].reserve(gsize[h]);
+        for (uint32_t i = 0; i < N; ++i) {
+            if (d[i] > kHubDegree) hubs.push_back(i);
+            else groups[pop.neighbourhood[i]].push_back(i);
+        }
+        std::vector<uint32_t> tmp, cnt;
+        // ids in increasing order, degrees <= kHubDegree: a stable counting sort gives (degree desc, id asc)
+        for (auto& g : groups) counting_sort_desc(g, 0, g.size(), kHubDegree, [&](uint32_t a) { return (uint32_t)d[a]; }, tmp, cnt);
     }
     auto by_degree = [&](uint32_t a, uint32_t b) { return d[a] != d[b] ? d[a] > d[b] : a < b; };
     std::sort(hubs.begin(), hubs.end(), by_degree);
@@ -65,9 +87,6 @@ int layout_begin(const mvb_population& pop, uint32_t H, uint32_t capacity_agents
         for (uint32_t j = 0; j < hubs.size(); ++j) dealt[(j % n_hs) * 32 + j / n_hs] = hubs[j];
         hubs.swap(dealt);                               // from here on: hubs[slot], kInvalid where a slice has a free place
     }
-    std::vector<uint32_t> tmp, cnt;
-    // groups hold ids in increasing order and degrees <= kHubDegree: a stable counting sort gives (degree desc, id asc)
-    for (auto& g : groups) counting_sort_desc(g, 0, g.size(), kHubDegree, [&](uint32_t a) { return (uint32_t)d[a]; }, tmp, cnt);
 
     // ---- hot set: all hubs + the highest-degree agents of every group, as many as fit ---------
     std::vector<uint32_t>& take = W.take;               // hot agents of group h (a prefix in degree order)
