@@ -291,7 +291,7 @@ struct TmpBuf {
 };
 
 // Pinned host buffers are slow to make (about 15 ms for 9 MB on the B200 boxes), so the few that set-up needs are
-// kept for the next handle of the process (at most 8; never returned to the driver before exit).
+// kept for the next handle of the process (at most 12; never returned to the driver before exit).
 struct PinnedCache {
     std::mutex m;
     std::vector<std::pair<char*, size_t>> idle;
@@ -307,7 +307,7 @@ struct PinnedCache {
     void put(char* p, size_t cap) {
         if (!p) return;
         std::lock_guard<std::mutex> lk(m);
-        if (idle.size() < 8) idle.emplace_back(p, cap); else cudaFreeHost(p);
+        if (idle.size() < 12) idle.emplace_back(p, cap); else cudaFreeHost(p);
     }
 };
 static PinnedCache& pinned_cache() { static PinnedCache* c = new PinnedCache(); return *c; }
@@ -581,8 +581,9 @@ static int create_impl(uint32_t R, const mvb_population* const* pops, const mvb_
     //         the hot links of every agent (and range-checks the targets), the counts come back to pinned memory
     //   F(g)  crew: waits for the counts, layout_finish (final order, slices, offsets)
     //   S2(g) this thread: layout arrays up, tcode + fill kernels, then the state of the replicas that use g
-    // S1 runs kLook graphs ahead of S2 so that the copies of later graphs hide the host work of earlier ones.
-    constexpr uint32_t kLook = 2, kSlots = kLook + 2;
+    // S1 runs kLook graphs ahead of S2 so that the copies of later graphs hide the host work of earlier ones and
+    // several F jobs run side by side.
+    constexpr uint32_t kLook = 6, kSlots = kLook + 2;          // F jobs of up to kLook + 1 graphs run side by side
     const uint32_t G = (uint32_t)graphs.size();
     struct GraphWork {
         LayoutWork W;
