@@ -154,15 +154,17 @@ def make_inputs(args, replica_ids, pinned=False):
     return [p for p, _ in res], [t for _, t in res]
 
 
-def cpu_reference_throughput(args, n_threads, n_days, warm_days=1):
+def cpu_reference_throughput(args, n_threads, n_days, warm_days=1, shape="dense", agents=None):
     """The reference's CPU path (one single-threaded replica per rayon worker, src/main.rs:89-121) on this box's
-    cores, via the oracle port rebuilt here with -O3 -march=native: agent-days/s over n_days weekdays."""
+    cores, via the oracle port rebuilt here with -O3 -march=native: agent-days/s over n_days weekdays.
+    shape="reference": the reference-shaped twin of the oracle (heap objects, a map per intermediate result)."""
     import motivate_b200 as mb
     from oracle.binding import OracleSimulation
-    base = [mb.synth_population(args.agents, 4, 10, 5, 10, seed=s) for s in range(min(2, n_threads))]
-    tabs = [mb.synth_tables(4, 10, args.agents, seed=s) for s in range(len(base))]
+    agents = agents or args.agents
+    base = [mb.synth_population(agents, 4, 10, 5, 10, seed=s) for s in range(min(2, n_threads))]
+    tabs = [mb.synth_tables(4, 10, agents, seed=s) for s in range(len(base))]
     prm = mb.make_params()
-    sims = [OracleSimulation(base[i % len(base)], tabs[i % len(base)], prm, native=True) for i in range(n_threads)]
+    sims = [OracleSimulation(base[i % len(base)], tabs[i % len(base)], prm, native=True, shape=shape) for i in range(n_threads)]
     w = mb.weather_pattern(warm_days + n_days + 2, seed=0)
 
     def work(sim, lo, hi):
@@ -179,7 +181,7 @@ def cpu_reference_throughput(args, n_threads, n_days, warm_days=1):
     dt = run(1 + warm_days, 1 + warm_days + n_days)
     for s in sims:
         s.close()
-    return n_threads * args.agents * n_days / dt, dt
+    return n_threads * agents * n_days / dt, dt
 
 
 def run_reference(args, rank):
@@ -333,6 +335,13 @@ def main():
         out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                "sample": f"{cores} replicas x {args.agents} agents x {args.cpu_baseline_days} weekdays "
                                          f"({dt:.1f} s), one single-threaded replica per core, oracle -O3 -march=native"}
+        # the same update in the reference's own shape (heap objects, a map per intermediate result): what the dense
+        # port above leaves out of the reference's cost; a smaller sample, it is ~60x slower per core
+        rs_agents = min(args.agents, 50_000)
+        v2, dt2 = cpu_reference_throughput(args, cores, 4, shape="reference", agents=rs_agents)
+        out["cpu_baseline"]["reference_shaped"] = {
+            "value": v2, "unit": UNIT, "cores": cores,
+            "sample": f"{cores} replicas x {rs_agents} agents x 4 weekdays ({dt2:.1f} s), oracle/reference_shaped.cpp -O3 -march=native"}
     if rank == 0:
         print(json.dumps(out))
     if world > 1:

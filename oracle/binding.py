@@ -1,4 +1,5 @@
-"""ctypes binding of the CPU oracle (oracle/motivate_oracle.c).  TEST INFRASTRUCTURE ONLY:
+"""ctypes binding of the CPU oracle (oracle/motivate_oracle.c) and of its reference-shaped twin
+(oracle/reference_shaped.cpp: same entry points over heap objects and per-call maps).  TEST INFRASTRUCTURE ONLY:
 imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
 legs — never by the product package."""
 from __future__ import annotations
@@ -15,33 +16,39 @@ from motivate_b200.api import InterventionData, PopulationData, TablesData, _ptr
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmotivate_oracle.so")
+REFSHAPED_PATH = os.path.join(_HERE, "libmotivate_refshaped.so")
 _libs = {}
 
 
-def build(native=False, out=None):
-    """Compile the oracle with gcc.  native=True adds -O3 -march=native (the README's intent for the
-    reference's release build, README.md:89-92) for CPU-baseline timing on the box it runs on."""
-    out = out or LIB_PATH
+def build(native=False, out=None, shape="dense"):
+    """Compile the oracle with gcc (shape="reference": reference_shaped.cpp with g++).  native=True adds -O3
+    -march=native (the README's intent for the reference's release build, README.md:89-92) for CPU-baseline timing
+    on the box it runs on."""
+    out = out or (LIB_PATH if shape == "dense" else REFSHAPED_PATH)
     flags = ["-O3", "-march=native"] if native else ["-O2", "-march=x86-64-v2"]
-    cmd = ["gcc", *flags, "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-std=c11", "-shared",
-           "-o", out, os.path.join(_HERE, "motivate_oracle.c")]
+    if shape == "dense":
+        cmd = ["gcc", *flags, "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-std=c11", "-shared",
+               "-o", out, os.path.join(_HERE, "motivate_oracle.c")]
+    else:
+        cmd = ["g++", *flags, "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-std=c++17", "-shared",
+               "-o", out, os.path.join(_HERE, "reference_shaped.cpp")]
     subprocess.run(cmd, check=True)
     return out
 
 
-def load(native=False):
-    key = "native" if native else "portable"
+def load(native=False, shape="dense"):
+    key = ("native" if native else "portable", shape)
     if key in _libs:
         return _libs[key]
-    path = LIB_PATH
+    path = LIB_PATH if shape == "dense" else REFSHAPED_PATH
     if native:
-        path = os.path.join(tempfile.gettempdir(), f"libmotivate_oracle_native_{os.getpid()}.so")
+        path = os.path.join(tempfile.gettempdir(), f"libmotivate_{shape}_native_{os.getpid()}.so")
         try:
-            build(native=True, out=path)
+            build(native=True, out=path, shape=shape)
         except Exception:
-            return load(False)
+            return load(False, shape)
     elif not os.path.exists(path):
-        build()
+        build(shape=shape)
     lib = C.CDLL(path, mode=C.RTLD_LOCAL)
     P = C.c_void_p
     sig = {
@@ -63,10 +70,11 @@ def load(native=False):
 
 
 class OracleSimulation:
-    """One replica on the CPU oracle; same method names as motivate_b200.Simulation."""
+    """One replica on the CPU oracle; same method names as motivate_b200.Simulation.  shape="reference" runs the
+    reference-shaped twin (heap objects, per-call maps) instead of the dense oracle."""
 
-    def __init__(self, pop: PopulationData, tab: TablesData, params, native=False):
-        self._lib = load(native)
+    def __init__(self, pop: PopulationData, tab: TablesData, params, native=False, shape="dense"):
+        self._lib = load(native, shape)
         self.pop, self.tab, self.params = pop, tab, params
         self._h = C.c_void_p()
         rc = self._lib.mvo_create(C.byref(pop.struct()), C.byref(tab.struct()), C.byref(params), C.byref(self._h))

@@ -11,7 +11,9 @@
  * What pins this file instead: (1) hand-computed micro-cases in
  * tests/test_oracle_micro.py, (2) an independent literal model that keeps the
  * reference's HashMap / union_of structure (oracle/literal_model.py) and the
- * golden vectors generated from it (tests/golden/).
+ * golden vectors generated from it (tests/golden/), (3) a compiled restatement
+ * in the reference's own shape (oracle/reference_shaped.cpp) compared with this
+ * file on 5k random and 100k BASELINE-shaped agents (tests/test_reference_shaped.py).
  *
  * Dense restatement rules (each proven equivalent to the sparse HashMap code in
  * SURVEY.md §8a):  an absent map key == +0.0f for additive folds and == 1.0f for
