@@ -240,3 +240,25 @@ def test_both_claim_group_instantiations(group, monkeypatch):
         odays, orows = o.run(w, n_days)
         assert np.array_equal(days, odays) and np.array_equal(rows[r], orows), (group, r)
         assert_state_equal(states[r], o.get_state(), f"group {group} replica {r}")
+
+
+@pytest.mark.gpu
+def test_gpu_equals_reference_shaped_model():
+    """The CUDA path against oracle/reference_shaped.cpp directly (heap objects, a map per intermediate result: the
+    reference's own shape), not only against the dense oracle: hubs, duplicates, per-agent weights, every day."""
+    n, S, H, n_days = 4000, 4, 6, 24
+    pop = random_population(n, S, H, 31, per_agent=True, max_deg=12)
+    tab = random_tables(S, H, n, 31)
+    prm = mb.make_params(days_in_habit_average=6)
+    w = mb.weather_pattern(n_days, seed=31, p_good_given_good=0.6, p_good_given_bad=0.5)
+    ref = OracleSimulation(pop, tab, prm, shape="reference")
+    with mb.Simulation(pop, tab, prm) as sim:
+        prev = w[0]
+        for day in range(1, n_days):
+            if day % 7 >= 5:
+                continue
+            sim.step(w[day], prev != w[day])
+            ref.step(w[day], prev != w[day])
+            prev = w[day]
+            assert_state_equal(sim.get_state(), ref.get_state(), f"day {day}")
+            assert np.array_equal(sim.stats_row(), ref.stats_row())
