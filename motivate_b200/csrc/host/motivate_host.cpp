@@ -148,8 +148,8 @@ mvb_population Population::view() const {
 }
 
 // Weather::make_pattern, src/weather.rs:19-50, with the transition matrix and the 0.14 chance of rain on day 0 of
-// src/main.rs:73-85.  The reference draws from StdRng::from_seed([0; 32]) (HC-128); that stream is not restated
-// (SURVEY.md §8 f3), so the pattern is a seeded realisation of the same chain, not the reference's own sequence.
+// src/main.rs:73-85, drawn from a SplitMix64 stream: a seeded realisation of the same chain for synthetic runs.
+// The reference's own sequence (StdRng::from_seed([0; 32]) = HC-128) is make_pattern below.
 std::vector<uint8_t> make_weather_pattern(size_t days, uint64_t seed) {
     SplitMix64 rng(seed * 0x9E3779B97F4A7C15ull + 104729);
     std::vector<uint8_t> w(days, 0);

@@ -9,6 +9,7 @@ together.
 from __future__ import annotations
 
 import os
+import zlib
 from dataclasses import dataclass
 from typing import Optional, Sequence
 
@@ -37,7 +38,8 @@ def prepare(id: str, generate: bool, agents_file: str, scenario_file: str, numbe
     network as (rowptr, col) or a path to config/networks/{id}.yaml; with generate=True and network=None a seeded
     Barabási–Albert network is made (what main.rs --generate does before calling run)."""
     scenario = Scenario.from_file(scenario_file)
-    seed = (abs(hash(id)) % (1 << 31)) if seed is None else seed
+    if seed is None:       # deterministic across processes (str hashes are salted): numeric ids as main.cpp's seed*1000+id
+        seed = int(id) if str(id).isdigit() else zlib.crc32(str(id).encode())
     S, H = len(scenario.subculture_ids), len(scenario.neighbourhood_ids)
     if generate:
         gmm = [tuple(d) for d in distributions] or list(DEFAULT_GMM)
@@ -97,6 +99,12 @@ def run_many(preps: Sequence[Prepared], ids: Sequence[str], total_years: int, we
              output_dir: str = "output", device: int = 0):
     """All replicas of one GPU in one batch (src/main.rs:89-121)."""
     n_days = total_years * 365
+    # mvb_create_batch takes ONE mvb_params for the handle: replicas with other uniform weights must not be batched
+    key = lambda q: (q.consistency, q.social_connectivity, q.subculture_connectivity, q.neighbourhood_connectivity,
+                     q.average_weight, q.flags)
+    if any(key(p.params) != key(preps[0].params) for p in preps):
+        raise ValueError("run_many: all replicas of a batch must share the same uniform weights (mvb_params); "
+                         "batch them separately or give per-agent weight arrays")
     with Simulation([p.population for p in preps], [p.tables for p in preps], preps[0].params, device=device) as sim:
         days, rows = sim.run(weather_pattern, n_days, interventions=[p.intervention for p in preps])
     os.makedirs(output_dir, exist_ok=True)

@@ -151,3 +151,33 @@ def test_simulation_run_end_to_end_on_gpu(tmp_path):
     do, ro = o.run(w, 730, intervention=prep.intervention)
     assert np.array_equal(r1, ro) and np.array_equal(d1, do)
     assert not np.array_equal(ro[259], ro[275])                                # the day-365 intervention moved something
+
+
+def test_default_seed_is_the_same_in_every_process(tmp_path):
+    """prepare() without a seed: the neighbour networks (never saved, rebuilt every run: simulation.rs:165-189) and the
+    resolved intervention must not depend on the process (str hashes are salted per interpreter)."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, zlib, numpy as np; sys.path.insert(0, %r)\n"
+        "from motivate_b200 import simulation\n"
+        "p = simulation.prepare(sys.argv[1], True, '', %r, 12500, 0.7, 0.5, 0.3, 3, 10, [], number_of_social_network_links=3)\n"
+        "h = zlib.crc32(p.population['neighbour_col'].tobytes())\n"
+        "h = zlib.crc32(p.population['social_col'].tobytes(), h)\n"
+        "h = zlib.crc32(p.intervention.owns_car.tobytes(), h); h = zlib.crc32(p.intervention.owns_bike.tobytes(), h)\n"
+        "print(h)\n" % (ROOT, os.path.join(CFG, "scenario.yaml")))
+    outs = {}
+    for ident in ("7", "run-a"):
+        outs[ident] = [subprocess.run([sys.executable, "-c", code, ident], check=True, capture_output=True, text=True,
+                                      env={**os.environ, "PYTHONHASHSEED": str(hs)}).stdout.strip() for hs in (1, 2)]
+        assert outs[ident][0] == outs[ident][1], ident
+    assert outs["7"][0] != outs["run-a"][0]                          # different ids still give different populations
+
+
+def test_run_many_refuses_mixed_uniform_weights(tmp_path):
+    prep = simulation.prepare("1", True, "", os.path.join(CFG, "scenario.yaml"), 12500, 0.7, 0.5, 0.3, 3, 10, [],
+                              number_of_social_network_links=3, seed=1)
+    other = simulation.prepare("2", True, "", os.path.join(CFG, "scenario.yaml"), 12500, 0.9, 0.5, 0.3, 3, 10, [],
+                               number_of_social_network_links=3, seed=2)
+    with pytest.raises(ValueError, match="same uniform weights"):
+        simulation.run_many([prep, other], ["1", "2"], 1, mb.weather_pattern(365, seed=0), output_dir=str(tmp_path))
