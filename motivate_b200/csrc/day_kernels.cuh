@@ -56,6 +56,7 @@ struct RepDev {                     // device-side descriptor of one replica
     const float* supp; const float* desir;       // [H][4], [S][4]
     const uint32_t* cap; const uint32_t* nres;   // [H][4], [H]
     float* cong;                    // [H][4] modifier used by the last step (for mvb_get_state)
+    const uint32_t* int2ext;        // [N_pad] internal slot -> caller's agent id (kInvalid = padding); not read by the day kernel
 };
 
 __host__ __device__ inline uint32_t rec_width(uint32_t S, uint32_t H) { return 4 * H + 7 + S; }

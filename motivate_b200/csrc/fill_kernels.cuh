@@ -20,6 +20,7 @@ struct FillArgs {
     uint32_t n_hub_slices, n_sell_slices;
     const uint4* sell_meta; uint32_t* sell_codes; uint32_t* deg;
     const uint64_t* hub_off; const uint4* hub_deg; uint32_t* hub_codes;
+    uint32_t own_hub_begin, own_hub_end, own_sell_begin, own_sell_end;   // slices whose codes this handle stores (all, unless agent-partitioned)
 };
 
 __global__ void fill_u32_kernel(uint32_t* __restrict__ p, uint64_t n, uint32_t v) {
@@ -83,7 +84,7 @@ __device__ __forceinline__ void put_cold(uint32_t* blk, uint32_t K, uint32_t lan
 __global__ void fill_sell_kernel(FillArgs a) {
     const uint32_t slot_in_sell = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t s = slot_in_sell >> 5, lane = slot_in_sell & 31u;
-    if (s >= a.n_sell_slices) return;
+    if (s >= a.n_sell_slices || s < a.own_sell_begin || s >= a.own_sell_end) return;
     const uint32_t slot = (a.n_hub_slices + s) * 32 + lane;
     const uint32_t e = a.int2ext[slot];
     if (e == kInvalid) { a.deg[slot] = 0; return; }
@@ -108,7 +109,7 @@ __global__ void fill_sell_kernel(FillArgs a) {
 // Lane l of the warp handles list positions by ballot-compaction, so the order of the lists is the link order.
 __global__ void fill_hub_kernel(FillArgs a, uint32_t n_hubs) {
     const uint32_t hub = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
-    if (hub >= n_hubs) return;
+    if (hub >= n_hubs || (hub >> 5) < a.own_hub_begin || (hub >> 5) >= a.own_hub_end) return;
     const uint32_t e = a.int2ext[hub];
     if (e == kInvalid) return;
     const uint4 hd = a.hub_deg[hub];
@@ -199,6 +200,35 @@ __global__ void set_ownership_kernel(const uint32_t* int2ext, uint32_t N_pad, co
     if (car)  w = (w & ~(1u << 26)) | ((car[e] ? 1u : 0u) << 26);
     if (bike) w = (w & ~(1u << 27)) | ((bike[e] ? 1u : 0u) << 27);
     state[rec_word(i, kRecStat)] = w;
+}
+
+// `intervene` (simulation.rs:304-464) as ONE launch for every replica whose intervention falls on the day: the host
+// has resolved it to new tables and ownership bits (caller's agent order), staged in device scratch before the day
+// loop starts; blockIdx.y picks the entry.  Tables: supportiveness[H][4] | desirability[S][4] and capacity[H][4].
+struct IvDev {
+    uint32_t replica, has_tables;
+    const uint8_t* car; const uint8_t* bike;              // [N] or nullptr (= unchanged)
+    const float* tf; const uint32_t* tu;                  // staged tables (has_tables)
+};
+struct IvRep {                                            // what the kernel needs of a replica
+    const uint32_t* int2ext; uint32_t* state; float* tables_f; uint32_t* tables_u; uint32_t N_pad, S, H;
+};
+__global__ void apply_interventions_kernel(const IvDev* __restrict__ ivs, const IvRep* __restrict__ reps) {
+    const IvDev iv = ivs[blockIdx.y];
+    const IvRep r = reps[iv.replica];
+    if (iv.has_tables && blockIdx.x == 0) {
+        for (uint32_t k = threadIdx.x; k < 4 * (r.H + r.S); k += blockDim.x) r.tables_f[k] = iv.tf[k];
+        for (uint32_t k = threadIdx.x; k < 4 * r.H; k += blockDim.x) r.tables_u[k] = iv.tu[k];
+    }
+    if (!iv.car && !iv.bike) return;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < r.N_pad; i += gridDim.x * blockDim.x) {
+        const uint32_t e = r.int2ext[i];
+        if (e == kInvalid) continue;
+        uint32_t w = r.state[rec_word(i, kRecStat)];
+        if (iv.car)  w = (w & ~(1u << 26)) | ((iv.car[e] ? 1u : 0u) << 26);
+        if (iv.bike) w = (w & ~(1u << 27)) | ((iv.bike[e] ? 1u : 0u) << 27);
+        r.state[rec_word(i, kRecStat)] = w;
+    }
 }
 
 }  // namespace mvb

@@ -22,6 +22,7 @@
 
 #include "day_kernels.cuh"
 #include "fill_kernels.cuh"
+#include "setup_kernels.cuh"
 #include "layout.h"
 #include "mvb_internal.h"
 
@@ -164,6 +165,12 @@ struct mvb_sim {
     uint32_t rank = 0, world = 1;
     ncclComm_t comm = nullptr;
     std::vector<uint32_t> bounds;        // [world+1] global slice index where each rank's range starts
+    uint32_t own[4] = {0, 0, 0, 0};      // this rank's hub slices [0],[1]) and SELL slices [2],[3])
+    // interventions of the current run, staged before the day loop (apply_interventions_kernel)
+    DevBuf d_ivreps;                     // IvRep[R]
+    char* iv_pinned = nullptr;           // library-owned pinned staging: the caller's arrays are only borrowed for the call
+    size_t iv_pinned_cap = 0;
+    cudaEvent_t iv_ev = nullptr;         // the copy out of iv_pinned has finished
 };
 
 namespace {
@@ -312,80 +319,6 @@ struct PinnedCache {
 };
 static PinnedCache& pinned_cache() { static PinnedCache* c = new PinnedCache(); return *c; }
 
-// Two pinned staging slots for the arrays the layout builder leaves in pageable vectors: a copy out of pageable
-// memory would make the host wait for everything queued on the stream; out of a slot it is asynchronous.  A slot is
-// reused once the copies issued from it have finished (event).
-struct PinnedRing {
-    char* base[2] = {nullptr, nullptr};
-    size_t cap[2] = {0, 0}, used = 0;
-    cudaEvent_t ev[2] = {nullptr, nullptr};
-    int cur = 1;
-    ~PinnedRing() {
-        for (int k = 0; k < 2; ++k) { if (ev[k]) { cudaEventSynchronize(ev[k]); cudaEventDestroy(ev[k]); } pinned_cache().put(base[k], cap[k]); }
-    }
-    cudaError_t begin(size_t bytes) {                         // next slot, at least `bytes` large
-        cur ^= 1; used = 0;
-        cudaError_t e;
-        if (!ev[cur]) { if ((e = cudaEventCreateWithFlags(&ev[cur], cudaEventDisableTiming)) != cudaSuccess) return e; }
-        else if ((e = cudaEventSynchronize(ev[cur])) != cudaSuccess) return e;
-        if (bytes > cap[cur]) {
-            pinned_cache().put(base[cur], cap[cur]);
-            base[cur] = nullptr; cap[cur] = 0;
-            if ((e = pinned_cache().get(bytes, &base[cur], &cap[cur])) != cudaSuccess) { base[cur] = nullptr; cap[cur] = 0; return e; }
-        }
-        return cudaSuccess;
-    }
-    template <class T> const T* put(const std::vector<T>& v) {
-        char* dst = base[cur] + used;
-        memcpy(dst, v.data(), sizeof(T) * v.size());
-        used += (sizeof(T) * v.size() + 255) & ~(size_t)255;
-        return reinterpret_cast<const T*>(dst);
-    }
-    template <class T> static size_t need(const std::vector<T>& v) { return (sizeof(T) * v.size() + 255) & ~(size_t)255; }
-    cudaError_t end(cudaStream_t st) { return cudaEventRecord(ev[cur], st); }
-};
-
-template <class T>
-int upload_staged(Arena& mem, DevBuf& b, const std::vector<T>& v, PinnedRing& ring, cudaStream_t st) {
-    MVB_CARVE(mem, b, sizeof(T) * v.size());
-    if (!v.empty()) MVB_CUDA(cudaMemcpyAsync(b.p, ring.put(v), sizeof(T) * v.size(), cudaMemcpyHostToDevice, st));
-    return MVB_OK;
-}
-
-// Host threads that run `job(i)` for i = 0..n-1 in index order while the caller consumes the results as they come:
-// wait(i) blocks until job i is done.  The destructor stops handing out jobs and joins.
-class Crew {
-public:
-    template <class F>
-    Crew(uint32_t n, F job) : n_(n), done_(n, 0) {
-        const uint32_t nt = std::max(1u, std::min(n, std::thread::hardware_concurrency()));
-        for (uint32_t t = 0; t < nt; ++t)
-            th_.emplace_back([this, job] {
-                for (uint32_t i; !stop_.load() && (i = next_.fetch_add(1)) < n_;) {
-                    job(i);
-                    { std::lock_guard<std::mutex> lk(m_); done_[i] = 1; }
-                    cv_.notify_all();
-                }
-            });
-    }
-    void wait(uint32_t i) {
-        std::unique_lock<std::mutex> lk(m_);
-        cv_.wait(lk, [&] { return done_[i] != 0; });
-    }
-    ~Crew() {
-        stop_.store(true);
-        for (auto& t : th_) t.join();
-    }
-private:
-    uint32_t n_;
-    std::vector<char> done_;
-    std::atomic<uint32_t> next_{0};
-    std::atomic<bool> stop_{false};
-    std::mutex m_;
-    std::condition_variable cv_;
-    std::vector<std::thread> th_;
-};
-
 // the u64 of one slice (lanes 0-15 in .x, 16-31 in .y, as finish_slice packs them) -> 32 two-bit values
 void unpack_slices(const std::vector<uint32_t>& int2ext, const std::vector<uint2>& in, uint8_t* values) {
     for (size_t i = 0; i < int2ext.size(); ++i) {
@@ -396,7 +329,17 @@ void unpack_slices(const std::vector<uint32_t>& int2ext, const std::vector<uint2
     }
 }
 
-// Run f(0..n-1) on up to hardware_concurrency host threads (setup only: validation, layout builds).
+// The internal order lives on the device (create.cuh builds it there); the host copy is fetched when a caller asks
+// for state in its own agent order.
+int host_int2ext(mvb_sim* s, Graph& g) {
+    if (!g.L.int2ext.empty() || g.L.N_pad == 0) return MVB_OK;
+    MVB_CUDA(cudaSetDevice(s->device));
+    MVB_CUDA(cudaStreamSynchronize(s->stream));
+    g.L.int2ext.resize(g.L.N_pad);
+    MVB_CUDA(cudaMemcpy(g.L.int2ext.data(), g.int2ext.p, 4 * (size_t)g.L.N_pad, cudaMemcpyDeviceToHost));
+    return MVB_OK;
+}
+
 int check_tables(const mvb_tables* t) {
     if (!t || !t->supportiveness || !t->capacity || !t->desirability || t->n_subcultures == 0 ||
         t->n_subcultures > 256 || t->n_neighbourhoods == 0 || t->n_neighbourhoods > 65536) {
@@ -412,41 +355,6 @@ int upload_tables(mvb_sim* s, Replica& r, const mvb_tables* t) {
     MVB_CUDA(cudaMemcpyAsync(r.tables_f.as<float>() + 4 * r.H, t->desirability, sizeof(float) * 4 * r.S,
                              cudaMemcpyHostToDevice, s->stream));
     MVB_CUDA(cudaMemcpyAsync(r.tables_u.p, t->capacity, sizeof(uint32_t) * 4 * r.H, cudaMemcpyHostToDevice, s->stream));
-    return MVB_OK;
-}
-
-int check_population_arrays(const mvb_population* p) {          // O(1): what must hold before anything is read
-    if (!p || p->n_agents == 0 || !p->subculture || !p->neighbourhood || !p->commute || !p->owns_car ||
-        !p->owns_bike || !p->weather_sensitivity || !p->habit || !p->current_mode || !p->norm ||
-        !p->social_rowptr || !p->neighbour_rowptr) {
-        set_error("population has null arrays or zero agents");
-        return MVB_ERR_ARG;
-    }
-    const uint64_t es = p->social_rowptr[p->n_agents], en = p->neighbour_rowptr[p->n_agents];
-    if ((es && !p->social_col) || (en && !p->neighbour_col)) { set_error("null column array"); return MVB_ERR_ARG; }
-    if (es >= (1ull << 40) || en >= (1ull << 40)) { set_error("rowptr[n_agents] is not a plausible link count"); return MVB_ERR_ARG; }
-    return MVB_OK;
-}
-
-// O(N), or O(N + E) with check_cols: every index in range.  mvb_create* leaves the link targets to count_hot_kernel.
-int validate_population(const mvb_population* p, const mvb_tables* t, bool check_cols) {
-    if (int rc = check_population_arrays(p)) return rc;
-    const uint32_t N = p->n_agents;
-    for (uint32_t i = 0; i < N; ++i) {
-        if (p->subculture[i] >= t->n_subcultures) { set_error("agent %u: subculture index %u out of range (\"Subculture not found\")", i, p->subculture[i]); return MVB_ERR_ARG; }
-        if (p->neighbourhood[i] >= t->n_neighbourhoods) { set_error("agent %u: neighbourhood index %u out of range", i, p->neighbourhood[i]); return MVB_ERR_ARG; }
-        if (p->commute[i] > 2 || p->current_mode[i] > 3 || p->norm[i] > 3) { set_error("agent %u: bad commute/mode/norm code", i); return MVB_ERR_ARG; }
-    }
-    for (int g = 0; g < 2; ++g) {
-        const uint64_t* rp = g ? p->neighbour_rowptr : p->social_rowptr;
-        const uint32_t* cl = g ? p->neighbour_col : p->social_col;
-        if (rp[0] != 0) { set_error("rowptr[0] must be 0"); return MVB_ERR_ARG; }
-        for (uint32_t i = 0; i < N; ++i)
-            if (rp[i + 1] < rp[i]) { set_error("rowptr not monotone at %u", i); return MVB_ERR_ARG; }
-        if (rp[N] && !cl) { set_error("null column array"); return MVB_ERR_ARG; }
-        for (uint64_t e = 0; check_cols && e < rp[N]; ++e)
-            if (cl[e] >= N) { set_error("link target %u out of range", cl[e]); return MVB_ERR_ARG; }
-    }
     return MVB_OK;
 }
 
@@ -476,6 +384,8 @@ void mvb_destroy(mvb_sim* s) {
     if (s->comm && nccl()) nccl()->CommDestroy(s->comm);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->iv_ev) cudaEventDestroy(s->iv_ev);
+    pinned_cache().put(s->iv_pinned, s->iv_pinned_cap);
     if (s->stream) cudaStreamDestroy(s->stream);
     const double t2 = now();
     s->mem.chunks.clear();
@@ -486,424 +396,9 @@ void mvb_destroy(mvb_sim* s) {
                 t1 - t0, t2 - t1, t3 - t2, now() - t3);
 }
 
-static int create_impl(uint32_t R, const mvb_population* const* pops, const mvb_tables* const* tabs,
-                       const mvb_params* prm, int device, uint32_t rank, uint32_t world, const void* unique_id,
-                       mvb_sim** out) {
-    if (out) *out = nullptr;
-    if (!out || !pops || !tabs || !prm || R == 0) { set_error("null argument or zero replicas"); return MVB_ERR_ARG; }
-    int ndev = mvb_device_count();
-    if (ndev <= 0) { set_error("no CUDA device available (this library has no CPU path)"); return MVB_ERR_CUDA; }
-    if (device < 0 || device >= ndev) { set_error("device %d out of range (have %d)", device, ndev); return MVB_ERR_ARG; }
-    for (uint32_t r = 0; r < R; ++r) {
-        int rc = check_tables(tabs[r]);
-        if (rc) return rc;
-    }
-    // MVB_TIMING=1 prints where the set-up time went (stderr)
-    const bool timing = getenv("MVB_TIMING") != nullptr;
-    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-    const double tm0 = now();
-    double tm_wait = 0, tm_graph = 0, tm_state = 0;
-    for (uint32_t r = 0; r < R; ++r)
-        if (int rc = check_population_arrays(pops[r])) return rc;
-    const double tm1 = now();
-    MVB_CUDA(cudaSetDevice(device));
-    std::unique_ptr<mvb_sim, void (*)(mvb_sim*)> sp(new (std::nothrow) mvb_sim(), mvb_destroy);
-    mvb_sim* s = sp.get();
-    if (!s) { set_error("out of memory"); return MVB_ERR_NOMEM; }
-    s->device = device;
-    s->prm = *prm;
-    {   // the uniform-weight kernel's division shortcut (decide.cuh FAST_SHARES) needs tame connectivities;
-        // anything else goes through the general kernel, which divides with plain IEEE `/`
-        auto tame = [](float w) { return w >= 0x1p-60f && w <= 0x1p60f; };
-        if (!tame(prm->social_connectivity) || !tame(prm->neighbourhood_connectivity)) s->any_per_agent = true;
-    }
-    MVB_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-    MVB_CUDA(cudaEventCreate(&s->ev0));
-    MVB_CUDA(cudaEventCreate(&s->ev1));
-
-    // shared-memory budget: everything the device lets one block opt in to (227 KB on B200); what the
-    // tables do not need holds the staged mode vector
-    int sms = 0, smem_optin = 0;
-    MVB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-    MVB_CUDA(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-    uint32_t tail_max = 0, census_words = 0;
-    for (uint32_t r = 0; r < R; ++r) {
-        tail_max = std::max(tail_max, tail_words(tabs[r]->n_subcultures, tabs[r]->n_neighbourhoods));
-        census_words = std::max(census_words, rec_width(tabs[r]->n_subcultures, tabs[r]->n_neighbourhoods));
-    }
-    tail_max = (tail_max + 3u) & ~3u;
-    if ((uint64_t)tail_max * 4 + 4096 > (uint64_t)smem_optin) {
-        set_error("too many neighbourhoods/subcultures: the per-block tables need %u bytes of shared memory", tail_max * 4);
-        return MVB_ERR_ARG;
-    }
-    s->smem_bytes = (size_t)smem_optin;
-    s->vec_cap_words = ((uint32_t)smem_optin / 4 - tail_max) & ~3u;
-    s->census_smem = sizeof(uint32_t) * census_words;
-    const uint32_t capacity_agents = staged_capacity_agents(s->vec_cap_words);
-    s->grid = (uint32_t)sms;
-
-    s->reps.resize(R);
-    s->h_reps.resize(R);
-    // distinct link graphs (replicas that pass the same graph + neighbourhood arrays share one), laid out in parallel
-    std::vector<std::shared_ptr<Graph>> graphs;
-    std::vector<uint32_t> graph_of(R), first_rep;
-    for (uint32_t r = 0; r < R; ++r) {
-        const mvb_population* p = pops[r];
-        const void* key[5] = {p->social_rowptr, p->social_col, p->neighbour_rowptr, p->neighbour_col, p->neighbourhood};
-        uint32_t g = 0;
-        for (; g < graphs.size(); ++g)
-            if (pops[first_rep[g]]->n_agents == p->n_agents && !memcmp(graphs[g]->key, key, sizeof key) &&
-                tabs[first_rep[g]]->n_neighbourhoods == tabs[r]->n_neighbourhoods) break;
-        if (g == graphs.size()) {
-            graphs.push_back(std::make_shared<Graph>());
-            memcpy(graphs.back()->key, key, sizeof key);
-            first_rep.push_back(r);
-        }
-        graph_of[r] = g;
-    }
-    {   // first chunk of device memory: an estimate of everything the graphs and replicas will need (link codes ~ the
-        // caller's CSR columns + slice padding, 12 B per agent of graph arrays, 27-47 B per agent of state)
-        size_t est = 64u << 20;
-        for (uint32_t g = 0; g < graphs.size(); ++g) {
-            const mvb_population* p = pops[first_rep[g]];
-            const size_t e = p->social_rowptr[p->n_agents] + p->neighbour_rowptr[p->n_agents];
-            est += 4 * e + e / 4 + 16 * (size_t)p->n_agents + (1u << 20);
-        }
-        for (uint32_t r = 0; r < R; ++r) est += 48 * (size_t)pops[r]->n_agents + (1u << 16);
-        size_t free_b = 0, total_b = 0;
-        MVB_CUDA(cudaMemGetInfo(&free_b, &total_b));
-        s->mem.chunk_bytes = std::max<size_t>(256u << 20, std::min(est, free_b / 2));
-    }
-    // Set-up is a pipeline between host threads (the crew) and the device, driven by this thread:
-    //   A(r)  crew: range checks of replica r's arrays, residents per neighbourhood, and, if r is the first replica
-    //         of its graph g, layout_begin (degree order, hot set)
-    //   S1(g) this thread: the caller's CSR goes up as it is; once A is done, is_hot goes up, count_hot_kernel counts
-    //         the hot links of every agent (and range-checks the targets), the counts come back to pinned memory
-    //   F(g)  crew: waits for the counts, layout_finish (final order, slices, offsets)
-    //   S2(g) this thread: layout arrays up, tcode + fill kernels, then the state of the replicas that use g
-    // S1 runs kLook graphs ahead of S2 so that the copies of later graphs hide the host work of earlier ones and
-    // several F jobs run side by side.
-    constexpr uint32_t kLook = 6, kSlots = kLook + 2;          // F jobs of up to kLook + 1 graphs run side by side
-    const uint32_t G = (uint32_t)graphs.size();
-    struct GraphWork {
-        LayoutWork W;
-        TmpBuf srp, scol, nrp, ncol, is_hot, counts, flag;
-        uint32_t* h_counts = nullptr;                            // pinned: nsh[N] | nnh[N] | bad flag
-    };
-    std::vector<GraphWork> work(G);
-    struct Slots {                                               // pinned buffers the counts come back into
-        char* base[kSlots] = {};
-        size_t cap[kSlots] = {};
-        cudaEvent_t ev[kSlots] = {};
-        ~Slots() { for (uint32_t k = 0; k < kSlots; ++k) { if (ev[k]) { cudaEventSynchronize(ev[k]); cudaEventDestroy(ev[k]); } pinned_cache().put(base[k], cap[k]); } }
-    } slots;
-    {
-        size_t slot_bytes = 0;
-        for (uint32_t g = 0; g < G; ++g) slot_bytes = std::max(slot_bytes, 9 * (size_t)pops[first_rep[g]]->n_agents + 64);
-        for (uint32_t k = 0; k < std::min(kSlots, G); ++k) {
-            MVB_CUDA(pinned_cache().get(slot_bytes, &slots.base[k], &slots.cap[k]));
-            MVB_CUDA(cudaEventCreateWithFlags(&slots.ev[k], cudaEventDisableTiming));
-        }
-    }
-    struct Signals {                                             // S1(g) queued -> F(g) may wait for its event
-        std::mutex m;
-        std::condition_variable cv;
-        std::vector<char> queued;
-        bool abort = false;
-    } sig;
-    sig.queued.assign(G, 0);
-    // crew job list: A(r) in replica order; F(g) follows the A of graph g + kLook
-    std::vector<std::pair<char, uint32_t>> jobs;
-    std::vector<uint32_t> job_a(R), job_f(G);
-    for (uint32_t r = 0; r < R; ++r) {
-        job_a[r] = (uint32_t)jobs.size();
-        jobs.emplace_back('A', r);
-        const uint32_t g = graph_of[r];
-        if (first_rep[g] == r && g >= kLook) { job_f[g - kLook] = (uint32_t)jobs.size(); jobs.emplace_back('F', g - kLook); }
-    }
-    for (uint32_t g = G > kLook ? G - kLook : 0; g < G; ++g) { job_f[g] = (uint32_t)jobs.size(); jobs.emplace_back('F', g); }
-    std::vector<int> job_rc(jobs.size(), MVB_OK);
-    std::vector<std::string> job_msg(jobs.size());
-    std::vector<std::vector<uint32_t>> nres_all(R);
-    Crew crew((uint32_t)jobs.size(), [&](uint32_t j) {
-        auto fail = [&](int rc) { job_rc[j] = rc; job_msg[j] = mvb_last_error(); };
-        if (jobs[j].first == 'A') {
-            const uint32_t r = jobs[j].second, g = graph_of[r];
-            if (int rc = validate_population(pops[r], tabs[r], false)) return fail(rc);
-            nres_all[r].assign(tabs[r]->n_neighbourhoods, 0u);
-            for (uint32_t i = 0; i < pops[r]->n_agents; ++i) nres_all[r][pops[r]->neighbourhood[i]]++;
-            if (first_rep[g] != r) return;
-            if (int rc = layout_begin(*pops[r], tabs[r]->n_neighbourhoods, capacity_agents, graphs[g]->L, work[g].W)) return fail(rc);
-        } else {
-            const uint32_t g = jobs[j].second;
-            {
-                std::unique_lock<std::mutex> lk(sig.m);
-                sig.cv.wait(lk, [&] { return sig.queued[g] || sig.abort; });
-                if (sig.abort) return;
-            }
-            cudaSetDevice(device);
-            if (cudaEventSynchronize(slots.ev[g % kSlots]) != cudaSuccess) { set_error("waiting for the device failed"); return fail(MVB_ERR_CUDA); }
-            GraphWork& w = work[g];
-            const uint32_t N = pops[first_rep[g]]->n_agents;
-            if (w.h_counts[2 * (size_t)N]) { set_error("a link target is out of range"); return fail(MVB_ERR_ARG); }
-            w.W.nsh = w.h_counts;
-            w.W.nnh = w.h_counts + N;
-            if (int rc = layout_finish(*pops[first_rep[g]], w.W, graphs[g]->L, false)) return fail(rc);
-            LayoutWork done;                                     // only is_hot's device copy is still needed
-            std::swap(done, w.W);
-        }
-    });
-    struct Abort {                                               // declared after the crew: runs before it joins
-        Signals& sig;
-        ~Abort() { { std::lock_guard<std::mutex> lk(sig.m); sig.abort = true; } sig.cv.notify_all(); }
-    } abort_guard{sig};
-    auto wait_job = [&](uint32_t j, const char* what, uint32_t idx) -> int {
-        crew.wait(j);
-        if (job_rc[j]) { set_error("%s %u: %s", what, idx, job_msg[j].c_str()); return job_rc[j]; }
-        return MVB_OK;
-    };
-    uint32_t csr_issued = 0, s1_done = 0;                        // graphs [0, x) have their CSR copies / their S1 queued
-    auto issue_csr = [&](uint32_t upto) -> int {
-        for (; csr_issued < std::min(upto, G); ++csr_issued) {
-            const mvb_population* p = pops[first_rep[csr_issued]];
-            const size_t nb_rp = 8 * ((size_t)p->n_agents + 1), es = p->social_rowptr[p->n_agents], en = p->neighbour_rowptr[p->n_agents];
-            GraphWork& c = work[csr_issued];
-            MVB_CUDA(c.srp.alloc(nb_rp, s->stream)); MVB_CUDA(c.nrp.alloc(nb_rp, s->stream));
-            MVB_CUDA(c.scol.alloc(4 * es, s->stream)); MVB_CUDA(c.ncol.alloc(4 * en, s->stream));
-            MVB_CUDA(cudaMemcpyAsync(c.srp.p, p->social_rowptr, nb_rp, cudaMemcpyHostToDevice, s->stream));
-            MVB_CUDA(cudaMemcpyAsync(c.nrp.p, p->neighbour_rowptr, nb_rp, cudaMemcpyHostToDevice, s->stream));
-            if (es) MVB_CUDA(cudaMemcpyAsync(c.scol.p, p->social_col, 4 * es, cudaMemcpyHostToDevice, s->stream));
-            if (en) MVB_CUDA(cudaMemcpyAsync(c.ncol.p, p->neighbour_col, 4 * en, cudaMemcpyHostToDevice, s->stream));
-        }
-        return MVB_OK;
-    };
-    auto stage1 = [&](uint32_t upto) -> int {
-        for (; s1_done < std::min(upto, G); ++s1_done) {
-            const uint32_t g = s1_done, r0 = first_rep[g], N = pops[r0]->n_agents;
-            if (int rc = issue_csr(g + 1)) return rc;
-            const double tw = now();
-            if (int rc = wait_job(job_a[r0], "replica", r0)) return rc;
-            tm_wait += now() - tw;
-            GraphWork& w = work[g];
-            char* slot = slots.base[g % kSlots];
-            w.h_counts = reinterpret_cast<uint32_t*>(slot);
-            uint8_t* h_hot = reinterpret_cast<uint8_t*>(slot) + 8 * (size_t)N + 64;
-            memcpy(h_hot, w.W.is_hot.data(), N);
-            MVB_CUDA(w.is_hot.alloc(N, s->stream));
-            MVB_CUDA(w.counts.alloc(8 * (size_t)N + 4, s->stream));
-            MVB_CUDA(cudaMemcpyAsync(w.is_hot.p, h_hot, N, cudaMemcpyHostToDevice, s->stream));
-            uint32_t* d_bad = w.counts.as<uint32_t>() + 2 * (size_t)N;
-            MVB_CUDA(cudaMemsetAsync(d_bad, 0, 4, s->stream));
-            count_hot_kernel<<<(unsigned)std::min<uint64_t>(((uint64_t)N * 32 + 255) / 256, (uint64_t)sms * 32), 256, 0, s->stream>>>(
-                N, w.srp.as<uint64_t>(), w.scol.as<uint32_t>(), w.nrp.as<uint64_t>(), w.ncol.as<uint32_t>(), w.is_hot.as<uint8_t>(),
-                w.counts.as<uint32_t>(), w.counts.as<uint32_t>() + N, d_bad);
-            MVB_CUDA(cudaGetLastError());
-            MVB_CUDA(cudaMemcpyAsync(w.h_counts, w.counts.p, 8 * (size_t)N + 4, cudaMemcpyDeviceToHost, s->stream));
-            MVB_CUDA(cudaEventRecord(slots.ev[g % kSlots], s->stream));
-            { std::lock_guard<std::mutex> lk(sig.m); sig.queued[g] = 1; }
-            sig.cv.notify_all();
-        }
-        return MVB_OK;
-    };
-    PinnedRing ring;
-    {   // scratch buffers come from the device's stream-ordered pool; let it keep what it has between replicas
-        cudaMemPool_t pool;
-        MVB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-        uint64_t keep = ~0ull;
-        MVB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-    }
-    std::vector<char> uploaded(graphs.size(), 0);
-    std::list<std::vector<float>> host_f;
-    const double tm2 = now();
-    for (uint32_t r = 0; r < R; ++r) {
-        const double tr = now();
-        const mvb_population* p = pops[r];
-        const mvb_tables* t = tabs[r];
-        Replica& rp = s->reps[r];
-        const uint32_t N = p->n_agents;
-        rp.N = N; rp.S = t->n_subcultures; rp.H = t->n_neighbourhoods;
-        rp.rec_width = rec_width(rp.S, rp.H);
-        rp.rec_off = s->rec_stride;
-        s->rec_stride += rp.rec_width;
-        rp.graph = graphs[graph_of[r]];
-        if (int rc = stage1(graph_of[r] + 1 + kLook)) return rc;
-        if (int rc = issue_csr(graph_of[r] + 2 + kLook)) return rc;
-        {
-            const double tw = now();
-            if (int rc = wait_job(job_a[r], "replica", r)) return rc;
-            if (!uploaded[graph_of[r]])
-                if (int rc = wait_job(job_f[graph_of[r]], "replica", r)) return rc;
-            tm_wait += now() - tw;
-        }
-        if (!uploaded[graph_of[r]]) {
-            uploaded[graph_of[r]] = 1;
-            Graph* g = rp.graph.get();
-            GraphLayout& L = g->L;
-            int rc;
-            MVB_CUDA(ring.begin(PinnedRing::need(L.ranges) + PinnedRing::need(L.hub_off) + PinnedRing::need(L.hub_deg) +
-                                PinnedRing::need(L.sell_meta) + PinnedRing::need(L.hub_units) + PinnedRing::need(L.hub_unit_begin) +
-                                PinnedRing::need(L.int2ext)));
-            if ((rc = upload_staged(s->mem, g->ranges, L.ranges, ring, s->stream)) || (rc = upload_staged(s->mem, g->hub_off, L.hub_off, ring, s->stream)) ||
-                (rc = upload_staged(s->mem, g->hub_deg, L.hub_deg, ring, s->stream)) || (rc = upload_staged(s->mem, g->sell_meta, L.sell_meta, ring, s->stream)) ||
-                (rc = upload_staged(s->mem, g->hub_units, L.hub_units, ring, s->stream)) ||
-                (rc = upload_staged(s->mem, g->hub_unit_begin, L.hub_unit_begin, ring, s->stream)) ||
-                (rc = upload_staged(s->mem, g->int2ext, L.int2ext, ring, s->stream)))
-                return rc;
-            MVB_CARVE(s->mem, g->deg, sizeof(uint32_t) * (size_t)L.N_pad);
-            MVB_CARVE(s->mem, g->hub_codes, sizeof(uint32_t) * L.hub_codes_len);
-            MVB_CARVE(s->mem, g->sell_codes, sizeof(uint32_t) * L.sell_codes_len);
-            // unused entries = the code of the always-zero shared-memory word (layout.h)
-            fill_u32_kernel<<<sms * 8, 256, 0, s->stream>>>(g->hub_codes.as<uint32_t>(), L.hub_codes_len, pad_code(s->vec_cap_words));
-            fill_u32_kernel<<<sms * 8, 256, 0, s->stream>>>(g->sell_codes.as<uint32_t>(), L.sell_codes_len, pad_code(s->vec_cap_words));
-            MVB_CUDA(cudaGetLastError());
-            // the caller's CSR went to the device as it is (issue_csr); the fill kernels re-encode it there, then it is dropped
-            GraphWork& c = work[graph_of[r]];
-            TmpBuf t_tcode;
-            MVB_CUDA(t_tcode.alloc(4 * (size_t)N, s->stream));
-            MVB_CUDA(ring.end(s->stream));
-            tcode_kernel<<<(L.N_pad + 255) / 256, 256, 0, s->stream>>>(L.N_pad, g->int2ext.as<uint32_t>(), g->ranges.as<StageRange>(),
-                                                                     (uint32_t)L.ranges.size(), c.is_hot.as<uint8_t>(), t_tcode.as<uint32_t>());
-            MVB_CUDA(cudaGetLastError());
-            FillArgs fa{c.srp.as<uint64_t>(), c.scol.as<uint32_t>(), c.nrp.as<uint64_t>(), c.ncol.as<uint32_t>(),
-                        t_tcode.as<uint32_t>(), g->int2ext.as<uint32_t>(), L.n_hub_slices, L.n_sell_slices,
-                        g->sell_meta.as<uint4>(), g->sell_codes.as<uint32_t>(), g->deg.as<uint32_t>(),
-                        g->hub_off.as<uint64_t>(), g->hub_deg.as<uint4>(), g->hub_codes.as<uint32_t>()};
-            MVB_CUDA(cudaMemsetAsync(g->deg.p, 0, g->deg.bytes, s->stream));
-            if (L.n_sell_slices) {
-                fill_sell_kernel<<<(L.n_sell_slices * 32 + 255) / 256, 256, 0, s->stream>>>(fa);
-                MVB_CUDA(cudaGetLastError());
-            }
-            if (L.n_hub_slices) {
-                fill_hub_kernel<<<(L.n_hub_slices * 32 * 32 + 255) / 256, 256, 0, s->stream>>>(fa, L.n_hub_slices * 32);
-                MVB_CUDA(cudaGetLastError());
-            }
-            c.srp.release(); c.scol.release(); c.nrp.release(); c.ncol.release(); c.is_hot.release(); c.counts.release();   // back to the pool, in stream order
-            std::vector<uint4x>().swap(L.sell_meta);
-        }
-        const GraphLayout& L = rp.graph->L;
-        const uint32_t NP = L.N_pad;
-        s->max_npad = std::max(s->max_npad, NP);
-        const double ts = now();
-        tm_graph += ts - tr;
-        // per-agent state: the caller's arrays go up as they are, a kernel permutes them into internal slot order
-        const float* pa_src[5] = {p->consistency, p->social_connectivity, p->subculture_connectivity,
-                                  p->neighbourhood_connectivity, p->average_weight};
-        const float pa_def[5] = {prm->consistency, prm->social_connectivity, prm->subculture_connectivity,
-                                 prm->neighbourhood_connectivity, prm->average_weight};
-        rp.per_agent = false;
-        for (int k = 0; k < 5; ++k) rp.per_agent |= (pa_src[k] != nullptr);
-        if (rp.per_agent) s->any_per_agent = true;
-        {
-            const size_t hub_cnt_bytes = sizeof(uint32_t) * 8 * 32 * (size_t)L.n_hub_slices;
-            MVB_CARVE(s->mem, rp.state, (size_t)(NP / 32) * kRecWords * 4);
-            // + 64 bytes: the early gather of a padded cold-list entry reads the word a padding code names (at most
-            // 16 bytes past a vector that only just exceeds the shared-memory capacity); its value is never used
-            MVB_CARVE(s->mem, rp.vec[0], NP / 4 + 64); MVB_CARVE(s->mem, rp.vec[1], NP / 4 + 64); MVB_CARVE(s->mem, rp.normvec, NP / 4);
-            if (rp.per_agent) MVB_CARVE(s->mem, rp.pa, 20 * (size_t)NP);
-            MVB_CARVE(s->mem, rp.tables_f, sizeof(float) * 4 * (rp.H + rp.S));
-            MVB_CARVE(s->mem, rp.tables_u, sizeof(uint32_t) * 5 * rp.H);
-            MVB_CARVE(s->mem, rp.cong, sizeof(float) * 4 * rp.H);
-            MVB_CARVE(s->mem, rp.hub_cnt, hub_cnt_bytes);
-            TmpBuf t[14];
-            auto up = [&](TmpBuf& b, const void* src, size_t bytes) -> int {
-                MVB_CUDA(b.alloc(bytes, s->stream));
-                MVB_CUDA(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, s->stream));
-                return MVB_OK;
-            };
-            int rc;
-            if ((rc = up(t[0], p->subculture, N)) || (rc = up(t[1], p->neighbourhood, 2 * (size_t)N)) ||
-                (rc = up(t[2], p->commute, N)) || (rc = up(t[3], p->owns_car, N)) || (rc = up(t[4], p->owns_bike, N)) ||
-                (rc = up(t[5], p->weather_sensitivity, 4 * (size_t)N)) || (rc = up(t[6], p->habit, 16 * (size_t)N)) ||
-                (rc = up(t[7], p->current_mode, N)) || (rc = up(t[8], p->norm, N)))
-                return rc;
-            InitArgs ia{};
-            ia.int2ext = rp.graph->int2ext.as<uint32_t>(); ia.N = N; ia.N_pad = NP;
-            ia.sub = t[0].as<uint8_t>(); ia.nbhd = t[1].as<uint16_t>(); ia.commute = t[2].as<uint8_t>();
-            ia.car = t[3].as<uint8_t>(); ia.bike = t[4].as<uint8_t>(); ia.ws = t[5].as<float>();
-            ia.habit = t[6].as<float4>(); ia.mode = t[7].as<uint8_t>(); ia.norm = t[8].as<uint8_t>();
-            for (int k = 0; k < 5; ++k) {
-                ia.pa_src[k] = nullptr; ia.pa_def[k] = pa_def[k];
-                if (rp.per_agent && pa_src[k]) { if ((rc = up(t[9 + k], pa_src[k], 4 * (size_t)N))) return rc; ia.pa_src[k] = t[9 + k].as<float>(); }
-            }
-            ia.lens = rp.graph->deg.as<uint32_t>(); ia.state = rp.state.as<uint32_t>();
-            ia.pa_out = rp.per_agent ? rp.pa.as<float>() : nullptr;
-            ia.vec0 = rp.vec[0].as<uint2>(); ia.vec1 = rp.vec[1].as<uint2>(); ia.normvec = rp.normvec.as<uint2>();
-            init_state_kernel<<<(NP + 255) / 256, 256, 0, s->stream>>>(ia);
-            MVB_CUDA(cudaGetLastError());                        // the scratch goes back to the pool in stream order
-        }
-        // tables + residents
-        if (int rc = upload_tables(s, rp, t)) return rc;
-        MVB_CUDA(cudaMemcpyAsync(rp.tables_u.as<uint32_t>() + 4 * rp.H, nres_all[r].data(), 4 * rp.H, cudaMemcpyHostToDevice, s->stream));
-        host_f.emplace_back(4 * rp.H, 1.0f);          // default_congestion_modifier, neighbourhood.rs:34-41; lives until the final synchronize
-        MVB_CUDA(cudaMemcpyAsync(rp.cong.p, host_f.back().data(), 16 * rp.H, cudaMemcpyHostToDevice, s->stream));
-
-        Graph& g = *rp.graph;
-        RepDev& d = s->h_reps[r];
-        d.N = N; d.N_pad = NP; d.S = rp.S; d.H = rp.H; d.rec_off = rp.rec_off;
-        d.n_hub_slices = L.n_hub_slices; d.n_sell_slices = L.n_sell_slices;
-        d.n_ranges = (uint32_t)L.ranges.size(); d.hot_words = L.hot_words;
-        d.hub_begin = 0; d.hub_end = L.n_hub_slices; d.sell_begin = 0; d.sell_end = L.n_sell_slices;
-        if (world > 1) {                               // this rank's slice range, split into its hub and SELL parts
-            partition_slices(L, world, s->bounds);
-            const uint32_t b = s->bounds[rank], e = s->bounds[rank + 1], nh = L.n_hub_slices;
-            d.hub_begin = std::min(b, nh); d.hub_end = std::min(e, nh);
-            d.sell_begin = std::max(b, nh) - nh; d.sell_end = std::max(e, nh) - nh;
-        }
-        d.state = rp.state.as<uint32_t>();
-        d.pa = rp.per_agent ? rp.pa.as<float>() : nullptr;
-        d.vec[0] = rp.vec[0].as<uint2>(); d.vec[1] = rp.vec[1].as<uint2>(); d.normvec = rp.normvec.as<uint2>();
-        d.ranges = g.ranges.as<StageRange>();
-        if (rp.hub_cnt.bytes) MVB_CUDA(cudaMemsetAsync(rp.hub_cnt.p, 0, rp.hub_cnt.bytes, s->stream));
-        d.hub_units = g.hub_units.as<uint4>(); d.hub_unit_begin = g.hub_unit_begin.as<uint32_t>();
-        d.hub_off = g.hub_off.as<uint64_t>(); d.hub_deg = g.hub_deg.as<uint4>(); d.hub_cnt = rp.hub_cnt.as<uint32_t>();
-        d.hub_codes = g.hub_codes.as<uint32_t>();
-        d.sell_meta = g.sell_meta.as<uint4>(); d.sell_codes = g.sell_codes.as<uint32_t>();
-        d.supp = rp.tables_f.as<float>(); d.desir = rp.tables_f.as<float>() + 4 * rp.H;
-        d.cap = rp.tables_u.as<uint32_t>(); d.nres = rp.tables_u.as<uint32_t>() + 4 * rp.H;
-        d.cong = rp.cong.as<float>();
-        if (L.hot_words + 4 > s->vec_cap_words) { set_error("internal: staged vector larger than its shared-memory slot"); return MVB_ERR_STATE; }
-        tm_state += now() - ts;
-    }
-    const double tm3 = now();
-    MVB_CUDA(cudaFuncSetAttribute(day_kernel<true, 1024, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
-    MVB_CUDA(cudaFuncSetAttribute(day_kernel<true, 1024, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
-    MVB_CUDA(cudaFuncSetAttribute(day_kernel<false, 1024, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
-    MVB_CUDA(cudaFuncSetAttribute(day_kernel<false, 1024, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
-    if (s->census_smem > 48 * 1024)
-        MVB_CUDA(cudaFuncSetAttribute(census_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->census_smem));
-    s->rank = rank; s->world = world;
-    if (world > 1) {
-        Nccl* n = nccl();
-        if (!n) { set_error("agent-partitioned mode needs NCCL (libnccl.so.2 could not be loaded: %s)", dlerror()); return MVB_ERR_COMM; }
-        ncclUniqueId id;
-        memcpy(&id, unique_id, sizeof id);
-        MVB_NCCL(n->CommInitRank(&s->comm, (int)world, id, (int)rank));
-    }
-    s->rep_args.assign((R + kMaxRepsPerLaunch - 1) / kMaxRepsPerLaunch, RepArray{});
-    for (uint32_t r = 0; r < R; ++r) s->rep_args[r / kMaxRepsPerLaunch].r[r % kMaxRepsPerLaunch] = s->h_reps[r];
-    MVB_CUDA(s->d_reps.alloc(sizeof(RepDev) * R));
-    int rc = upload_reps(s);
-    if (rc) return rc;
-    rc = ensure_rows(s, 8);
-    if (rc) return rc;
-    s->cursor = 0;
-    s->row_days.assign(1, 0);
-    rc = launch_census(s, 0);
-    if (rc) return rc;
-    MVB_CUDA(cudaStreamSynchronize(s->stream));
-    if (timing)
-        fprintf(stderr, "mvb_create: checks %.3f s, set-up %.3f s, replicas %.3f s (waiting for host threads %.3f, graph enqueue %.3f, "
-                "state enqueue %.3f), drain %.3f s\n", tm1 - tm0, tm2 - tm1, tm3 - tm2, tm_wait, tm_graph - tm_wait, tm_state, now() - tm3);
-    {   // hand the scratch memory back
-        cudaMemPool_t pool;
-        MVB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-        uint64_t keep = 0;
-        MVB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-        MVB_CUDA(cudaMemPoolTrimTo(pool, 0));
-    }
-    *out = sp.release();
-    return MVB_OK;
-}
+}  // extern "C"
+#include "create.cuh"
+extern "C" {
 
 int mvb_create_batch(uint32_t R, const mvb_population* const* pops, const mvb_tables* const* tabs,
                      const mvb_params* prm, int device, mvb_sim** out) {
@@ -940,6 +435,7 @@ static void owners_from_bounds(const GraphLayout& L, const std::vector<uint32_t>
 
 int mvb_partition_owner(const mvb_sim* s, uint32_t* rank_out) {
     if (!s || !rank_out) { set_error("null argument"); return MVB_ERR_ARG; }
+    if (int rc = host_int2ext(const_cast<mvb_sim*>(s), *s->reps[0].graph)) return rc;
     const GraphLayout& L = s->reps[0].graph->L;
     if (s->world <= 1) { for (uint32_t i = 0; i < L.N; ++i) rank_out[i] = 0; return MVB_OK; }
     owners_from_bounds(L, s->bounds, s->world, rank_out);
@@ -1001,9 +497,9 @@ int mvb_set_ownership(mvb_sim* s, uint32_t r, const uint8_t* car, const uint8_t*
     Replica& rp = s->reps[r];
     const uint32_t NP = rp.graph->L.N_pad;
     MVB_CUDA(cudaSetDevice(s->device));
-    DevBuf tc, tb;
-    if (car)  { MVB_CUDA(tc.alloc(rp.N)); MVB_CUDA(cudaMemcpyAsync(tc.p, car, rp.N, cudaMemcpyHostToDevice, s->stream)); }
-    if (bike) { MVB_CUDA(tb.alloc(rp.N)); MVB_CUDA(cudaMemcpyAsync(tb.p, bike, rp.N, cudaMemcpyHostToDevice, s->stream)); }
+    TmpBuf tc, tb;                                  // stream-ordered pool: no device-wide synchronisation
+    if (car)  { MVB_CUDA(tc.alloc(rp.N, s->stream)); MVB_CUDA(cudaMemcpyAsync(tc.p, car, rp.N, cudaMemcpyHostToDevice, s->stream)); }
+    if (bike) { MVB_CUDA(tb.alloc(rp.N, s->stream)); MVB_CUDA(cudaMemcpyAsync(tb.p, bike, rp.N, cudaMemcpyHostToDevice, s->stream)); }
     set_ownership_kernel<<<(NP + 255) / 256, 256, 0, s->stream>>>(rp.graph->int2ext.as<uint32_t>(), NP,
                                                                   car ? tc.as<uint8_t>() : nullptr, bike ? tb.as<uint8_t>() : nullptr,
                                                                   rp.state.as<uint32_t>());
@@ -1046,16 +542,76 @@ int mvb_run_async(mvb_sim* s, const uint8_t* weather, uint32_t first_day, uint32
     for (uint32_t d = d0; d < end_day; ++d) n_week += (d % 7 < 5);
     int rc = ensure_rows(s, n_week);
     if (rc) return rc;
+    // Interventions that fall inside [d0, end_day): everything they need goes to the device BEFORE the day loop (one
+    // copy out of a library-owned pinned buffer into stream-ordered scratch), so that on the day itself `intervene`
+    // is one kernel launch for all replicas concerned: no allocation, no copy, no synchronisation inside the loop.
+    struct Fire { uint32_t day, r; const mvb_intervention* iv; size_t car, bike, tf, tu; };
+    std::vector<Fire> fires;
+    size_t stage_bytes = 0;
+    auto take = [&](size_t n) { const size_t at = stage_bytes; stage_bytes += (n + 255) & ~(size_t)255; return at; };
+    if (ivs)
+        for (uint32_t r = 0; r < s->reps.size(); ++r) {
+            const mvb_intervention* iv = ivs[r];
+            if (!iv || iv->day < d0 || iv->day >= end_day) continue;
+            const Replica& rp = s->reps[r];
+            if (iv->tables) {
+                if ((rc = check_tables(iv->tables))) return rc;
+                if (iv->tables->n_subcultures != rp.S || iv->tables->n_neighbourhoods != rp.H) { set_error("table shape differs from the replica's"); return MVB_ERR_ARG; }
+            }
+            Fire f{iv->day, r, iv, 0, 0, 0, 0};
+            if (iv->owns_car) f.car = take(rp.N);
+            if (iv->owns_bike) f.bike = take(rp.N);
+            if (iv->tables) { f.tf = take(16 * (size_t)(rp.H + rp.S)); f.tu = take(16 * (size_t)rp.H); }
+            fires.push_back(f);
+        }
+    std::stable_sort(fires.begin(), fires.end(), [](const Fire& a, const Fire& b) { return a.day < b.day; });
+    TmpBuf iv_scratch;
+    const IvDev* d_ivs = nullptr;
+    if (!fires.empty()) {
+        const size_t list_at = take(sizeof(IvDev) * fires.size());
+        MVB_CUDA(cudaEventSynchronize(s->iv_ev));                  // the previous run is done with the pinned buffer
+        if (stage_bytes > s->iv_pinned_cap) {
+            pinned_cache().put(s->iv_pinned, s->iv_pinned_cap);
+            s->iv_pinned = nullptr; s->iv_pinned_cap = 0;
+            MVB_CUDA(pinned_cache().get(stage_bytes, &s->iv_pinned, &s->iv_pinned_cap));
+        }
+        MVB_CUDA(iv_scratch.alloc(stage_bytes, s->stream));
+        char* h = s->iv_pinned;
+        char* d = iv_scratch.as<char>();
+        IvDev* list = reinterpret_cast<IvDev*>(h + list_at);
+        for (size_t k = 0; k < fires.size(); ++k) {
+            const Fire& f = fires[k];
+            const Replica& rp = s->reps[f.r];
+            IvDev e{f.r, f.iv->tables ? 1u : 0u, nullptr, nullptr, nullptr, nullptr};
+            if (f.iv->owns_car)  { memcpy(h + f.car, f.iv->owns_car, rp.N);   e.car = reinterpret_cast<const uint8_t*>(d + f.car); }
+            if (f.iv->owns_bike) { memcpy(h + f.bike, f.iv->owns_bike, rp.N); e.bike = reinterpret_cast<const uint8_t*>(d + f.bike); }
+            if (f.iv->tables) {
+                float* tf = reinterpret_cast<float*>(h + f.tf);
+                memcpy(tf, f.iv->tables->supportiveness, 16 * (size_t)rp.H);
+                memcpy(tf + 4 * rp.H, f.iv->tables->desirability, 16 * (size_t)rp.S);
+                memcpy(h + f.tu, f.iv->tables->capacity, 16 * (size_t)rp.H);
+                e.tf = reinterpret_cast<const float*>(d + f.tf); e.tu = reinterpret_cast<const uint32_t*>(d + f.tu);
+            }
+            list[k] = e;
+        }
+        MVB_CUDA(cudaMemcpyAsync(d, h, stage_bytes, cudaMemcpyHostToDevice, s->stream));
+        MVB_CUDA(cudaEventRecord(s->iv_ev, s->stream));
+        d_ivs = reinterpret_cast<const IvDev*>(d + list_at);
+    }
     s->last_launches = 0;
     MVB_CUDA(cudaEventRecord(s->ev0, s->stream));
+    size_t next_fire = 0;
     for (uint32_t day = d0; day < end_day; ++day) {
-        if (ivs)
-            for (uint32_t r = 0; r < s->reps.size(); ++r) {
-                const mvb_intervention* iv = ivs[r];
-                if (!iv || iv->day != day) continue;                        // simulation.rs:103-105
-                if (iv->tables && (rc = mvb_set_tables(s, r, iv->tables))) return rc;
-                if ((rc = mvb_set_ownership(s, r, iv->owns_car, iv->owns_bike))) return rc;
-            }
+        size_t last = next_fire;
+        while (last < fires.size() && fires[last].day == day) ++last;                   // simulation.rs:103-105
+        if (last > next_fire) {
+            uint32_t np_max = 0;
+            for (size_t k = next_fire; k < last; ++k) np_max = std::max(np_max, s->reps[fires[k].r].graph->L.N_pad);
+            const dim3 grid(std::min<uint32_t>((np_max + 255) / 256, 4 * s->grid), (unsigned)(last - next_fire));
+            apply_interventions_kernel<<<grid, 256, 0, s->stream>>>(d_ivs + next_fire, s->d_ivreps.as<IvRep>());
+            MVB_CUDA(cudaGetLastError());
+            next_fire = last;
+        }
         if (day % 7 < 5) {                                                  // simulation.rs:108, 297-299
             const uint8_t w = weather[day];
             if (w > 1) { set_error("weather[%u] = %u is not a weather code", day, w); return MVB_ERR_ARG; }
@@ -1147,6 +703,7 @@ int mvb_get_state(mvb_sim* s, uint32_t r, float* habit, uint8_t* cur, uint8_t* l
     MVB_CUDA(cudaSetDevice(s->device));
     MVB_CUDA(cudaStreamSynchronize(s->stream));
     Replica& rp = s->reps[r];
+    if (int rc = host_int2ext(s, *rp.graph)) return rc;
     const std::vector<uint32_t>& int2ext = rp.graph->L.int2ext;
     const size_t NP = int2ext.size();
     if (habit) {
@@ -1172,6 +729,47 @@ int mvb_get_state(mvb_sim* s, uint32_t r, float* habit, uint8_t* cur, uint8_t* l
                                    sizeof(uint32_t) * 4 * rp.H, cudaMemcpyDeviceToHost));
     if (cong)  MVB_CUDA(cudaMemcpy(cong, rp.cong.p, sizeof(float) * 4 * rp.H, cudaMemcpyDeviceToHost));
     return MVB_OK;
+}
+
+// Test hook (not part of the ABI in include/): the layout the GPU built for replica r against the host builder
+// (layout.cpp, the specification) on the same population (host pointers).  0 = identical; otherwise msg says what differs.
+int mvbx_compare_layout_with_host(mvb_sim* s, uint32_t r, const mvb_population* pop, char* msg, size_t cap) {
+    if (!s || r >= s->reps.size() || !pop) return -1;
+    auto say = [&](const char* what, size_t at) { if (msg && cap) snprintf(msg, cap, "%s differs at %zu", what, at); return 1; };
+    cudaSetDevice(s->device);
+    cudaStreamSynchronize(s->stream);
+    Replica& rp = s->reps[r];
+    Graph& g = *rp.graph;
+    GraphLayout H;
+    uint32_t capacity = staged_capacity_agents(s->vec_cap_words);
+    if (const char* e = getenv("MVB_STAGE_AGENTS")) capacity = std::min<uint32_t>(capacity, std::max(64, atoi(e)) / 64 * 64);
+    if (build_graph_layout(*pop, rp.H, capacity, H)) return -2;
+    const GraphLayout& L = g.L;
+    if (H.N_pad != L.N_pad || H.n_hub_slices != L.n_hub_slices || H.n_sell_slices != L.n_sell_slices || H.hot_words != L.hot_words) return say("sizes", 0);
+    if (H.ranges.size() != L.ranges.size()) return say("range count", 0);
+    for (size_t k = 0; k < H.ranges.size(); ++k)
+        if (memcmp(&H.ranges[k], &L.ranges[k], 12)) return say("ranges", k);
+    auto fetch = [&](const DevBuf& b, size_t bytes) { std::vector<char> v(bytes); cudaMemcpy(v.data(), b.p, bytes, cudaMemcpyDeviceToHost); return v; };
+    {
+        auto v = fetch(g.int2ext, 4 * (size_t)L.N_pad);
+        const uint32_t* d = (const uint32_t*)v.data();
+        for (size_t k = 0; k < L.N_pad; ++k) if (d[k] != H.int2ext[k]) return say("int2ext", k);
+    }
+    if (s->world == 1) {
+        if (H.sell_codes_len != L.sell_codes_len || H.hub_codes_len != L.hub_codes_len) return say("code lengths", 0);
+        auto v = fetch(g.sell_meta, 16 * (size_t)L.n_sell_slices);
+        if (memcmp(v.data(), H.sell_meta.data(), v.size())) return say("sell_meta", 0);
+        const size_t rows = (size_t)L.n_hub_slices * 32;
+        auto o = fetch(g.hub_off, 8 * rows);
+        if (memcmp(o.data(), H.hub_off.data(), o.size())) return say("hub_off", 0);
+        auto dg = fetch(g.hub_deg, 16 * rows);
+        if (memcmp(dg.data(), H.hub_deg.data(), dg.size())) return say("hub_deg", 0);
+        auto ub = fetch(g.hub_unit_begin, 4 * ((size_t)L.n_hub_slices + 1));
+        if (memcmp(ub.data(), H.hub_unit_begin.data(), ub.size())) return say("hub_unit_begin", 0);
+        auto hu = fetch(g.hub_units, 16 * H.hub_units.size());
+        if (memcmp(hu.data(), H.hub_units.data(), hu.size())) return say("hub_units", 0);
+    }
+    return 0;
 }
 
 uint64_t mvb_algorithmic_bytes_per_day(const mvb_sim* s, uint32_t r) {
