@@ -67,6 +67,9 @@ extern "C" {
  * as structure-of-arrays.  Agent ids are positions 0..n_agents-1 (the ids used
  * by config/networks/N.yaml, src/simulation.rs:274-291).  Link lists keep
  * duplicates: a friend listed twice counts twice (src/agent.rs:322-332). */
+/* The arrays may live in host memory (they are copied to the device during mvb_create*; pinned memory makes those
+ * copies asynchronous) or, all of them, in device memory of the GPU the handle is created on (then they are read in
+ * place during mvb_create* and must not be written until it returns). */
 typedef struct mvb_population {
     uint32_t n_agents;
     const uint8_t*  subculture;            /* [N] index into mvb_tables.desirability rows           */
@@ -264,6 +267,14 @@ typedef struct mvb_synth_spec {
 } mvb_synth_spec;
 
 int  mvb_synth_create(const mvb_synth_spec* spec, mvb_synth** out);
+/* The same kind of population generated ON THE GPU `device` (every agent and every link is a thread;
+ * preferential attachment by chasing the chain of endpoint picks, see csrc/synth_device.cuh): 50M agents with
+ * 1.5 G link entries take well under a second where the host generator needs minutes.  The arrays
+ * mvb_synth_population() exposes then live in DEVICE memory of that GPU; mvb_create* accepts such a population as
+ * it is (no host copy is made), mvb_synth_copy_to_host() brings it to the host.  Its own seeded stream: the same
+ * distributions as mvb_synth_create, not the same draws. */
+int  mvb_synth_create_device(const mvb_synth_spec* spec, int device, mvb_synth** out);
+int  mvb_synth_copy_to_host(const mvb_synth* device_population, mvb_synth** host_out);
 void mvb_synth_destroy(mvb_synth* s);
 const mvb_population* mvb_synth_population(const mvb_synth* s);
 /* Barabási–Albert network exactly as src/social_network.rs:12-48 builds it

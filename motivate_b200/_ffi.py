@@ -83,6 +83,8 @@ SIGNATURES = {
     "mvb_partition_owner": (C.c_int, [SimP, u32p]),
     "mvb_partition_plan": (C.c_int, [PopP, C.c_uint32, C.c_uint32, C.c_uint32, u32p]),
     "mvb_synth_create": (C.c_int, [C.POINTER(SynthSpec), C.POINTER(C.c_void_p)]),
+    "mvb_synth_create_device": (C.c_int, [C.POINTER(SynthSpec), C.c_int, C.POINTER(C.c_void_p)]),
+    "mvb_synth_copy_to_host": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "mvb_synth_destroy": (None, [C.c_void_p]),
     "mvb_synth_population": (PopP, [C.c_void_p]),
     "mvb_synth_ba_network": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint64, C.POINTER(u64p), C.POINTER(u32p)]),

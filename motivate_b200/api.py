@@ -221,6 +221,74 @@ def synth_population(n_agents, n_subcultures=4, n_neighbourhoods=10, social_link
     return PopulationData(out)
 
 
+def _synth_spec(n_agents, n_subcultures, n_neighbourhoods, social_links_min, neighbour_links_min, car_ratio, bike_ratio, seed, gmm):
+    sp = _ffi.SynthSpec()
+    sp.n_agents, sp.n_subcultures, sp.n_neighbourhoods = n_agents, n_subcultures, n_neighbourhoods
+    sp.social_links_min, sp.neighbour_links_min = social_links_min, neighbour_links_min
+    sp.n_cars = int(round(car_ratio * n_agents))
+    sp.n_bikes = sp.n_cars if bike_ratio is None else int(round(bike_ratio * n_agents))
+    sp.seed = seed
+    sp.n_gmm = len(gmm)
+    for g, row in enumerate(gmm):
+        for k in range(3):
+            sp.gmm[g][k] = row[k]
+    return sp
+
+
+def _population_from_struct(p) -> "PopulationData":
+    N = p.n_agents
+
+    def arr(ptr, n, dt):
+        return np.ctypeslib.as_array(ptr, shape=(n,)).astype(dt, copy=True) if n else np.zeros(0, dt)
+
+    s_rowptr = arr(p.social_rowptr, N + 1, np.uint64)
+    n_rowptr = arr(p.neighbour_rowptr, N + 1, np.uint64)
+    return PopulationData(dict(
+        subculture=arr(p.subculture, N, np.uint8), neighbourhood=arr(p.neighbourhood, N, np.uint16),
+        commute=arr(p.commute, N, np.uint8), owns_car=arr(p.owns_car, N, np.uint8),
+        owns_bike=arr(p.owns_bike, N, np.uint8), weather_sensitivity=arr(p.weather_sensitivity, N, np.float32),
+        habit=arr(p.habit, 4 * N, np.float32).reshape(N, 4), current_mode=arr(p.current_mode, N, np.uint8),
+        norm=arr(p.norm, N, np.uint8), social_rowptr=s_rowptr,
+        social_col=arr(p.social_col, int(s_rowptr[N]), np.uint32), neighbour_rowptr=n_rowptr,
+        neighbour_col=arr(p.neighbour_col, int(n_rowptr[N]), np.uint32)))
+
+
+class DevicePopulation:
+    """A synthetic population generated on the GPU and living in its memory (mvb_synth_create_device): pass it to
+    Simulation / Simulation.partitioned like a PopulationData (nothing crosses PCIe); to_host() copies it out."""
+
+    def __init__(self, n_agents, n_subcultures=4, n_neighbourhoods=10, social_links_min=5, neighbour_links_min=10,
+                 car_ratio=64926 / 111166, bike_ratio=None, seed=0, gmm=DEFAULT_GMM, device=0):
+        self._lib = _ffi.load()
+        sp = _synth_spec(n_agents, n_subcultures, n_neighbourhoods, social_links_min, neighbour_links_min, car_ratio,
+                         bike_ratio, seed, gmm)
+        self._h = C.c_void_p()
+        _check(self._lib.mvb_synth_create_device(C.byref(sp), device, C.byref(self._h)))
+        self.device = device
+
+    @property
+    def n_agents(self):
+        return int(self._lib.mvb_synth_population(self._h).contents.n_agents)
+
+    def struct(self) -> _ffi.Population:
+        return self._lib.mvb_synth_population(self._h).contents          # device pointers
+
+    def to_host(self) -> "PopulationData":
+        h = C.c_void_p()
+        _check(self._lib.mvb_synth_copy_to_host(self._h, C.byref(h)))
+        try:
+            return _population_from_struct(self._lib.mvb_synth_population(h).contents)
+        finally:
+            self._lib.mvb_synth_destroy(h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.mvb_synth_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+
 def synth_tables(n_subcultures=4, n_neighbourhoods=10, n_agents=1_000_000, seed=0) -> TablesData:
     """Synthetic scenario tables of SURVEY.md §8(d): desirability ~U[0.4,0.9], supportiveness ~U[0.25,0.75],
     Car/PT capacity = shipped magnitudes (config/scenario.yaml:45-49, ~3725 / ~5548 for 5294 residents)
@@ -273,7 +341,7 @@ class Simulation:
 
     def __init__(self, pops, tabs, params: Optional[_ffi.Params] = None, device: int = 0):
         self._lib = _ffi.load()
-        if isinstance(pops, PopulationData):
+        if isinstance(pops, (PopulationData, DevicePopulation)):
             pops = [pops]
         if isinstance(tabs, TablesData):
             tabs = [tabs] * len(pops)

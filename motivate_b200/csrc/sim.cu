@@ -398,6 +398,7 @@ void mvb_destroy(mvb_sim* s) {
 
 }  // extern "C"
 #include "create.cuh"
+#include "synth_device.cuh"
 extern "C" {
 
 int mvb_create_batch(uint32_t R, const mvb_population* const* pops, const mvb_tables* const* tabs,

@@ -9,7 +9,10 @@
 #include <cstring>
 #include <numeric>
 
+#include <cuda_runtime_api.h>
+
 #include "mvb_internal.h"
+#include "synth.h"
 
 namespace mvb {
 
@@ -58,15 +61,6 @@ static void ba_edges(uint32_t min_links, uint32_t n, uint64_t seed, std::vector<
 }  // namespace mvb
 
 using namespace mvb;
-
-struct mvb_synth {
-    mvb_population pop{};
-    std::vector<uint8_t> sub, commute, car, bike, mode, norm;
-    std::vector<uint16_t> nbhd;
-    std::vector<float> ws, habit;
-    std::vector<uint64_t> s_rowptr, n_rowptr;
-    std::vector<uint32_t> s_col, n_col;
-};
 
 extern "C" {
 
@@ -210,7 +204,11 @@ int mvb_synth_create(const mvb_synth_spec* sp, mvb_synth** out) {
     return MVB_OK;
 }
 
-void mvb_synth_destroy(mvb_synth* s) { delete s; }
+void mvb_synth_destroy(mvb_synth* s) {
+    if (!s) return;
+    if (s->d_block || s->d_block2) { cudaSetDevice(s->device); cudaFree(s->d_block); cudaFree(s->d_block2); }
+    delete s;
+}
 const mvb_population* mvb_synth_population(const mvb_synth* s) { return s ? &s->pop : nullptr; }
 
 }  // extern "C"

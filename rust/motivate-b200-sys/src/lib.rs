@@ -135,6 +135,8 @@ pub mod raw {
         pub fn mvb_partition_owner(sim: *const mvb_sim, rank_out: *mut u32) -> c_int;
         pub fn mvb_partition_plan(pop: *const mvb_population, n_subcultures: u32, n_neighbourhoods: u32, world: u32, rank_out: *mut u32) -> c_int;
         pub fn mvb_synth_create(spec: *const mvb_synth_spec, out: *mut *mut mvb_synth) -> c_int;
+        pub fn mvb_synth_create_device(spec: *const mvb_synth_spec, device: c_int, out: *mut *mut mvb_synth) -> c_int;
+        pub fn mvb_synth_copy_to_host(device_population: *const mvb_synth, host_out: *mut *mut mvb_synth) -> c_int;
         pub fn mvb_synth_destroy(s: *mut mvb_synth);
         pub fn mvb_synth_population(s: *const mvb_synth) -> *const mvb_population;
         pub fn mvb_synth_ba_network(min_links: u32, n_nodes: u32, seed: u64, rowptr_out: *mut *mut u64, col_out: *mut *mut u32) -> c_int;
@@ -492,6 +494,17 @@ impl Synth {
     pub fn create(spec: &raw::mvb_synth_spec) -> Result<Synth, Error> {
         let mut h = ptr::null_mut();
         check(unsafe { raw::mvb_synth_create(spec, &mut h) })?;
+        Ok(Synth { h: h })
+    }
+    /// Generated on GPU `device`; `population()` then holds DEVICE pointers, which `mvb_create*` accepts as they are.
+    pub fn create_on_device(spec: &raw::mvb_synth_spec, device: i32) -> Result<Synth, Error> {
+        let mut h = ptr::null_mut();
+        check(unsafe { raw::mvb_synth_create_device(spec, device, &mut h) })?;
+        Ok(Synth { h: h })
+    }
+    pub fn copy_to_host(&self) -> Result<Synth, Error> {
+        let mut h = ptr::null_mut();
+        check(unsafe { raw::mvb_synth_copy_to_host(self.h, &mut h) })?;
         Ok(Synth { h: h })
     }
     /// Borrowed view; valid while `self` lives.

@@ -79,3 +79,71 @@ def test_partly_staged_small_population_equals_oracle(stage_env, stage):
         prev = w[day]
         assert_state_equal(g.get_state(0), o.get_state(), f"day {day}")
     g.close()
+
+
+def test_device_generated_population_statistics_and_structure():
+    """mvb_synth_create_device: the distributions of src/agent_generation.rs (exact owner counts, initial mode by
+    ownership, habit one-hot, commute classes of the GMM), Barabási–Albert graphs with duplicates kept (symmetric,
+    2·min links per agent on average, heavy tail), neighbour links inside the neighbourhood."""
+    n, S, H = 300_000, 4, 10
+    d = mb.DevicePopulation(n, S, H, 5, 10, seed=3)
+    p = d.to_host()
+    assert p.n_agents == n
+    assert int(p["owns_car"].sum()) == round(64926 / 111166 * n) == int(p["owns_bike"].sum())
+    assert abs(np.corrcoef(p["owns_car"], p["owns_bike"])[0, 1]) < 0.01             # independent samples
+    assert np.bincount(p["subculture"], minlength=S).min() > 0.95 * n / S and p["subculture"].max() == S - 1
+    assert np.bincount(p["neighbourhood"], minlength=H).min() > 0.95 * n / H and p["neighbourhood"].max() == H - 1
+    assert 0.49 < p["weather_sensitivity"].mean() < 0.51 and p["weather_sensitivity"].max() < 1.0
+    cm = np.bincount(p["commute"], minlength=3) / n                                  # |GMM| vs the 4241 m / 19457 m thresholds
+    host = np.bincount(mb.synth_population(n, S, H, 2, 2, seed=1)["commute"], minlength=3) / n
+    assert np.allclose(cm, host, atol=0.01), (cm, host)
+    assert np.array_equal(p["habit"].argmax(1), p["current_mode"]) and np.all(p["habit"].sum(1) == 1.0)
+    assert np.array_equal(p["norm"], p["current_mode"])
+    both = (p["owns_car"] == 1) & (p["owns_bike"] == 1)
+    share = np.bincount(p["current_mode"][both], minlength=4) / both.sum()
+    assert np.allclose(share, [0.40, 0.15, 0.30, 0.15], atol=0.01), share            # agent_generation.rs:286-325
+    none = (p["owns_car"] == 0) & (p["owns_bike"] == 0)
+    assert np.allclose(np.bincount(p["current_mode"][none], minlength=4) / none.sum(), [0, 0.5, 0, 0.5], atol=0.01)
+    for g, m in (("social", 5), ("neighbour", 10)):
+        rp, col = p[g + "_rowptr"].astype(np.int64), p[g + "_col"].astype(np.int64)
+        deg = np.diff(rp)
+        assert rp[0] == 0 and rp[-1] == len(col) and col.max() < n
+        assert abs(deg.mean() - 2 * m) < 0.02 and deg.min() >= m - 1 + (g == "neighbour") * 0
+        assert deg.max() > 40 * m                                                     # preferential attachment: hubs
+        src = np.repeat(np.arange(n), deg)
+        # symmetric WITH multiplicity: the multiset of (a, b) equals the multiset of (b, a)
+        fw = np.sort(src * n + col); bw = np.sort(col * n + src)
+        assert np.array_equal(fw, bw)
+        assert not np.any(src == col)                                                 # no self links
+        if g == "neighbour":
+            assert np.array_equal(p["neighbourhood"][src], p["neighbourhood"][col])  # simulation.rs:165-173
+    # the degree tail follows the BA law P(k) ~ 2 m^2 / k^3: the share of agents with degree >= 4m is about (m / 4m)^2
+    deg = np.diff(p["social_rowptr"].astype(np.int64))
+    assert 0.04 < (deg >= 20).mean() < 0.09
+    # different seeds give different populations, the same seed the same one
+    q = mb.DevicePopulation(n, S, H, 5, 10, seed=3).to_host()
+    assert np.array_equal(q["social_rowptr"], p["social_rowptr"]) and np.array_equal(q["current_mode"], p["current_mode"])
+    rows = np.repeat(np.arange(n), np.diff(p["social_rowptr"].astype(np.int64)))
+    canon = lambda c: c[np.lexsort((c, rows))]                                       # (the order inside a row is not fixed)
+    assert np.array_equal(canon(q["social_col"]), canon(p["social_col"]))
+    r = mb.DevicePopulation(n, S, H, 5, 10, seed=4).to_host()
+    assert not np.array_equal(r["current_mode"], p["current_mode"])
+
+
+def test_device_resident_population_runs_like_its_host_copy():
+    """mvb_create* on a population that lives in device memory (no host copy made) against the oracle on its host copy,
+    and against a handle created from the host copy: same layout, same results."""
+    n = 50_000
+    d = mb.DevicePopulation(n, 4, 10, 5, 10, seed=8)
+    p = d.to_host()
+    tab = mb.synth_tables(4, 10, n, seed=8)
+    w = mb.weather_pattern(40, seed=8)
+    with mb.Simulation(d, tab, mb.make_params()) as a, mb.Simulation(p, tab, mb.make_params()) as b:
+        compare_with_host(a, p)
+        da, ra = a.run(w)
+        db, rb = b.run(w)
+        assert np.array_equal(ra[0], rb[0])
+        o = OracleSimulation(p, tab, mb.make_params())
+        do, ro = o.run(w)
+        assert np.array_equal(ra[0], ro)
+        assert_state_equal(a.get_state(0), o.get_state(), "device-resident population")
