@@ -9,6 +9,15 @@ weekday).  A STEP is one simulated weekday of every replica: update_habit + cong
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
 Under torchrun (N > 1) one process per GPU; time = max over ranks of the CUDA-event time of the K launches.
+
+The same JSON line carries an `extra` block with the other BASELINE.json configurations, each on its own named
+calendar (device-timed, not part of `value`):
+  N = 1: c1 (the shipped configuration, 8 replicas x 111 166 agents x 5 years, intervention on day 365),
+         c2 (1 x 1M agents x 2 years), c5 (256 scenario variants x 100k agents over one shared population, 2 years,
+         every variant's day-365 intervention firing inside the timed run)
+  N > 1: c4 (ONE population agent-partitioned over the N ranks): first bit-exact checks of the partitioned run at
+         world = N against the CPU oracle (20k agents) and against a 1-rank GPU run (8M agents), then the timed run
+         on 50M agents (N = 8) or 6M x N agents, with per-rank times.
 """
 from __future__ import annotations
 
@@ -43,6 +52,7 @@ def parse():
     ap.add_argument("--sweep", action="store_true",
                     help="BASELINE config 5: --replicas scenario variants (tables + ownership differ) over ONE shared population")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra legs (c1, c2, c5 at N=1; c4 at N>1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-baseline-days", type=int, default=100)
     return ap.parse_args()
@@ -159,9 +169,9 @@ def cpu_reference_throughput(args, n_threads, n_days, warm_days=1, shape="dense"
     cores, via the oracle port rebuilt here with -O3 -march=native: agent-days/s over n_days weekdays.
     shape="reference": the reference-shaped twin of the oracle (heap objects, a map per intermediate result)."""
     import motivate_b200 as mb
-    from oracle.binding import OracleSimulation
+    from oracle.binding import OracleSimulation, synth_population
     agents = agents or args.agents
-    base = [mb.synth_population(agents, 4, 10, 5, 10, seed=s) for s in range(min(2, n_threads))]
+    base = [synth_population(agents, 4, 10, 5, 10, seed=s) for s in range(min(2, n_threads))]
     tabs = [mb.synth_tables(4, 10, agents, seed=s) for s in range(len(base))]
     prm = mb.make_params()
     sims = [OracleSimulation(base[i % len(base)], tabs[i % len(base)], prm, native=True, shape=shape) for i in range(n_threads)]
@@ -189,10 +199,9 @@ def run_reference(args, rank):
         return
     cores = os.cpu_count() or 1
     # bounded sample: one replica per core, K weekdays each (the reference's own parallelism)
-    per_step = []
-    import motivate_b200 as mb
-    from oracle.binding import OracleSimulation
-    base = [mb.synth_population(args.agents, 4, 10, 5, 10, seed=s) for s in range(min(2, cores))]
+    import motivate_b200 as mb                      # python helpers only: this arm never loads libmotivate_b200.so
+    from oracle.binding import OracleSimulation, synth_population
+    base = [synth_population(args.agents, 4, 10, 5, 10, seed=s) for s in range(min(2, cores))]      # oracle/libmotivate_synthhost.so
     tabs = [mb.synth_tables(4, 10, args.agents, seed=s) for s in range(len(base))]
     prm = mb.make_params()
     sims = [OracleSimulation(base[i % len(base)], tabs[i % len(base)], prm, native=True) for i in range(cores)]
@@ -214,6 +223,11 @@ def run_reference(args, rank):
     dt = time.perf_counter() - t0
     value = cores * args.agents * args.steps / dt
     sample = f"{cores} replicas x {args.agents} agents x {args.steps} weekdays, one single-threaded replica per core"
+    try:
+        product_loaded = "libmotivate_b200.so" in open("/proc/self/maps").read()
+    except OSError:
+        product_loaded = None
+    assert not product_loaded, "the CPU arm must not load the product library"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
@@ -221,6 +235,7 @@ def run_reference(args, rank):
         "config": workload_config(args, note="CPU arm: bounded sample, " + sample),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "product_library_loaded": product_loaded,
     }))
 
 
@@ -308,22 +323,26 @@ def main():
     max_ms = float(t.item())
     # sanity: statistics rows are populated (work was not skipped)
     days, rows = sim.fetch_rows()
-    assert len(days) == 1 + args.warmup + args.steps and all(int(r[-1, 0]) > 0 or int(r[-1, 1]) >= 0 for r in rows)
+    assert len(days) == 1 + args.warmup + args.steps
+    for r in rows:          # work was not skipped: every row counts active agents, and the per-neighbourhood columns add up to ActiveMode
+        assert int(r[-1, 0]) > 0 and int(r[-1, 0]) == int(r[-1, 7 + 4:].sum()) and not np.array_equal(r[0], r[-1])
     sim.close()
 
     total_agents = args.agents * args.replicas
     value = total_agents * args.steps / (max_ms * 1e-3)
     peak, peak_src = peaks()
-    ach = alg_bytes * args.steps / (ms * 1e-3) / 1e9
+    # per-GPU roofline of the slowest rank: replicas are dealt evenly, so every rank moves alg_bytes per launch
+    ach = alg_bytes * args.steps / (max_ms * 1e-3) / 1e9
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": workload_config(args),
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                     "traffic": profile_traffic(per) if args.agents == 1_000_000 else None, "peak_source": peak_src,
+                     "traffic": profile_traffic(per) if args.agents == 1_000_000 else None,
+                     "traffic_source": traffic_source() if args.agents == 1_000_000 else None, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes,
-                     "kernel": "day kernel (one launch per weekday per rank), rank 0"},
+                     "kernel": "day kernel (one launch per weekday per rank); time = max over ranks"},
         "clocks": clocks,
     }
 
@@ -342,10 +361,213 @@ def main():
         out["cpu_baseline"]["reference_shaped"] = {
             "value": v2, "unit": UNIT, "cores": cores,
             "sample": f"{cores} replicas x {rs_agents} agents x 4 weekdays ({dt2:.1f} s), oracle/reference_shaped.cpp -O3 -march=native"}
+    if not args.no_extra:
+        del pops, tabs
+        out["extra"] = extra_legs(args, rank, local_rank, world, torch, dist, mb)
     if rank == 0:
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def device_run(sim, w, n_days, interventions=None):
+    """The whole calendar [0, n_days) on the device, device-timed; returns (ms, launches, days, rows)."""
+    sim.run_async(w, 0, n_days, interventions)
+    sim.sync()
+    ms, launches = sim.last_run_stats()
+    days, rows = sim.fetch_rows()
+    return ms, launches, days, rows
+
+
+def leg_line(n_agents_total, weekdays, ms, alg_bytes_per_day, peak, what, **more):
+    return {"workload": what, "agent_days_per_sec": n_agents_total * weekdays / (ms * 1e-3), "weekdays": weekdays,
+            "ms_per_weekday": ms / weekdays, "roofline_frac": alg_bytes_per_day * weekdays / (ms * 1e-3) / 1e9 / peak, **more}
+
+
+def extra_legs(args, rank, local_rank, world, torch, dist, mb):
+    peak, _ = peaks()
+    prm = mb.make_params()
+    extra = {}
+    if world > 1:
+        extra["c4"] = leg_c4(args, rank, local_rank, world, torch, dist, mb, peak)
+        return extra
+    # ---- c2: BASELINE configs[1] -------------------------------------------------------------------------------
+    n_days = 730
+    w = mb.weather_pattern(n_days, seed=0)
+    pop, tab = mb.synth_population(1_000_000, 4, 10, 5, 10, seed=0), mb.synth_tables(4, 10, 1_000_000, seed=0)
+    with mb.Simulation(pop, tab, prm, device=local_rank) as sim:
+        device_run(sim, w, 60)                                                   # warm-up
+        ms, launches, days, rows = device_run(sim, w, n_days)
+        extra["c2"] = leg_line(1_000_000, launches, ms, sim.algorithmic_bytes_per_day(0), peak,
+                               "C2: 1 replica x 1M agents (S=4, H=10, BA links 5+10) x 2 years = 521 weekdays on one B200",
+                               l2="171 MB per weekday: partly L2-resident between launches, a small-population number")
+        assert launches == 521 and int(rows[0][-1, 0]) == int(rows[0][-1, 11:].sum()) > 0
+    del pop
+    # ---- c5: BASELINE configs[4], every variant's intervention fires on day 365, inside the timed run ----------
+    V, n = 256, 100_000
+    base, tab0 = mb.synth_population(n, 4, 10, 5, 10, seed=0), mb.synth_tables(4, 10, n, seed=0)
+    rng = np.random.default_rng(5)
+    pops, tabs, ivs = [], [], []
+    for v in range(V):
+        p = mb.PopulationData(dict(base.arrays))                                 # same graph arrays: stored once on the device
+        t = tab0.copy()
+        sel = rng.random(t.H) < 0.5
+        t.supportiveness[sel, 2:] += np.float32(0.05 * (v % 3))
+        pops.append(p); tabs.append(t)
+        # day 365 (src/simulation.rs:103-105): supportiveness +-0.1 and a Car capacity cut on a subset of neighbourhoods,
+        # cars / bikes +-5 % of the agents (the shape of config/scenario.yaml:3-43, README.md:48-76)
+        t2 = t.copy()
+        sel2 = rng.random(t.H) < 0.5
+        t2.supportiveness[sel2, 2:] += np.float32(0.1); t2.supportiveness[sel2, 0] -= np.float32(0.1)
+        t2.capacity[sel2, 0] = (t2.capacity[sel2, 0] * 0.8).astype(np.uint32)
+        own = {}
+        for k, sign in (("owns_car", (-1, 0, 1)[v % 3]), ("owns_bike", (1, -1, 0)[v % 3])):
+            a = base[k].copy()
+            if sign:
+                pool = np.flatnonzero(a == (0 if sign > 0 else 1))
+                a[rng.choice(pool, n // 20, replace=False)] = 1 if sign > 0 else 0
+            own[k] = a
+        ivs.append(mb.InterventionData(day=365, tables=t2, owns_car=own["owns_car"], owns_bike=own["owns_bike"]))
+    with mb.Simulation(pops, tabs, prm, device=local_rank) as sim:
+        alg = sum(sim.algorithmic_bytes_per_day(r) for r in range(V))
+        device_run(sim, w, 40)                                                   # warm-up
+        ms, launches, days, rows = device_run(sim, w, n_days, ivs)
+        k365 = int(np.searchsorted(days, 365))
+        moved = sum(int(not np.array_equal(r[k365 - 1, 11:], r[k365 + 4, 11:])) for r in rows)
+        extra["c5"] = leg_line(V * n, launches // -(-V // 64), ms, alg, peak,
+                               "C5: 256 scenario variants x 100k agents over ONE shared population and link graph, 2 years; every variant's "
+                               "intervention (tables + car/bike ownership) fires on day 365, inside the timed run",
+                               intervention={"day": 365, "variants": V, "inside_timed_region": True, "rows_changed_after": moved,
+                                             "how": "staged before the loop, applied by ONE apply_interventions_kernel launch"},
+                               l2="link codes of the shared graph are L2-resident by design; per-variant state streams from HBM")
+        assert moved == V
+    del pops, tabs, ivs, base
+    # ---- c1: BASELINE configs[0], the shipped configuration + the three documented fixes -------------------------
+    import tempfile
+    from motivate_b200 import c1, simulation
+    from motivate_b200.scenario import Parameters
+    from motivate_b200.weather import make_pattern
+    d = tempfile.mkdtemp()
+    pp, sp = c1.materialise(d)
+    P = Parameters.from_file(pp)
+    preps = [simulation.prepare(str(i), True, "", sp, P.number_of_people, P.social_connectivity, P.subculture_connectivity,
+                                P.neighbourhood_connectivity, P.number_of_neighbour_links, P.days_in_habit_average, P.distributions,
+                                number_of_social_network_links=P.number_of_social_network_links)
+             for i in range(1, P.number_of_simulations + 1)]
+    n_days = 365 * P.total_years
+    w = make_pattern(n_days)                                                     # the reference's own rain sequence (HC-128, zero seed)
+    with mb.Simulation([p.population for p in preps], [p.tables for p in preps], preps[0].params, device=local_rank) as sim:
+        alg = sum(sim.algorithmic_bytes_per_day(r) for r in range(len(preps)))
+        device_run(sim, w, 60)
+        ms, launches, days, rows = device_run(sim, w, n_days, [p.intervention for p in preps])
+        extra["c1"] = leg_line(P.number_of_people * len(preps), launches, ms, alg, peak,
+                               f"C1: the reference's shipped configuration (examples/c1: {P.number_of_people} agents, 3 subcultures, 20 "
+                               f"neighbourhoods, intervention on day 365) x {len(preps)} simulations x {P.total_years} years, HC-128 rain sequence",
+                               l2="19 MB per replica per weekday: L2-resident, a small-population number",
+                               parity="tests/test_gpu_c1.py: bit-exact against the oracle every weekday of years 1-2")
+        assert launches == 1304
+    return extra
+
+
+def leg_c4(args, rank, local_rank, world, torch, dist, mb, peak):
+    """BASELINE configs[3]: ONE population agent-partitioned over the ranks.  Populations are generated on each rank's own
+    GPU from the same seed (mvb_synth_create_device: identical on every rank up to the order inside a link list, which the
+    update does not depend on)."""
+    from oracle.binding import OracleSimulation
+    prm = mb.make_params()
+    dev = torch.device("cuda", local_rank)
+
+    def uid():
+        u = [mb.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(u, src=0)
+        return u[0]
+
+    def all_ok(flag):
+        t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item())
+
+    def same_state(a, b, owner_mask):
+        return (np.array_equal(a["current_mode"], b["current_mode"]) and np.array_equal(a["norm"], b["norm"]) and
+                np.array_equal(a["hist"], b["hist"]) and
+                np.array_equal(a["habit"][owner_mask].view(np.uint32), b["habit"][owner_mask].view(np.uint32)))
+
+    out = {}
+    # 1. against the CPU oracle: 20k agents, 6 weeks, an intervention on a Sunday
+    n = 20_000
+    d = mb.DevicePopulation(n, 4, 10, 5, 10, seed=11, device=local_rank)
+    p = d.to_host()
+    tab = mb.synth_tables(4, 10, n, seed=11)
+    w = mb.weather_pattern(43, seed=11)
+    tab2 = tab.copy(); tab2.capacity[:, 0] //= 2; tab2.supportiveness[::2, 2:] += np.float32(0.1)
+    iv = mb.InterventionData(day=20, tables=tab2, owns_car=1 - p["owns_car"], owns_bike=None)
+    sim = mb.Simulation.partitioned(d, tab, prm, device=local_rank, rank=rank, world=world, unique_id=uid())
+    days, rows = sim.run(w, interventions=iv)
+    st = sim.get_state(0)
+    mine = sim.partition_owner() == rank
+    sim.close()
+    o = OracleSimulation(p, tab, prm)
+    d2, r2 = o.run(w, intervention=iv)
+    ok = np.array_equal(days, d2) and np.array_equal(rows[0], r2) and same_state(st, o.get_state(), mine)
+    out["partitioned_parity_vs_oracle"] = {"agents": n, "weekdays": len(days) - 1, "world": world,
+                                            "result": "bit-exact" if all_ok(ok) else "MISMATCH",
+                                            "compared": "statistics rows, every agent's mode and norm, habit bits of the agents each rank owns"}
+    d.close()
+    # 2. against a 1-rank GPU run: 8M agents (most links gathered from L2: the large-population path), 12 weekdays
+    n = 8_000_000
+    d = mb.DevicePopulation(n, 4, 10, 5, 10, seed=12, device=local_rank)
+    tab = mb.synth_tables(4, 10, n, seed=12)
+    w = mb.weather_pattern(17, seed=12)
+    sim = mb.Simulation.partitioned(d, tab, prm, device=local_rank, rank=rank, world=world, unique_id=uid())
+    days, rows = sim.run(w)
+    st = sim.get_state(0)
+    mine = sim.partition_owner() == rank
+    sim.close()
+    one = mb.Simulation(d, tab, prm, device=local_rank)
+    d1, r1 = one.run(w)
+    s1 = one.get_state(0)
+    one.close()
+    ok = np.array_equal(days, d1) and np.array_equal(rows[0], r1[0]) and same_state(st, s1, mine)
+    import zlib
+    out["partitioned_parity_vs_one_gpu"] = {"agents": n, "weekdays": len(days) - 1, "world": world,
+                                             "result": "bit-exact" if all_ok(ok) else "MISMATCH",
+                                             "mode_vector_crc32": zlib.crc32(st["current_mode"].tobytes()),
+                                             "norm_vector_crc32": zlib.crc32(st["norm"].tobytes())}
+    out["partitioned_parity"] = ("bit-exact" if out["partitioned_parity_vs_oracle"]["result"] == "bit-exact" and
+                                 out["partitioned_parity_vs_one_gpu"]["result"] == "bit-exact" else "MISMATCH")
+    d.close()
+    del st, s1
+    # 3. the timed run
+    n = 50_000_000 if world == 8 else 6_000_000 * world
+    d = mb.DevicePopulation(n, 4, 10, 5, 10, seed=0, device=local_rank)
+    tab = mb.synth_tables(4, 10, n, seed=0)
+    n_days = weekdays_calendar(args.warmup + args.steps)
+    w = mb.weather_pattern(n_days, seed=0)
+    warm_end = weekdays_calendar(args.warmup)
+    t0 = time.perf_counter()
+    sim = mb.Simulation.partitioned(d, tab, prm, device=local_rank, rank=rank, world=world, unique_id=uid())
+    t_create = time.perf_counter() - t0
+    alg = sim.algorithmic_bytes_per_day(0)
+    sim.run_async(w, 0, warm_end); sim.sync()
+    dist.barrier(); torch.cuda.synchronize()
+    sim.run_async(w, warm_end, n_days); sim.sync()
+    torch.cuda.synchronize(); dist.barrier()
+    ms, launches = sim.last_run_stats()
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    per_rank = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(per_rank, t)
+    max_ms = max(float(x.item()) for x in per_rank)
+    mem = torch.cuda.memory_allocated(dev)            # (torch's own; the library's memory is outside torch's allocator)
+    free_b, total_b = torch.cuda.mem_get_info(dev)
+    sim.close(); d.close()
+    out.update({
+        "workload": f"C4: ONE population of {n} agents (S=4, H=10, BA links 5+10) agent-partitioned over {world} B200; per weekday one NCCL "
+                    "all-gather of the packed 2-bit modes + norms and one all-reduce of the counters",
+        "agents": n, "agent_days_per_sec": n * args.steps / (max_ms * 1e-3), "weekdays": args.steps, "ms_per_weekday": max_ms / args.steps,
+        "ms_per_weekday_by_rank": [float(x.item()) / args.steps for x in per_rank],
+        "roofline_frac_per_gpu": alg * args.steps / (max_ms * 1e-3) / 1e9 / world / peak,
+        "create_seconds_rank0": t_create, "device_memory_in_use_gb_rank0": (total_b - free_b) / 1e9})
+    return out
 
 
 def run_partitioned(args, rank, local_rank, world, torch, dist, mb):
@@ -407,6 +629,16 @@ def run_partitioned(args, rank, local_rank, world, torch, dist, mb):
         dist.destroy_process_group()
 
 
+def traffic_source():
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        j = json.load(open(p))
+        return ("NOT measured in this run: dram__bytes_read.sum + dram__bytes_write.sum of the day kernel from the committed ncu --set full "
+                f"capture {j.get('capture', 'under profiles/')}, per 1M-agent replica, times the replicas per launch")
+    except Exception:
+        return None
+
+
 def profile_traffic(replicas_on_rank):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the day kernel, from the committed `ncu --set full`
     capture (profiles/traffic.json holds it per replica of 1M agents; a launch steps `replicas_on_rank` of them)."""
@@ -424,6 +656,18 @@ def e2e(args, pops, tabs, prm, w, n_days, local_rank, world, dist, torch):
     pinned memory) + mvb_run over the same calendar (weather in, statistics rows D2H) + mvb_destroy."""
     import motivate_b200 as mb
     h2d = sum(sum(v.nbytes for v in p.arrays.values() if v is not None) for p in pops) + n_days
+    # context for the number below: what the same pinned buffers need as plain copies on this box (the PCIe floor of set-up)
+    floor = None
+    pins = [t for p in pops for t in getattr(p, "_pins", [])]
+    if pins:
+        dst = torch.empty(max(t.numel() for t in pins), dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        tf = time.perf_counter()
+        for t in pins:
+            dst[:t.numel()].copy_(t, non_blocking=True)
+        torch.cuda.synchronize()
+        floor = time.perf_counter() - tf
+        del dst
     if dist:
         dist.barrier()
     torch.cuda.synchronize()
@@ -435,6 +679,7 @@ def e2e(args, pops, tabs, prm, w, n_days, local_rank, world, dist, torch):
     sim.close()
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
+    t3 = t0 + dt                                       # rank-local end, before the max over ranks
     t = torch.tensor([dt], dtype=torch.float64, device="cuda")
     if dist:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -444,7 +689,7 @@ def e2e(args, pops, tabs, prm, w, n_days, local_rank, world, dist, torch):
     return {"value": args.agents * args.replicas * weekdays / dt, "unit": UNIT,
             "h2d_bytes_per_step": h2d / weekdays, "d2h_bytes_per_step": d2h / weekdays,
             "weekdays": weekdays, "seconds": dt,
-            "seconds_rank0": {"create": t1 - t0, "run": t2 - t1, "destroy": t0 + dt - t2},
+            "seconds_rank0": {"create": t1 - t0, "run": t2 - t1, "destroy": t3 - t2, "plain_h2d_of_the_same_buffers": floor},
             "what": "mvb_create_batch (H2D of populations from pinned host memory) + mvb_run (rows D2H) + mvb_destroy"}
 
 

@@ -187,38 +187,13 @@ def synth_population(n_agents, n_subcultures=4, n_neighbourhoods=10, social_link
     """Seeded synthetic population (mvb_synth_create).  Bikes default to the number of
     cars, reproducing src/agent_generation.rs:160."""
     lib = _ffi.load()
-    sp = _ffi.SynthSpec()
-    sp.n_agents, sp.n_subcultures, sp.n_neighbourhoods = n_agents, n_subcultures, n_neighbourhoods
-    sp.social_links_min, sp.neighbour_links_min = social_links_min, neighbour_links_min
-    sp.n_cars = int(round(car_ratio * n_agents))
-    sp.n_bikes = sp.n_cars if bike_ratio is None else int(round(bike_ratio * n_agents))
-    sp.seed = seed
-    sp.n_gmm = len(gmm)
-    for g, row in enumerate(gmm):
-        for k in range(3):
-            sp.gmm[g][k] = row[k]
+    sp = _synth_spec(n_agents, n_subcultures, n_neighbourhoods, social_links_min, neighbour_links_min, car_ratio, bike_ratio, seed, gmm)
     h = C.c_void_p()
     _check(lib.mvb_synth_create(C.byref(sp), C.byref(h)))
     try:
-        p = lib.mvb_synth_population(h).contents
-        N = p.n_agents
-
-        def arr(ptr, n, dt):
-            return np.ctypeslib.as_array(ptr, shape=(n,)).astype(dt, copy=True) if n else np.zeros(0, dt)
-
-        s_rowptr = arr(p.social_rowptr, N + 1, np.uint64)
-        n_rowptr = arr(p.neighbour_rowptr, N + 1, np.uint64)
-        out = dict(
-            subculture=arr(p.subculture, N, np.uint8), neighbourhood=arr(p.neighbourhood, N, np.uint16),
-            commute=arr(p.commute, N, np.uint8), owns_car=arr(p.owns_car, N, np.uint8),
-            owns_bike=arr(p.owns_bike, N, np.uint8), weather_sensitivity=arr(p.weather_sensitivity, N, np.float32),
-            habit=arr(p.habit, 4 * N, np.float32).reshape(N, 4), current_mode=arr(p.current_mode, N, np.uint8),
-            norm=arr(p.norm, N, np.uint8), social_rowptr=s_rowptr,
-            social_col=arr(p.social_col, int(s_rowptr[N]), np.uint32), neighbour_rowptr=n_rowptr,
-            neighbour_col=arr(p.neighbour_col, int(n_rowptr[N]), np.uint32))
+        return _population_from_struct(lib.mvb_synth_population(h).contents)
     finally:
         lib.mvb_synth_destroy(h)
-    return PopulationData(out)
 
 
 def _synth_spec(n_agents, n_subcultures, n_neighbourhoods, social_links_min, neighbour_links_min, car_ratio, bike_ratio, seed, gmm):

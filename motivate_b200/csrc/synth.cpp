@@ -9,7 +9,9 @@
 #include <cstring>
 #include <numeric>
 
+#ifndef MVB_NO_CUDA            // oracle/Makefile builds this file alone, without CUDA, as the CPU arm's input generator
 #include <cuda_runtime_api.h>
+#endif
 
 #include "mvb_internal.h"
 #include "synth.h"
@@ -206,7 +208,9 @@ int mvb_synth_create(const mvb_synth_spec* sp, mvb_synth** out) {
 
 void mvb_synth_destroy(mvb_synth* s) {
     if (!s) return;
+#ifndef MVB_NO_CUDA
     if (s->d_block || s->d_block2) { cudaSetDevice(s->device); cudaFree(s->d_block); cudaFree(s->d_block2); }
+#endif
     delete s;
 }
 const mvb_population* mvb_synth_population(const mvb_synth* s) { return s ? &s->pop : nullptr; }

@@ -69,6 +69,36 @@ def load(native=False, shape="dense"):
     return lib
 
 
+SYNTH_PATH = os.path.join(_HERE, "libmotivate_synthhost.so")
+
+
+def synth_population(n_agents, n_subcultures=4, n_neighbourhoods=10, social_links_min=5, neighbour_links_min=10,
+                     car_ratio=64926 / 111166, bike_ratio=None, seed=0, gmm=None) -> PopulationData:
+    """motivate_b200.synth_population (same seeded host generator, same output) WITHOUT loading the product library:
+    oracle/libmotivate_synthhost.so is motivate_b200/csrc/synth.cpp compiled on its own (oracle/Makefile).  For
+    bench.py's CPU arm, whose process must not depend on libmotivate_b200.so."""
+    from motivate_b200.api import DEFAULT_GMM, _population_from_struct, _synth_spec
+    if "synth" not in _libs:
+        if not os.path.exists(SYNTH_PATH):
+            subprocess.run(["make", "-C", _HERE, "libmotivate_synthhost.so"], check=True)
+        lib = C.CDLL(SYNTH_PATH, mode=C.RTLD_LOCAL)
+        lib.mvb_synth_create.restype, lib.mvb_synth_create.argtypes = C.c_int, [C.POINTER(_ffi.SynthSpec), C.POINTER(C.c_void_p)]
+        lib.mvb_synth_population.restype, lib.mvb_synth_population.argtypes = _ffi.PopP, [C.c_void_p]
+        lib.mvb_synth_destroy.restype, lib.mvb_synth_destroy.argtypes = None, [C.c_void_p]
+        lib.mvb_last_error.restype = C.c_char_p
+        _libs["synth"] = lib
+    lib = _libs["synth"]
+    sp = _synth_spec(n_agents, n_subcultures, n_neighbourhoods, social_links_min, neighbour_links_min, car_ratio, bike_ratio,
+                     seed, gmm or DEFAULT_GMM)
+    h = C.c_void_p()
+    if lib.mvb_synth_create(C.byref(sp), C.byref(h)):
+        raise RuntimeError((lib.mvb_last_error() or b"").decode())
+    try:
+        return _population_from_struct(lib.mvb_synth_population(h).contents)
+    finally:
+        lib.mvb_synth_destroy(h)
+
+
 class OracleSimulation:
     """One replica on the CPU oracle; same method names as motivate_b200.Simulation.  shape="reference" runs the
     reference-shaped twin (heap objects, per-call maps) instead of the dense oracle."""

@@ -22,6 +22,7 @@ def test_reference_arm_prints_one_contract_line():
     assert "workload" in d["config"] and "model" not in d["config"]
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert d["product_library_loaded"] is False                 # inputs come from oracle/libmotivate_synthhost.so
     e = d["e2e"]
     assert e["value"] == d["value"] and e["unit"] == d["unit"] and e["h2d_bytes_per_step"] == 0 and e["d2h_bytes_per_step"] == 0
 
