@@ -20,7 +20,8 @@ struct SetupScalars {                 // device -> host after each stage
 struct Plan {
     uint32_t N = 0, H = 0, n_hubs = 0, hub_pad = 0, n_hs = 0, N_pad = 0, n2 = 0, staged_hub_slots = 0, hot_words = 0;
     bool all_hot = false;
-    std::vector<uint32_t> gsize, gpad, gstart, gofs, take;
+    uint32_t mode = kLayoutGlobal;
+    std::vector<uint32_t> gsize, gpad, gstart, gofs, take, nb_slice_begin;
     std::vector<StageRange> ranges;
 };
 inline uint32_t round_up_u32(uint32_t v, uint32_t m) { return (v + m - 1) / m * m; }
@@ -51,7 +52,14 @@ int make_plan(uint32_t N, uint32_t H, uint32_t capacity_agents, const uint32_t* 
     P.N_pad = (uint32_t)total;
     P.n2 = N - n_hubs;
     P.all_hot = P.N_pad <= capacity_agents;
-    if (P.all_hot) {
+    P.mode = pick_layout_mode(P.N_pad, capacity_agents);
+    P.staged_hub_slots = P.all_hot ? P.hub_pad : std::min(P.hub_pad, capacity_agents);
+    if (P.mode == kLayoutLocal) {
+        // hubs get at most half of shared memory, the rest holds the prefix of the block's own neighbourhood
+        P.staged_hub_slots = std::min(P.hub_pad, capacity_agents / 2 / 64 * 64);
+        const uint32_t local = capacity_agents - P.staged_hub_slots;
+        for (uint32_t h = 0; h < H; ++h) P.take[h] = std::min(P.gsize[h], local);
+    } else if (P.all_hot) {
         P.take = P.gsize;
     } else {
         // largest degree threshold theta such that {hubs} U {d >= theta} (rounded to 64 per group) fits
@@ -78,14 +86,25 @@ int make_plan(uint32_t N, uint32_t H, uint32_t capacity_agents, const uint32_t* 
             P.take[h] += extra; used += extra;
         }
     }
-    P.staged_hub_slots = P.all_hot ? P.hub_pad : std::min(P.hub_pad, capacity_agents);
+    P.nb_slice_begin.resize((size_t)H + 1);
+    for (uint32_t h = 0; h < H; ++h) P.nb_slice_begin[h] = (P.gstart[h] - P.hub_pad) / 32;
+    P.nb_slice_begin[H] = (P.N_pad - P.hub_pad) / 32;
     uint32_t staged = 0;
     auto add_range = [&](uint32_t start, uint32_t count) {
         if (!count) return;
         P.ranges.push_back(StageRange{start / 16, count / 16, staged / 16, 0});
         staged += count;
     };
-    if (P.all_hot) add_range(0, P.N_pad);
+    if (P.mode == kLayoutLocal) {
+        P.ranges.push_back(StageRange{0, P.staged_hub_slots / 16, 0, 0});
+        uint32_t longest = 0;
+        for (uint32_t h = 0; h < H; ++h) {
+            const uint32_t words = round_up_u32(P.take[h], 64) / 16;
+            P.ranges.push_back(StageRange{P.gstart[h] / 16, words, P.staged_hub_slots / 16, 0});
+            longest = std::max(longest, words);
+        }
+        staged = P.staged_hub_slots + longest * 16;
+    } else if (P.all_hot) add_range(0, P.N_pad);
     else {
         add_range(0, std::min(P.hub_pad, capacity_agents));
         for (uint32_t h = 0; h < H; ++h) add_range(P.gstart[h], P.take[h]);
@@ -339,7 +358,7 @@ static int create_impl(uint32_t R, const mvb_population* const* pops, const mvb_
 
     // pinned landing zone of the small device -> host reads (one graph at a time) and source of the plan uploads
     const size_t cnt_bytes = (sizeof(uint32_t) * (size_t)H_max * (kHubDegree + 1) + 255) & ~(size_t)255;
-    const size_t plan_bytes = sizeof(uint32_t) * 3 * (size_t)H_max + sizeof(StageRange) * ((size_t)H_max + 2);
+    const size_t plan_bytes = sizeof(uint32_t) * (4 * (size_t)H_max + 1) + sizeof(StageRange) * ((size_t)H_max + 2);
     char* pin = nullptr; size_t pin_cap = 0;
     MVB_CUDA(pinned_cache().get(cnt_bytes + plan_bytes + 256, &pin, &pin_cap));
     struct PinGuard { char* p; size_t cap; ~PinGuard() { pinned_cache().put(p, cap); } } pin_guard{pin, pin_cap};
@@ -399,19 +418,23 @@ static int create_impl(uint32_t R, const mvb_population* const* pops, const mvb_
             L = GraphLayout();
             L.N = N; L.N_pad = P.N_pad; L.Es = gi.Es; L.En = gi.En;
             L.n_hub_slices = P.n_hs; L.n_sell_slices = (P.N_pad - P.hub_pad) / 32; L.hot_words = P.hot_words;
-            L.ranges = P.ranges;
+            L.ranges = P.ranges; L.mode = P.mode; L.nb_slice_begin = P.nb_slice_begin;
             if (L.hot_words + 4 > s->vec_cap_words) { set_error("internal: staged vector larger than its shared-memory slot"); return MVB_ERR_STATE; }
             const uint32_t n_hub_rows = P.n_hs * 32, n_sell = L.n_sell_slices, n2 = P.n2, n_hubs = P.n_hubs;
             // ---- stage B: the two orders, hot counts, slices, offsets ------------------------------------------
             uint32_t* hp = reinterpret_cast<uint32_t*>(h_plan);
             memcpy(hp, P.gofs.data(), 4 * (size_t)H); memcpy(hp + H, P.take.data(), 4 * (size_t)H); memcpy(hp + 2 * H, P.gstart.data(), 4 * (size_t)H);
-            memcpy(hp + 3 * H, P.ranges.data(), sizeof(StageRange) * P.ranges.size());
+            memcpy(hp + 3 * H, P.nb_slice_begin.data(), 4 * ((size_t)H + 1));
+            uint32_t* hr = hp + 4 * H + 2;                                        // (8-byte aligned: StageRange is 16 bytes of u32)
+            memcpy(hr, P.ranges.data(), sizeof(StageRange) * P.ranges.size());
             UpBuf plan;
             MVB_CUDA(plan.alloc(4 * 3 * (size_t)H, S));
             MVB_CUDA(cudaMemcpyAsync(plan.p, hp, 4 * 3 * (size_t)H, cudaMemcpyHostToDevice, S));
             const uint32_t* d_gofs = plan.as<uint32_t>(); const uint32_t* d_take = d_gofs + H; const uint32_t* d_gstart = d_gofs + 2 * H;
             MVB_CARVE(s->mem, g->ranges, sizeof(StageRange) * P.ranges.size());
-            MVB_CUDA(cudaMemcpyAsync(g->ranges.p, hp + 3 * H, sizeof(StageRange) * P.ranges.size(), cudaMemcpyHostToDevice, S));
+            MVB_CUDA(cudaMemcpyAsync(g->ranges.p, hr, sizeof(StageRange) * P.ranges.size(), cudaMemcpyHostToDevice, S));
+            MVB_CARVE(s->mem, g->nb_slice_begin, 4 * ((size_t)H + 1));
+            MVB_CUDA(cudaMemcpyAsync(g->nb_slice_begin.p, hp + 3 * H, 4 * ((size_t)H + 1), cudaMemcpyHostToDevice, S));
             MVB_CARVE(s->mem, g->int2ext, 4 * (size_t)P.N_pad);
             MVB_CARVE(s->mem, g->deg, 4 * (size_t)P.N_pad);
             MVB_CARVE(s->mem, g->hub_off, 8 * (size_t)n_hub_rows + 8);
@@ -437,11 +460,11 @@ static int create_impl(uint32_t R, const mvb_population* const* pops, const mvb_
                 MVB_CUDA(radix_sort_pairs(hkk, hvv, n_hubs, 32, scratch.as<uint32_t>(), &hc, S));
                 place_hubs_kernel<<<(n_hubs + 255) / 256, 256, 0, S>>>(n_hubs, P.n_hs, P.staged_hub_slots, hvv[hc], g->int2ext.as<uint32_t>(), is_hot.as<uint8_t>());
             }
-            if (n2) mark_hot_kernel<<<(n2 + 255) / 256, 256, 0, S>>>(n2, key1s, order1, d_gofs, d_take, is_hot.as<uint8_t>());
+            if (n2) mark_hot_kernel<<<(n2 + 255) / 256, 256, 0, S>>>(n2, key1s, order1, d_gofs, d_take, P.mode == kLayoutLocal ? 2 : 1, is_hot.as<uint8_t>());
             uint32_t* d_bad = &d_scal->flag.code;              // count_hot_kernel ORs 1 in: translated below
             MVB_CUDA(cudaMemsetAsync(d_bad, 0, 4, S));
             count_hot_kernel<<<(unsigned)std::min<uint64_t>(((uint64_t)N * 32 + 255) / 256, (uint64_t)sms * 32), 256, 0, S>>>(
-                N, gi.srp, gi.scol, gi.nrp, gi.ncol, is_hot.as<uint8_t>(), nsh.as<uint32_t>(), nnh.as<uint32_t>(), d_bad);
+                N, gi.srp, gi.scol, gi.nrp, gi.ncol, is_hot.as<uint8_t>(), gi.nbhd, nsh.as<uint32_t>(), nnh.as<uint32_t>(), d_bad);
             MVB_CUDA(cudaGetLastError());
             if (n2) {
                 key2_kernel<<<(n2 + 255) / 256, 256, 0, S>>>(n2, key1s, order1, d_gofs, d_take, nsh.as<uint32_t>(), nnh.as<uint32_t>(), kk[cur ^ 1]);
@@ -509,15 +532,17 @@ static int create_impl(uint32_t R, const mvb_population* const* pops, const mvb_
             // unused entries = the code of the always-zero shared-memory word (layout.h)
             fill_u32_kernel<<<sms * 8, 256, 0, S>>>(g->hub_codes.as<uint32_t>(), L.hub_codes_len, pad_code(s->vec_cap_words));
             fill_u32_kernel<<<sms * 8, 256, 0, S>>>(g->sell_codes.as<uint32_t>(), L.sell_codes_len, pad_code(s->vec_cap_words));
-            UpBuf tcode;
+            UpBuf tcode, tcold;
             MVB_CUDA(tcode.alloc(4 * (size_t)N, S));
+            if (P.mode == kLayoutLocal) MVB_CUDA(tcold.alloc(4 * (size_t)N, S));
             tcode_kernel<<<(P.N_pad + 255) / 256, 256, 0, S>>>(P.N_pad, g->int2ext.as<uint32_t>(), g->ranges.as<StageRange>(), (uint32_t)P.ranges.size(),
-                                                             is_hot.as<uint8_t>(), tcode.as<uint32_t>());
+                                                             is_hot.as<uint8_t>(), P.mode == kLayoutLocal ? gi.nbhd : nullptr, tcode.as<uint32_t>(), tcold.as<uint32_t>());
             MVB_CUDA(cudaGetLastError());
             FillArgs fa{gi.srp, gi.scol, gi.nrp, gi.ncol, tcode.as<uint32_t>(), g->int2ext.as<uint32_t>(), P.n_hs, n_sell,
                         g->sell_meta.as<uint4>(), g->sell_codes.as<uint32_t>(), g->deg.as<uint32_t>(),
                         g->hub_off.as<uint64_t>(), g->hub_deg.as<uint4>(), g->hub_codes.as<uint32_t>(),
-                        own_hub_b, own_hub_e, own_sell_b, own_sell_e};
+                        own_hub_b, own_hub_e, own_sell_b, own_sell_e,
+                        P.mode == kLayoutLocal ? tcold.as<uint32_t>() : nullptr, is_hot.as<uint8_t>(), gi.nbhd};
             MVB_CUDA(cudaMemsetAsync(g->deg.p, 0, g->deg.bytes, S));
             if (n_sell) fill_sell_kernel<<<(unsigned)(((uint64_t)n_sell * 32 + 255) / 256), 256, 0, S>>>(fa);
             if (P.n_hs) fill_hub_kernel<<<(unsigned)(((uint64_t)n_hub_rows * 32 + 255) / 256), 256, 0, S>>>(fa, n_hub_rows);
@@ -525,7 +550,7 @@ static int create_impl(uint32_t R, const mvb_population* const* pops, const mvb_
             if (world > 1) { s->own[0] = own_hub_b; s->own[1] = own_hub_e; s->own[2] = own_sell_b; s->own[3] = own_sell_e; }
             // everything temporary goes back to the pool in stream order
             for (UpBuf* b : {&deg, &key[0], &key[1], &val[0], &val[1], &cnt, &scal, &scratch, &is_hot, &nsh, &nnh, &plan, &hk[0], &hk[1], &hv[0], &hv[1],
-                             &sell_K, &sell_len, &sell_off, &hub_nu, &hub_len, &unit_base, &sums, &tcode})
+                             &sell_K, &sell_len, &sell_off, &hub_nu, &hub_len, &unit_base, &sums, &tcode, &tcold})
                 b->release(S);
             for (UpBuf& b : gi.b) b.release(S);
         }
@@ -590,6 +615,8 @@ static int create_impl(uint32_t R, const mvb_population* const* pops, const mvb_
         d.cap = rp.tables_u.as<uint32_t>(); d.nres = rp.tables_u.as<uint32_t>() + 4 * rp.H;
         d.cong = rp.cong.as<float>();
         d.int2ext = g->int2ext.as<uint32_t>();
+        d.local_mode = L.mode == kLayoutLocal ? 1u : 0u;
+        d.nb_slice_begin = g->nb_slice_begin.as<uint32_t>();
     }
     const double tm3 = now();
     MVB_CUDA(cudaFuncSetAttribute(day_kernel<true, 1024, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
@@ -605,6 +632,10 @@ static int create_impl(uint32_t R, const mvb_population* const* pops, const mvb_
         ncclUniqueId id;
         memcpy(&id, unique_id, sizeof id);
         MVB_NCCL(n->CommInitRank(&s->comm, (int)world, id, (int)rank));
+        for (uint32_t k = 0; k < world; ++k) s->xchg_words = std::max(s->xchg_words, s->bounds[k + 1] - s->bounds[k]);
+        MVB_CUDA(s->xchg.alloc((size_t)world * 2 * s->xchg_words * sizeof(uint2)));
+        MVB_CUDA(s->d_bounds.alloc(4 * ((size_t)world + 1)));
+        MVB_CUDA(cudaMemcpyAsync(s->d_bounds.p, s->bounds.data(), 4 * ((size_t)world + 1), cudaMemcpyHostToDevice, S));
     }
     s->rep_args.assign((R + kMaxRepsPerLaunch - 1) / kMaxRepsPerLaunch, RepArray{});
     for (uint32_t r = 0; r < R; ++r) s->rep_args[r / kMaxRepsPerLaunch].r[r % kMaxRepsPerLaunch] = s->h_reps[r];

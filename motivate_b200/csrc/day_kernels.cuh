@@ -57,6 +57,8 @@ struct RepDev {                     // device-side descriptor of one replica
     const uint32_t* cap; const uint32_t* nres;   // [H][4], [H]
     float* cong;                    // [H][4] modifier used by the last step (for mvb_get_state)
     const uint32_t* int2ext;        // [N_pad] internal slot -> caller's agent id (kInvalid = padding); not read by the day kernel
+    const uint32_t* nb_slice_begin; // [H + 1] SELL slices of every neighbourhood (LOCAL layout: parts are neighbourhood-pure)
+    uint32_t local_mode, pad_;      // layout.h LayoutMode
 };
 
 __host__ __device__ inline uint32_t rec_width(uint32_t S, uint32_t H) { return 4 * H + 7 + S; }
@@ -357,11 +359,21 @@ day_kernel(const __grid_constant__ RepArray reps, uint32_t R, uint32_t P, uint32
         uint32_t* s_rec = reinterpret_cast<uint32_t*>(s_des + 4 * S);
         const uint32_t* __restrict__ g_vec = reinterpret_cast<const uint32_t*>(r.vec[parity]);
 
+        // LOCAL layout: part p = (neighbourhood p / Q, class p % Q of its slices); the block stages the hub region and
+        // that neighbourhood's own prefix.  GLOBAL: class p of all slices; every range is staged.
+        uint32_t Q = P, q = p, sell_b = r.sell_begin, sell_e = r.sell_end, nb_part = 0;
+        if (r.local_mode) {
+            Q = P / H; nb_part = p / Q; q = p - nb_part * Q;
+            sell_b = max(sell_b, r.nb_slice_begin[nb_part]); sell_e = max(sell_b, min(sell_e, r.nb_slice_begin[nb_part + 1]));
+        }
         if (tid == 0) {                               // 1. stage yesterday's modes (TMA bulk copies)
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_expect_tx(s_bar, r.hot_words * 4u);
-            for (uint32_t k = 0; k < r.n_ranges; ++k) {
-                const StageRange g = r.ranges[k];
+            const uint32_t n_stage = r.local_mode ? 2u : r.n_ranges;
+            uint32_t words = r.hot_words;
+            if (r.local_mode) words = r.ranges[0].n_words + r.ranges[1 + nb_part].n_words;
+            mbar_expect_tx(s_bar, words * 4u);
+            for (uint32_t k = 0; k < n_stage; ++k) {
+                const StageRange g = r.ranges[r.local_mode && k ? 1 + nb_part : k];
                 for (uint32_t o = 0; o < g.n_words; o += 16384) {          // <= 64 KB per copy
                     const uint32_t n = min(g.n_words - o, 16384u);
                     bulk_g2s(s_vec + g.dst_word + o, g_vec + g.src_word + o, n * 4u, s_bar);
@@ -394,8 +406,8 @@ day_kernel(const __grid_constant__ RepArray reps, uint32_t R, uint32_t P, uint32
         // records and pulls the first one's link codes and agent state into L2; likewise the first hub unit of the warp.
         const uint32_t n_own_hub = r.hub_end - r.hub_begin;
         const uint32_t n_my_hub_slices = n_own_hub > p ? (n_own_hub - p + P - 1) / P : 0;
-        const uint32_t n_sell = r.sell_end - r.sell_begin;
-        const uint32_t n_my_sell = n_sell > p ? (n_sell - p + P - 1) / P : 0;
+        const uint32_t n_sell = sell_e - sell_b;
+        const uint32_t n_my_sell = n_sell > q ? (n_sell - q + Q - 1) / Q : 0;
         const uint32_t n_items = n_my_hub_slices + n_my_sell;
         // Items are claimed in groups of G consecutive ones (one shared-memory atomic and one shuffle per group: the
         // claim sits on the critical path of every slice it is made for).  G is a compile-time constant (a run-time
@@ -411,11 +423,11 @@ day_kernel(const __grid_constant__ RepArray reps, uint32_t R, uint32_t P, uint32
         };
         auto meta_of = [&](uint32_t item) -> uint4 {   // SELL items only; zero for hub items / past the end
             if (item < n_my_hub_slices || item >= n_items) return make_uint4(0, 0, 0, 0);
-            return ld_stream_v4(r.sell_meta + (r.sell_begin + p + (uint64_t)P * (item - n_my_hub_slices)));
+            return ld_stream_v4(r.sell_meta + (sell_b + q + (uint64_t)Q * (item - n_my_hub_slices)));
         };
         auto prefetch_item = [&](uint32_t item, const uint4& m) {
             if (item >= n_items || item < n_my_hub_slices) return;
-            const uint32_t s1 = r.sell_begin + p + P * (item - n_my_hub_slices);
+            const uint32_t s1 = sell_b + q + Q * (item - n_my_hub_slices);
             const uint32_t nrow = (m.z & 0xFFFFu) + (m.z >> 16);
             if (lane == 0 && nrow) prefetch_l2(r.sell_codes + (((uint64_t)m.y << 32) | m.x), nrow * 128u);
             if (lane == 1) prefetch_l2(r.state + (size_t)(r.n_hub_slices + s1) * kRecWords, kRecWords * 4u);
@@ -506,7 +518,7 @@ day_kernel(const __grid_constant__ RepArray reps, uint32_t R, uint32_t P, uint32
                 finish_slice<PER_AGENT>(r, hs, lane, false, hcs, ad.x + ad.z, hcn, ad.y + ad.w, stat, __uint_as_float(rec[kRecWs + lane]),
                                         reinterpret_cast<const float4*>(rec + kRecHabit)[lane], last, uw, s_cong, s_cost, s_crank, s_des, s_rec, weather, changed, parity, st);
             } else {
-            const uint32_t s = r.sell_begin + p + P * (it0 - n_my_hub_slices);
+            const uint32_t s = sell_b + q + Q * (it0 - n_my_hub_slices);
             const uint32_t slice = r.n_hub_slices + s;
             const uint32_t KK = meta.z;
             const uint32_t* blk = r.sell_codes + (((uint64_t)meta.y << 32) | meta.x);

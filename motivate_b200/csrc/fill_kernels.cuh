@@ -21,7 +21,17 @@ struct FillArgs {
     const uint4* sell_meta; uint32_t* sell_codes; uint32_t* deg;
     const uint64_t* hub_off; const uint4* hub_deg; uint32_t* hub_codes;
     uint32_t own_hub_begin, own_hub_end, own_sell_begin, own_sell_end;   // slices whose codes this handle stores (all, unless agent-partitioned)
+    const uint32_t* tcold;                               // LOCAL layout: [N] cold code of a target (nullptr: GLOBAL layout)
+    const uint8_t* cls;                                  // [N] 0 never staged, 1 staged for every block, 2 for blocks of its own neighbourhood
+    const uint16_t* nbhd;                                // [N] caller's neighbourhood array
 };
+// Code of the link src -> t (| 1 if hot).  LOCAL layout: a target staged with its neighbourhood's prefix is hot only for
+// sources of that neighbourhood that are not hubs (hub slices mix neighbourhoods); everybody else reads it from L2.
+__device__ __forceinline__ uint32_t link_code(const FillArgs& a, uint32_t src_nbhd, bool src_is_hub, uint32_t t) {
+    uint32_t c = a.tcode[t];
+    if (a.tcold && (c & 1u) && a.cls[t] == 2 && (src_is_hub || a.nbhd[t] != src_nbhd)) c = a.tcold[t];
+    return c;
+}
 
 __global__ void fill_u32_kernel(uint32_t* __restrict__ p, uint64_t n, uint32_t v) {
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = v;
@@ -32,19 +42,24 @@ __global__ void fill_u32_kernel(uint32_t* __restrict__ p, uint64_t n, uint32_t v
 // the CSR the fill kernels need anyway.  Also the range check of the link targets: any target >= N sets *bad.
 __global__ void count_hot_kernel(uint32_t N, const uint64_t* __restrict__ s_rowptr, const uint32_t* __restrict__ s_col,
                                  const uint64_t* __restrict__ n_rowptr, const uint32_t* __restrict__ n_col,
-                                 const uint8_t* __restrict__ is_hot, uint32_t* __restrict__ nsh, uint32_t* __restrict__ nnh,
-                                 uint32_t* __restrict__ bad) {
+                                 const uint8_t* __restrict__ is_hot, const uint16_t* __restrict__ nbhd, uint32_t* __restrict__ nsh,
+                                 uint32_t* __restrict__ nnh, uint32_t* __restrict__ bad) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < N; i += warps) {
         uint32_t a = 0, b = 0, oob = 0;
+        // class 1 = staged for every block; class 2 (LOCAL layout) = staged for the blocks of the target's own
+        // neighbourhood: hot for sources that live there and are not hubs (layout.h)
+        const uint32_t my_nb = nbhd[i];
+        const bool local_ok = (s_rowptr[i + 1] - s_rowptr[i]) + (n_rowptr[i + 1] - n_rowptr[i]) <= kHubDegree;
+        auto hot = [&](uint32_t t) -> uint32_t { const uint32_t c = is_hot[t]; return c == 1u || (c == 2u && local_ok && nbhd[t] == my_nb); };
         for (uint64_t x = s_rowptr[i] + lane; x < s_rowptr[i + 1]; x += 32) {
             const uint32_t t = s_col[x];
-            if (t < N) a += is_hot[t]; else oob = 1;
+            if (t < N) a += hot(t); else oob = 1;
         }
         for (uint64_t x = n_rowptr[i] + lane; x < n_rowptr[i + 1]; x += 32) {
             const uint32_t t = n_col[x];
-            if (t < N) b += is_hot[t]; else oob = 1;
+            if (t < N) b += hot(t); else oob = 1;
         }
         a = __reduce_add_sync(0xFFFFFFFFu, a);
         b = __reduce_add_sync(0xFFFFFFFFu, b);
@@ -56,12 +71,19 @@ __global__ void count_hot_kernel(uint32_t N, const uint64_t* __restrict__ s_rowp
 // Link code of every possible target (layout.h: word byte offset << 5 | shift, | 1 if hot): a hot agent is addressed
 // by its place in the staged vector (ranges), a cold one by its internal slot.  Same rule as layout_finish.
 __global__ void tcode_kernel(uint32_t N_pad, const uint32_t* __restrict__ int2ext, const StageRange* __restrict__ ranges,
-                             uint32_t n_ranges, const uint8_t* __restrict__ is_hot, uint32_t* __restrict__ tcode) {
+                             uint32_t n_ranges, const uint8_t* __restrict__ is_hot, const uint16_t* __restrict__ nbhd_local,
+                             uint32_t* __restrict__ tcode, uint32_t* __restrict__ tcold) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= N_pad) return;
     const uint32_t e = int2ext[t];
     if (e == kInvalid) return;
     uint32_t pos = t, hot = is_hot[e];
+    if (nbhd_local) {                                         // LOCAL layout: ranges[0] = hub region, ranges[1 + h] = prefix of neighbourhood h
+        tcold[e] = (t >> 4) << 7 | (30u - 2u * (t & 15u));
+        if (hot == 2u) { const StageRange r = ranges[1 + nbhd_local[e]]; pos = r.dst_word * 16u + (t - r.src_word * 16u); }
+        tcode[e] = ((pos >> 4) << 7 | (30u - 2u * (pos & 15u))) | (hot ? 1u : 0u);
+        return;
+    }
     if (hot) {
         uint32_t lo = 0, hi = n_ranges;                       // ranges are in increasing src_word order: last one starting at or before t
         while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (ranges[mid].src_word * 16u <= t) lo = mid; else hi = mid; }
@@ -92,13 +114,14 @@ __global__ void fill_sell_kernel(FillArgs a) {
     uint32_t* blk = a.sell_codes + (((uint64_t)meta.y << 32) | meta.x);
     const uint32_t K = meta.z & 0xFFFFu;
     uint32_t kh = 0, kc = 0;
+    const uint32_t my_nb = a.nbhd[e];
     for (uint64_t x = a.s_rowptr[e]; x < a.s_rowptr[e + 1]; ++x) {
-        const uint32_t c = a.tcode[a.s_col[x]];
+        const uint32_t c = link_code(a, my_nb, false, a.s_col[x]);
         if (c & 1u) put_hot(blk, K, lane, kh++, c & ~1u); else put_cold(blk, K, lane, kc++, c);
     }
     const uint32_t c_sh = kh, c_sc = kc;
     for (uint64_t x = a.n_rowptr[e]; x < a.n_rowptr[e + 1]; ++x) {
-        const uint32_t c = a.tcode[a.n_col[x]];
+        const uint32_t c = link_code(a, my_nb, false, a.n_col[x]);
         if (c & 1u) put_hot(blk, K, lane, kh++, c & ~1u); else put_cold(blk, K, lane, kc++, c);
     }
     a.deg[slot] = c_sh | (kh - c_sh) << 8 | c_sc << 16 | (kc - c_sc) << 24;
@@ -134,7 +157,7 @@ __global__ void fill_hub_kernel(FillArgs a, uint32_t n_hubs) {
             for (uint64_t x0 = b; x0 < end; x0 += 32) {
                 const uint64_t x = x0 + lane;
                 uint32_t c = 0; bool mine = false;
-                if (x < end) { c = a.tcode[cl[x]]; mine = ((c & 1u) != 0u) == (pass == 0); }
+                if (x < end) { c = link_code(a, 0u, true, cl[x]); mine = ((c & 1u) != 0u) == (pass == 0); }
                 const uint32_t m = __ballot_sync(0xFFFFFFFFu, mine);
                 if (mine) {
                     uint32_t i = pos + __popc(m & ((1u << lane) - 1u));
@@ -200,6 +223,25 @@ __global__ void set_ownership_kernel(const uint32_t* int2ext, uint32_t N_pad, co
     if (car)  w = (w & ~(1u << 26)) | ((car[e] ? 1u : 0u) << 26);
     if (bike) w = (w & ~(1u << 27)) | ((bike[e] ? 1u : 0u) << 27);
     state[rec_word(i, kRecStat)] = w;
+}
+
+// Agent-partitioned exchange (sim.cu launch_day): a rank's piece of the all-gather buffer is [M mode words | M norm
+// words] of its own slice range [b, e); after the all-gather the other ranks' pieces go back into the vectors.
+__global__ void pack_exchange_kernel(const uint2* __restrict__ vec, const uint2* __restrict__ normvec, uint32_t b, uint32_t e, uint32_t M,
+                                     uint2* __restrict__ send) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b + k < e) { send[k] = vec[b + k]; send[M + k] = normvec[b + k]; }
+}
+__global__ void unpack_exchange_kernel(const uint2* __restrict__ recv, const uint32_t* __restrict__ bounds, uint32_t world, uint32_t rank,
+                                       uint32_t M, uint32_t n_slices, uint2* __restrict__ vec, uint2* __restrict__ normvec) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_slices) return;
+    uint32_t r = 0;
+    while (r + 1 < world && bounds[r + 1] <= s) ++r;
+    if (r == rank) return;
+    const uint2* piece = recv + (size_t)r * 2 * M;
+    vec[s] = piece[s - bounds[r]];
+    normvec[s] = piece[M + (s - bounds[r])];
 }
 
 // `intervene` (simulation.rs:304-464) as ONE launch for every replica whose intervention falls on the day: the host

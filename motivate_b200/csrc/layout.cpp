@@ -2,6 +2,8 @@
 #include "layout.h"
 
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 #include <numeric>
 
 #include "mvb_internal.h"
@@ -24,6 +26,14 @@ void counting_sort_desc(std::vector<uint32_t>& v, size_t b, size_t e, uint32_t m
     std::copy(tmp.begin(), tmp.end(), v.begin() + b);
 }
 }  // namespace
+
+LayoutMode pick_layout_mode(uint32_t N_pad, uint32_t capacity_agents) {
+    if (const char* e = getenv("MVB_LAYOUT")) {
+        if (!strcmp(e, "local")) return N_pad > capacity_agents ? kLayoutLocal : kLayoutGlobal;   // (a population that fits is staged whole)
+        if (!strcmp(e, "global")) return kLayoutGlobal;
+    }
+    return (uint64_t)N_pad > (uint64_t)capacity_agents + capacity_agents / 2 ? kLayoutLocal : kLayoutGlobal;
+}
 
 int layout_begin(const mvb_population& pop, uint32_t H, uint32_t capacity_agents, GraphLayout& L, LayoutWork& W) {
     const uint32_t N = pop.n_agents;
@@ -99,7 +109,14 @@ int layout_begin(const mvb_population& pop, uint32_t H, uint32_t capacity_agents
     L.N_pad = (uint32_t)total;
     const bool all_hot = W.all_hot = L.N_pad <= capacity_agents;
     W.capacity_agents = capacity_agents;
-    if (all_hot) {
+    W.mode = L.mode = pick_layout_mode(L.N_pad, capacity_agents);
+    W.staged_hub_slots = all_hot ? hub_pad : std::min(hub_pad, capacity_agents);
+    if (W.mode == kLayoutLocal) {
+        // hubs get at most half of shared memory, the rest holds the prefix of the block's own neighbourhood
+        W.staged_hub_slots = std::min(hub_pad, capacity_agents / 2 / 64 * 64);
+        const uint32_t local = capacity_agents - W.staged_hub_slots;
+        for (uint32_t h = 0; h < H; ++h) take[h] = std::min((uint32_t)groups[h].size(), local);
+    } else if (all_hot) {
         for (uint32_t h = 0; h < H; ++h) take[h] = (uint32_t)groups[h].size();
     } else {
         // largest degree threshold theta such that {hubs} U {d >= theta} (rounded to 64 per group) fits
@@ -129,10 +146,10 @@ int layout_begin(const mvb_population& pop, uint32_t H, uint32_t capacity_agents
     }
     std::vector<uint8_t>& is_hot = W.is_hot;
     is_hot.assign(N, 0);
-    for (uint32_t k = 0; k < (all_hot ? hub_pad : std::min(hub_pad, capacity_agents)); ++k)     // hub slots that get staged
+    for (uint32_t k = 0; k < W.staged_hub_slots; ++k)     // hub slots that get staged
         if (hubs[k] != kInvalid) is_hot[hubs[k]] = 1;
     for (uint32_t h = 0; h < H; ++h)
-        for (uint32_t k = 0; k < take[h]; ++k) is_hot[groups[h][k]] = 1;
+        for (uint32_t k = 0; k < take[h]; ++k) is_hot[groups[h][k]] = W.mode == kLayoutLocal ? 2 : 1;
     return MVB_OK;
 }
 
@@ -142,8 +159,10 @@ void layout_count_hot(const mvb_population& pop, LayoutWork& W) {
     W.nnh_own.assign(N, 0);
     for (uint32_t i = 0; i < N; ++i) {
         uint32_t a = 0, b = 0;
-        for (uint64_t x = pop.social_rowptr[i]; x < pop.social_rowptr[i + 1]; ++x) a += W.is_hot[pop.social_col[x]];
-        for (uint64_t x = pop.neighbour_rowptr[i]; x < pop.neighbour_rowptr[i + 1]; ++x) b += W.is_hot[pop.neighbour_col[x]];
+        const bool local_ok = W.d[i] <= kHubDegree;            // LOCAL: a hub source only sees the staged hubs
+        auto hot = [&](uint32_t t) { const uint8_t c = W.is_hot[t]; return c == 1 || (c == 2 && local_ok && pop.neighbourhood[t] == pop.neighbourhood[i]); };
+        for (uint64_t x = pop.social_rowptr[i]; x < pop.social_rowptr[i + 1]; ++x) a += hot(pop.social_col[x]);
+        for (uint64_t x = pop.neighbour_rowptr[i]; x < pop.neighbour_rowptr[i + 1]; ++x) b += hot(pop.neighbour_col[x]);
         W.nsh_own[i] = a; W.nnh_own[i] = b;
     }
     W.nsh = W.nsh_own.data();
@@ -224,7 +243,20 @@ int layout_finish(const mvb_population& pop, LayoutWork& W, GraphLayout& L, bool
         L.ranges.push_back(StageRange{start / 16, count / 16, staged / 16, 0});
         staged += count;
     };
-    if (W.all_hot) {
+    L.nb_slice_begin.resize((size_t)H + 1);
+    for (uint32_t h = 0; h < H; ++h) L.nb_slice_begin[h] = (gstart[h] - hub_pad) / 32;
+    L.nb_slice_begin[H] = L.n_sell_slices;
+    if (W.mode == kLayoutLocal) {
+        // [0] the hub region; [1 + h] the prefix of neighbourhood h, every one of them placed right behind the hub region
+        L.ranges.push_back(StageRange{0, W.staged_hub_slots / 16, 0, 0});
+        uint32_t longest = 0;
+        for (uint32_t h = 0; h < H; ++h) {
+            const uint32_t words = (take[h] + 63) / 64 * 64 / 16;
+            L.ranges.push_back(StageRange{gstart[h] / 16, words, W.staged_hub_slots / 16, 0});
+            longest = std::max(longest, words);
+        }
+        staged = W.staged_hub_slots + longest * 16;
+    } else if (W.all_hot) {
         add_range(0, L.N_pad);
     } else {
         add_range(0, std::min(hub_pad, W.capacity_agents));
@@ -235,7 +267,17 @@ int layout_finish(const mvb_population& pop, LayoutWork& W, GraphLayout& L, bool
     // ---- link codes ---------------------------------------------------------------------------
     // code of every possible target; the arrays of codes are filled on the device (fill_kernels.cuh).  With
     // want_tcode == false the caller computes this table on the device as well (tcode_kernel, same rule).
-    if (want_tcode) {
+    if (want_tcode && W.mode == kLayoutLocal) {
+        L.tcode.resize(N); L.tcold.resize(N);
+        for (uint32_t t = 0; t < L.N_pad; ++t) {
+            const uint32_t e = L.int2ext[t];
+            if (e == kInvalid) continue;
+            L.tcold[e] = (t >> 4) << 7 | (30u - 2u * (t & 15u));
+            uint32_t pos = t;                                    // a staged hub sits at its own slot in the hub region
+            if (W.is_hot[e] == 2) pos = W.staged_hub_slots + (t - gstart[pop.neighbourhood[e]]);
+            L.tcode[e] = W.is_hot[e] ? (((pos >> 4) << 7 | (30u - 2u * (pos & 15u))) | 1u) : L.tcold[e];
+        }
+    } else if (want_tcode) {
         L.tcode.resize(N);
         for (const StageRange& r : L.ranges)
             for (uint32_t t = r.src_word * 16; t < (r.src_word + r.n_words) * 16; ++t) {

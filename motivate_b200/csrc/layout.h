@@ -81,6 +81,19 @@ __host__ __device__
 #endif
 inline size_t rec_habit_word(uint32_t slot) { return (size_t)(slot >> 5) * kRecWords + kRecHabit + 4u * (slot & 31u); }
 
+// Which part of yesterday's mode vector a block stages in shared memory:
+//   GLOBAL  one set for the whole population: all hubs + a degree-descending prefix of every neighbourhood group
+//           (everything, if the population fits).  Every block stages the same set; a part is any subset of slices.
+//   LOCAL   for populations far larger than shared memory: the neighbour network never leaves the neighbourhood
+//           (simulation.rs:165-173: two thirds of all links), so a block working on slices of neighbourhood h stages
+//           the hubs (a fixed region) + the degree-descending prefix of h ITSELF, as much as fits.  A link is hot if its
+//           target is a staged hub, or if source and target live in the same neighbourhood and the target is in that
+//           neighbourhood's prefix (hub SOURCES are handled in mixed slices and only get the first kind).  Parts are
+//           neighbourhood-pure.  With 8M agents in 10 neighbourhoods this turns 71 % of the links into shared-memory
+//           gathers where the global set reaches 34 %.
+enum LayoutMode : uint32_t { kLayoutGlobal = 0, kLayoutLocal = 1 };
+LayoutMode pick_layout_mode(uint32_t N_pad, uint32_t capacity_agents);      // MVB_LAYOUT=global|local overrides (tests)
+
 struct uint4x { uint32_t x, y, z, w; };   // host-side mirror of CUDA's uint4 (16 bytes)
 
 struct StageRange {                // one contiguous piece of the mode vector staged in shared memory
@@ -101,7 +114,12 @@ struct GraphLayout {
     std::vector<uint32_t> tcode;   // [N] link code of every possible target (caller's id) | 1 if the target is hot
                                    // (the low bit is free: the shift field of a code is even); input of the fill kernels.
                                    // Only filled by build_graph_layout: mvb_create* makes it on the device (tcode_kernel)
-    std::vector<StageRange> ranges;
+    std::vector<StageRange> ranges;   // GLOBAL: every range is staged by every block.  LOCAL: [0] = the hub region, [1 + h] = the
+                                      // prefix of neighbourhood h (a block stages [0] and the one of its neighbourhood)
+    uint32_t mode = kLayoutGlobal;
+    std::vector<uint32_t> nb_slice_begin;  // [H + 1] SELL slices of neighbourhood h: [nb_slice_begin[h], nb_slice_begin[h + 1])
+    std::vector<uint32_t> tcold;      // LOCAL, with tcode: the cold code of every target (a neighbourhood-prefix target is hot
+                                      // only for sources of its own neighbourhood)
     // hubs
     std::vector<uint64_t> hub_off;         // [n_hub_slices*32] offset of the hub's first block in hub_codes (u32 units)
     std::vector<uint32_t> hub_deg;         // [n_hub_slices*32][4] ds_hot, dn_hot, ds_cold, dn_cold
@@ -134,7 +152,8 @@ struct LayoutWork {                        // what layout_begin leaves for the l
     std::vector<uint32_t> take, gpad;      // per group: hot agents (a prefix), size rounded up to 64
     uint32_t hub_pad = 0, capacity_agents = 0;
     bool all_hot = false;
-    std::vector<uint8_t> is_hot;           // [N]
+    uint32_t mode = kLayoutGlobal, staged_hub_slots = 0;
+    std::vector<uint8_t> is_hot;           // [N] 0 = never staged, 1 = staged for every block, 2 = staged for blocks of its own neighbourhood (LOCAL)
     const uint32_t* nsh = nullptr;         // [N] social links with a hot target   (set by layout_count_hot, or by the
     const uint32_t* nnh = nullptr;         // [N] neighbour links with a hot target  caller from the device's counts)
     std::vector<uint32_t> nsh_own, nnh_own;

@@ -260,11 +260,11 @@ __global__ void place_hubs_kernel(uint32_t n_hubs, uint32_t n_hs, uint32_t stage
 }
 // first order (neighbourhood, degree desc, id asc), compact position q: hot if its rank in the group is below take[h]
 __global__ void mark_hot_kernel(uint32_t n2, const uint32_t* __restrict__ key1_sorted, const uint32_t* __restrict__ order1,
-                                const uint32_t* __restrict__ gofs, const uint32_t* __restrict__ take, uint8_t* __restrict__ is_hot) {
+                                const uint32_t* __restrict__ gofs, const uint32_t* __restrict__ take, uint32_t cls, uint8_t* __restrict__ is_hot) {
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n2) return;
     const uint32_t h = key1_sorted[q] >> 8;
-    is_hot[order1[q]] = (q - gofs[h]) < take[h];
+    is_hot[order1[q]] = (q - gofs[h]) < take[h] ? cls : 0;      // 1 = staged for every block, 2 = for blocks of its own neighbourhood (LOCAL)
 }
 // key of the second order: (group, hot part first, hot-list length desc); values keep the first order
 __global__ void key2_kernel(uint32_t n2, const uint32_t* __restrict__ key1_sorted, const uint32_t* __restrict__ order1,

@@ -80,7 +80,7 @@ struct Arena {
 // (scenario sweeps over one population pass the same graph + neighbourhood arrays).
 struct Graph {
     GraphLayout L;                 // host copy: permutation, sizes (code arrays are released after upload)
-    DevBuf deg, ranges, hub_off, hub_deg, hub_codes, hub_units, hub_unit_begin, sell_meta, sell_codes, int2ext;
+    DevBuf deg, ranges, hub_off, hub_deg, hub_codes, hub_units, hub_unit_begin, sell_meta, sell_codes, int2ext, nb_slice_begin;
     const void* key[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // caller pointers it was built from
 };
 
@@ -102,6 +102,7 @@ struct Nccl {
     ncclResult_t (*GroupEnd)() = nullptr;
     ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 Nccl* nccl() {
@@ -116,10 +117,10 @@ Nccl* nccl() {
         if (n.lib) {
 #define MVB_SYM(f) n.f = reinterpret_cast<decltype(n.f)>(dlsym(n.lib, "nccl" #f))
             MVB_SYM(GetUniqueId); MVB_SYM(CommInitRank); MVB_SYM(CommDestroy); MVB_SYM(GroupStart); MVB_SYM(GroupEnd);
-            MVB_SYM(Broadcast); MVB_SYM(AllReduce); MVB_SYM(GetErrorString);
+            MVB_SYM(Broadcast); MVB_SYM(AllReduce); MVB_SYM(AllGather); MVB_SYM(GetErrorString);
 #undef MVB_SYM
             if (!n.GetUniqueId || !n.CommInitRank || !n.CommDestroy || !n.GroupStart || !n.GroupEnd || !n.Broadcast ||
-                !n.AllReduce || !n.GetErrorString) n.lib = nullptr;
+                !n.AllReduce || !n.AllGather || !n.GetErrorString) n.lib = nullptr;
         }
     }
     return n.lib ? &n : nullptr;
@@ -166,6 +167,8 @@ struct mvb_sim {
     ncclComm_t comm = nullptr;
     std::vector<uint32_t> bounds;        // [world+1] global slice index where each rank's range starts
     uint32_t own[4] = {0, 0, 0, 0};      // this rank's hub slices [0],[1]) and SELL slices [2],[3])
+    DevBuf xchg, d_bounds;               // exchange buffer [world][2][xchg_words] u64 words (modes, norms); bounds on the device
+    uint32_t xchg_words = 0;             // longest rank range, in slices
     // interventions of the current run, staged before the day loop (apply_interventions_kernel)
     DevBuf d_ivreps;                     // IvRep[R]
     char* iv_pinned = nullptr;           // library-owned pinned staging: the caller's arrays are only borrowed for the call
@@ -224,7 +227,10 @@ uint32_t choose_parts(const mvb_sim* s, uint32_t first_rep, uint32_t R) {
     const double t_slice = 7.5, t_fixed = 10.0 + vec_bytes / 150e3;                    // microseconds (calibrated on B200)
     uint32_t best = 1;
     double best_t = 1e300;
-    for (uint32_t P = 1; P <= s->grid; ++P) {
+    // LOCAL layout (layout.h): parts are neighbourhood-pure, so P is a multiple of the number of neighbourhoods
+    const uint32_t step = s->h_reps[first_rep].local_mode ? s->h_reps[first_rep].H : 1u;
+    if (step > 1) best = step;
+    for (uint32_t P = step; P <= std::max(s->grid, step) * (step > 1 ? 4u : 1u); P += step) {
         const double rounds = std::ceil((double)R * P / s->grid);
         const double t = rounds * (t_fixed + (slices / P / 32.0 + 0.5) * t_slice);        // + half a round: the ragged end
         if (t < best_t * 0.999) { best_t = t; best = P; }
@@ -257,21 +263,24 @@ int launch_day(mvb_sim* s, uint8_t weather, uint8_t changed) {
     }
 #undef MVB_LAUNCH
     if (s->world > 1) {
-        // agent-partitioned: every rank now holds new modes / norms for its own slices and a partial record.
-        // One NCCL group: each rank broadcasts the packed words of its slice range, the record is all-reduced.
+        // agent-partitioned: every rank now holds new modes / norms for its own slices and a partial record.  The
+        // social network is global (simulation.rs:160), so tomorrow every rank needs everybody's modes: ONE all-gather
+        // of the packed 2-bit words (each rank's piece: its mode words, then its norm words, padded to the longest
+        // range) and ONE all-reduce of the day's counters.
         Replica& rp = s->reps[0];
         Nccl* n = nccl();
         uint2* vec_next = rp.vec[s->parity ^ 1u].as<uint2>();
         uint2* normvec = rp.normvec.as<uint2>();
-        MVB_NCCL(n->GroupStart());
-        for (uint32_t r = 0; r < s->world; ++r) {
-            const size_t b = s->bounds[r], cnt = (size_t)s->bounds[r + 1] - b;
-            if (!cnt) continue;
-            MVB_NCCL(n->Broadcast(vec_next + b, vec_next + b, cnt * 8, ncclUint8, (int)r, s->comm, s->stream));
-            MVB_NCCL(n->Broadcast(normvec + b, normvec + b, cnt * 8, ncclUint8, (int)r, s->comm, s->stream));
-        }
+        const uint32_t M = s->xchg_words;
+        uint2* send = s->xchg.as<uint2>() + (size_t)s->rank * 2 * M;
+        const uint32_t n_slices = s->bounds[s->world];
+        pack_exchange_kernel<<<(s->bounds[s->rank + 1] - s->bounds[s->rank] + 255) / 256, 256, 0, s->stream>>>(
+            vec_next, normvec, s->bounds[s->rank], s->bounds[s->rank + 1], M, send);
+        MVB_NCCL(n->AllGather(send, s->xchg.p, (size_t)2 * M * sizeof(uint2), ncclUint8, s->comm, s->stream));      // in place
+        unpack_exchange_kernel<<<(n_slices + 255) / 256, 256, 0, s->stream>>>(s->xchg.as<uint2>(), s->d_bounds.as<uint32_t>(), s->world, s->rank, M,
+                                                                            n_slices, vec_next, normvec);
+        MVB_CUDA(cudaGetLastError());
         MVB_NCCL(n->AllReduce(next, next, s->rec_stride, ncclUint32, ncclSum, s->comm, s->stream));
-        MVB_NCCL(n->GroupEnd());
     }
     s->cursor++;
     s->parity ^= 1u;

@@ -59,34 +59,60 @@ int main(int argc, char** argv) {
         if (nb != kInvalid) { CHECK(nb >= last_nb, "neighbourhood order"); last_nb = nb; }
     }
 
-    // ---- staged ranges: disjoint, increasing, inside the capacity; "hot" = inside a range
-    std::vector<uint8_t> hot_slot(L.N_pad, 0);
-    uint32_t staged = 0, prev_end = 0;
-    for (const StageRange& r : L.ranges) {
-        CHECK(r.n_words % 4 == 0 && r.dst_word == staged && r.src_word >= prev_end, "range geometry");
-        for (uint32_t t = r.src_word * 16; t < (r.src_word + r.n_words) * 16; ++t) { CHECK(t < L.N_pad, "range end"); hot_slot[t] = 1; }
-        staged += r.n_words; prev_end = r.src_word + r.n_words;
+    // ---- staged ranges.  GLOBAL: disjoint, increasing, inside the capacity; "hot" = inside a range.
+    // LOCAL: [0] = the hub region, [1 + h] = the prefix of neighbourhood h placed right behind it; a block stages [0] and one of the others.
+    std::vector<uint8_t> hot_slot(L.N_pad, 0);            // 1 = staged for every block, 2 = for blocks of its own neighbourhood
+    const bool local = L.mode == kLayoutLocal;
+    if (local) {
+        CHECK(L.ranges.size() == (size_t)H + 1 && L.ranges[0].src_word == 0 && L.ranges[0].dst_word == 0, "local ranges");
+        CHECK(L.ranges[0].n_words * 16 <= L.n_hub_slices * 32, "hub region");
+        uint32_t longest = 0;
+        for (uint32_t t = 0; t < L.ranges[0].n_words * 16; ++t) hot_slot[t] = 1;
+        for (uint32_t h = 0; h < H; ++h) {
+            const StageRange& r = L.ranges[1 + h];
+            CHECK(r.n_words % 4 == 0 && r.dst_word == L.ranges[0].n_words, "local range geometry");
+            CHECK(((uint64_t)L.ranges[0].n_words + r.n_words) * 16 <= cap, "neighbourhood %u stages more than fits", h);
+            CHECK(r.src_word * 16 >= L.n_hub_slices * 32 && (r.src_word * 16 - L.n_hub_slices * 32) / 32 == L.nb_slice_begin[h], "local range start");
+            for (uint32_t t = r.src_word * 16; t < (r.src_word + r.n_words) * 16; ++t) {
+                CHECK(t < L.N_pad && (t - L.n_hub_slices * 32) / 32 < L.nb_slice_begin[h + 1], "local range end");
+                if (L.int2ext[t] != kInvalid) hot_slot[t] = 2;
+            }
+            longest = std::max(longest, r.n_words);
+        }
+        CHECK(L.hot_words == L.ranges[0].n_words + longest, "hot_words");
+    } else {
+        uint32_t staged = 0, prev_end = 0;
+        for (const StageRange& r : L.ranges) {
+            CHECK(r.n_words % 4 == 0 && r.dst_word == staged && r.src_word >= prev_end, "range geometry");
+            for (uint32_t t = r.src_word * 16; t < (r.src_word + r.n_words) * 16; ++t) { CHECK(t < L.N_pad, "range end"); hot_slot[t] = 1; }
+            staged += r.n_words; prev_end = r.src_word + r.n_words;
+        }
+        CHECK(staged == L.hot_words && (uint64_t)staged * 16 <= cap, "staged %u words for a capacity of %u agents", staged, cap);
+        if (L.N_pad <= cap) CHECK((uint64_t)staged * 16 == L.N_pad, "everything fits but not everything is staged");
     }
-    CHECK(staged == L.hot_words && (uint64_t)staged * 16 <= cap, "staged %u words for a capacity of %u agents", staged, cap);
-    if (L.N_pad <= cap) CHECK((uint64_t)staged * 16 == L.N_pad, "everything fits but not everything is staged");
+    CHECK(L.nb_slice_begin.size() == (size_t)H + 1 && L.nb_slice_begin[H] == L.n_sell_slices, "nb_slice_begin");
 
     // ---- link codes of the targets (host table; mvb_create* computes the same on the device)
-    CHECK(L.tcode.size() == N, "tcode");
+    CHECK(L.tcode.size() == N && (!local || L.tcold.size() == N), "tcode");
     uint32_t n_hot = 0;
     for (uint32_t e = 0; e < N; ++e) {
         const uint32_t c = L.tcode[e], hot = c & 1u, word = c >> 7, shift = c & 0x1Eu, s = slot_of[e];
-        CHECK(hot == hot_slot[s], "hot flag of agent %u", e);
+        CHECK(hot == (hot_slot[s] != 0), "hot flag of agent %u", e);
         n_hot += hot;
         uint32_t pos = s;
-        if (hot) for (const StageRange& r : L.ranges) if (s >= r.src_word * 16 && s < (r.src_word + r.n_words) * 16) pos = r.dst_word * 16 + (s - r.src_word * 16);
+        if (hot && !local) for (const StageRange& r : L.ranges) if (s >= r.src_word * 16 && s < (r.src_word + r.n_words) * 16) pos = r.dst_word * 16 + (s - r.src_word * 16);
+        if (hot_slot[s] == 2) { const StageRange& r = L.ranges[1 + pop.neighbourhood[e]]; pos = r.dst_word * 16 + (s - r.src_word * 16); }
         CHECK(word == pos / 16 && shift == 30 - 2 * (pos % 16), "code of agent %u: word %u shift %u for position %u", e, word, shift, pos);
+        if (local) CHECK(L.tcold[e] == ((s >> 4) << 7 | (30u - 2u * (s & 15u))), "cold code of agent %u", e);
     }
 
     // ---- SELL slices: K / Kc are the longest hot / cold list of the slice, offsets are the running sum
     std::vector<uint32_t> n_hot_links(N, 0);
     for (uint32_t e = 0; e < N; ++e) {
-        for (uint64_t x = pop.social_rowptr[e]; x < pop.social_rowptr[e + 1]; ++x) n_hot_links[e] += L.tcode[pop.social_col[x]] & 1u;
-        for (uint64_t x = pop.neighbour_rowptr[e]; x < pop.neighbour_rowptr[e + 1]; ++x) n_hot_links[e] += L.tcode[pop.neighbour_col[x]] & 1u;
+        // a link is hot if its target is staged for every block, or for the blocks of the source's own neighbourhood (not for hub sources)
+        auto hot = [&](uint32_t t) { const uint8_t k = hot_slot[slot_of[t]]; return k == 1 || (k == 2 && deg(e) <= kHubDegree && pop.neighbourhood[t] == pop.neighbourhood[e]); };
+        for (uint64_t x = pop.social_rowptr[e]; x < pop.social_rowptr[e + 1]; ++x) n_hot_links[e] += hot(pop.social_col[x]);
+        for (uint64_t x = pop.neighbour_rowptr[e]; x < pop.neighbour_rowptr[e + 1]; ++x) n_hot_links[e] += hot(pop.neighbour_col[x]);
     }
     uint64_t off = 0, rows = 0, links = 0;
     for (uint32_t s = 0; s < L.n_sell_slices; ++s) {
@@ -145,7 +171,10 @@ int main(int argc, char** argv) {
         CHECK(b.size() == world + 1 && b[0] == 0 && b[world] == L.n_hub_slices + L.n_sell_slices, "bounds");
         for (uint32_t r = 0; r < world; ++r) CHECK(b[r] <= b[r + 1], "bounds order");
     }
-    printf("ok N_pad %u hubs %u hot %u ranges %zu sell_padding %.3f hub_slice_balance %.2f\n", L.N_pad, n_hubs, n_hot, L.ranges.size(), padding, hub_balance);
+    uint64_t all_links = 0, hot_links = 0;
+    for (uint32_t e = 0; e < N; ++e) { all_links += deg(e); hot_links += n_hot_links[e]; }
+    printf("ok N_pad %u hubs %u hot %u ranges %zu sell_padding %.3f hub_slice_balance %.2f mode %s hot_link_share %.3f\n", L.N_pad, n_hubs, n_hot, L.ranges.size(), padding, hub_balance,
+           local ? "local" : "global", all_links ? (double)hot_links / (double)all_links : 1.0);
     mvb_synth_destroy(syn);
     return 0;
 }

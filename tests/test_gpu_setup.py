@@ -26,8 +26,13 @@ def compare_with_host(sim, pop, r=0):
 
 @pytest.fixture
 def stage_env():
-    yield lambda v: os.environ.__setitem__("MVB_STAGE_AGENTS", str(v))
+    def set_env(v, layout=None):
+        os.environ["MVB_STAGE_AGENTS"] = str(v)
+        if layout:
+            os.environ["MVB_LAYOUT"] = layout
+    yield set_env
     os.environ.pop("MVB_STAGE_AGENTS", None)
+    os.environ.pop("MVB_LAYOUT", None)
 
 
 # (agents, subcultures, neighbourhoods, staged agents or None = what the GPU's shared memory holds, seed)
@@ -60,10 +65,22 @@ def test_batch_with_shared_graph_layouts(stage_env):
             compare_with_host(sim, pops[r], r)
 
 
+@pytest.mark.parametrize("n,s,h,stage,seed", [(40000, 4, 10, 8192, 2), (200000, 4, 10, 64000, 4), (5000, 1, 1, 64, 5), (30000, 3, 40, 4096, 7)])
+def test_device_layout_equals_host_layout_local_mode(stage_env, n, s, h, stage, seed):
+    """LOCAL staging (layout.h): hub region + the prefix of the block's own neighbourhood."""
+    stage_env(stage, "local")
+    pop = mb.synth_population(n, s, h, 5, 10, seed=seed)
+    tab = mb.synth_tables(s, h, n, seed=seed)
+    with mb.Simulation(pop, tab, mb.make_params()) as sim:
+        compare_with_host(sim, pop)
+
+
+@pytest.mark.parametrize("layout", ["global", "local"])
 @pytest.mark.parametrize("stage", [64, 1024, 6400])
-def test_partly_staged_small_population_equals_oracle(stage_env, stage):
-    """Cold lists (targets gathered from L2 instead of shared memory), hubs that are not staged: every day, full state."""
-    stage_env(stage)
+def test_partly_staged_small_population_equals_oracle(stage_env, stage, layout):
+    """Cold lists (targets gathered from L2 instead of shared memory), hubs that are not staged, both staging layouts:
+    every day, full state."""
+    stage_env(stage, layout)
     n = 12000
     pop = mb.synth_population(n, 4, 6, 5, 10, seed=stage)
     tab = mb.synth_tables(4, 6, n, seed=stage)

@@ -33,12 +33,19 @@ def checker(tmp_path_factory):
     (200000, 4, 10, 64000, 4),        # hubs + partial hot set
     (5000, 1, 1, 64, 5),              # smallest capacity the builder accepts: more hubs than fit
 ])
-def test_layout_invariants(checker, n, s, h, cap, seed):
-    out = subprocess.run([checker, str(n), str(s), str(h), str(cap), str(seed)], capture_output=True, text=True)
+@pytest.mark.parametrize("mode", ["global", "local"])
+def test_layout_invariants(checker, n, s, h, cap, seed, mode):
+    out = subprocess.run([checker, str(n), str(s), str(h), str(cap), str(seed)], capture_output=True, text=True,
+                         env=dict(os.environ, MVB_LAYOUT=mode))
     assert out.returncode == 0 and out.stdout.startswith("ok "), out.stdout + out.stderr
     fields = out.stdout.split()
+    assert fields[fields.index("mode") + 1] == (mode if n > cap else "global")       # a population that fits is staged whole
     padding = float(fields[fields.index("sell_padding") + 1])
     if n // h >= 2000:                                # (tiny neighbourhoods are mostly the ragged last slice)
         assert padding < 1.25, out.stdout             # degree / hot-length sorted slices keep the padding small
+    if (n, h, cap) == (40000, 10, 8192):
+        # staging the block's own neighbourhood makes far more links shared-memory gathers than one global set does
+        share = float(fields[fields.index("hot_link_share") + 1])
+        assert share > 0.6 if mode == "local" else share < 0.5, out.stdout
     balance = float(fields[fields.index("hub_slice_balance") + 1])
     assert balance < 2.0, out.stdout                  # hubs are dealt round the hub slices

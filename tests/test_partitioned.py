@@ -59,11 +59,20 @@ def gloo_worker(rank, world, port, out):
             continue
         o.step(w[day], prev != w[day]); prev = w[day]
         st = o.get_state()
-        # exchange: own modes / norms to everyone (allgather), counters summed (allreduce) — what NCCL does on the GPUs
-        mode = torch.from_numpy(np.where(mine, st["current_mode"], 0).astype(np.int32))
-        norm = torch.from_numpy(np.where(mine, st["norm"], 0).astype(np.int32))
-        dist.all_reduce(mode); dist.all_reduce(norm)
-        assert np.array_equal(mode.numpy(), st["current_mode"]) and np.array_equal(norm.numpy(), st["norm"])
+        # exchange, as launch_day does it on the GPUs: every rank packs its own piece [modes | norms] padded to the longest
+        # piece, ONE all-gather, every rank unpacks the others' pieces; then the counters are summed (all-reduce)
+        ids = [np.flatnonzero(owner == r) for r in range(world)]
+        M = max(len(x) for x in ids)
+        piece = np.zeros(2 * M, np.uint8)
+        piece[:len(ids[rank])] = st["current_mode"][ids[rank]]
+        piece[M:M + len(ids[rank])] = st["norm"][ids[rank]]
+        got = [torch.zeros(2 * M, dtype=torch.uint8) for _ in range(world)]
+        dist.all_gather(got, torch.from_numpy(piece))
+        mode, norm = np.zeros(N, np.uint8), np.zeros(N, np.uint8)
+        for r in range(world):
+            g = got[r].numpy()
+            mode[ids[r]] = g[:len(ids[r])]; norm[ids[r]] = g[M:M + len(ids[r])]
+        assert np.array_equal(mode, st["current_mode"]) and np.array_equal(norm, st["norm"])
         part = np.zeros(7 + S + H, np.int64)
         a, an = st["current_mode"] >= 2, st["norm"] >= 2
         for i in np.flatnonzero(mine):
