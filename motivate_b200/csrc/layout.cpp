@@ -32,7 +32,9 @@ LayoutMode pick_layout_mode(uint32_t N_pad, uint32_t capacity_agents) {
         if (!strcmp(e, "local")) return N_pad > capacity_agents ? kLayoutLocal : kLayoutGlobal;   // (a population that fits is staged whole)
         if (!strcmp(e, "global")) return kLayoutGlobal;
     }
-    return (uint64_t)N_pad > (uint64_t)capacity_agents + capacity_agents / 2 ? kLayoutLocal : kLayoutGlobal;
+    // measured on B200 (S=4, H=10, BA 5+10): GLOBAL wins up to ~2.5M agents (at 2M: 29.7 % vs 24.6 % of the HBM roofline),
+    // LOCAL beyond (3M: 25.8 vs 23.4; 8M: 27.3 vs 16.6; 50M in 64 neighbourhoods: 24.4 vs 12.8)
+    return (uint64_t)N_pad * 4 > (uint64_t)capacity_agents * 11 ? kLayoutLocal : kLayoutGlobal;
 }
 
 int layout_begin(const mvb_population& pop, uint32_t H, uint32_t capacity_agents, GraphLayout& L, LayoutWork& W) {
