@@ -493,7 +493,8 @@ def leg_c4(args, rank, local_rank, world, torch, dist, mb, peak):
                 np.array_equal(a["habit"][owner_mask].view(np.uint32), b["habit"][owner_mask].view(np.uint32)))
 
     out = {}
-    # 1. against the CPU oracle: 20k agents, 6 weeks, an intervention on a Sunday
+    # 1. against the CPU oracle: 20k agents, 6 weeks, an intervention on a Sunday; once staged whole (GLOBAL layout) and once
+    #    with a small staged set in the LOCAL layout (hub region + own neighbourhood prefix: the large-population path)
     n = 20_000
     d = mb.DevicePopulation(n, 4, 10, 5, 10, seed=11, device=local_rank)
     p = d.to_host()
@@ -501,15 +502,21 @@ def leg_c4(args, rank, local_rank, world, torch, dist, mb, peak):
     w = mb.weather_pattern(43, seed=11)
     tab2 = tab.copy(); tab2.capacity[:, 0] //= 2; tab2.supportiveness[::2, 2:] += np.float32(0.1)
     iv = mb.InterventionData(day=20, tables=tab2, owns_car=1 - p["owns_car"], owns_bike=None)
-    sim = mb.Simulation.partitioned(d, tab, prm, device=local_rank, rank=rank, world=world, unique_id=uid())
-    days, rows = sim.run(w, interventions=iv)
-    st = sim.get_state(0)
-    mine = sim.partition_owner() == rank
-    sim.close()
     o = OracleSimulation(p, tab, prm)
     d2, r2 = o.run(w, intervention=iv)
-    ok = np.array_equal(days, d2) and np.array_equal(rows[0], r2) and same_state(st, o.get_state(), mine)
-    out["partitioned_parity_vs_oracle"] = {"agents": n, "weekdays": len(days) - 1, "world": world,
+    so = o.get_state()
+    ok = True
+    for env in ({}, {"MVB_LAYOUT": "local", "MVB_STAGE_AGENTS": "2048"}):
+        os.environ.update(env)
+        sim = mb.Simulation.partitioned(d, tab, prm, device=local_rank, rank=rank, world=world, unique_id=uid())
+        for k in env:
+            os.environ.pop(k)
+        days, rows = sim.run(w, interventions=iv)
+        st = sim.get_state(0)
+        mine = sim.partition_owner() == rank
+        sim.close()
+        ok = ok and np.array_equal(days, d2) and np.array_equal(rows[0], r2) and same_state(st, so, mine)
+    out["partitioned_parity_vs_oracle"] = {"agents": n, "weekdays": len(days) - 1, "world": world, "layouts": ["global", "local"],
                                             "result": "bit-exact" if all_ok(ok) else "MISMATCH",
                                             "compared": "statistics rows, every agent's mode and norm, habit bits of the agents each rank owns"}
     d.close()
@@ -537,36 +544,41 @@ def leg_c4(args, rank, local_rank, world, torch, dist, mb, peak):
                                  out["partitioned_parity_vs_one_gpu"]["result"] == "bit-exact" else "MISMATCH")
     d.close()
     del st, s1
-    # 3. the timed run
+    # 3. the timed runs: H = 10 neighbourhoods (the shape of C2, as in round 1: a neighbourhood of 5M agents is 5x what shared
+    #    memory holds) and H = 64 (781k agents per neighbourhood at 50M: every neighbour link is a shared-memory gather)
     n = 50_000_000 if world == 8 else 6_000_000 * world
-    d = mb.DevicePopulation(n, 4, 10, 5, 10, seed=0, device=local_rank)
-    tab = mb.synth_tables(4, 10, n, seed=0)
     n_days = weekdays_calendar(args.warmup + args.steps)
     w = mb.weather_pattern(n_days, seed=0)
     warm_end = weekdays_calendar(args.warmup)
-    t0 = time.perf_counter()
-    sim = mb.Simulation.partitioned(d, tab, prm, device=local_rank, rank=rank, world=world, unique_id=uid())
-    t_create = time.perf_counter() - t0
-    alg = sim.algorithmic_bytes_per_day(0)
-    sim.run_async(w, 0, warm_end); sim.sync()
-    dist.barrier(); torch.cuda.synchronize()
-    sim.run_async(w, warm_end, n_days); sim.sync()
-    torch.cuda.synchronize(); dist.barrier()
-    ms, launches = sim.last_run_stats()
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    per_rank = [torch.zeros_like(t) for _ in range(world)]
-    dist.all_gather(per_rank, t)
-    max_ms = max(float(x.item()) for x in per_rank)
-    mem = torch.cuda.memory_allocated(dev)            # (torch's own; the library's memory is outside torch's allocator)
-    free_b, total_b = torch.cuda.mem_get_info(dev)
-    sim.close(); d.close()
-    out.update({
-        "workload": f"C4: ONE population of {n} agents (S=4, H=10, BA links 5+10) agent-partitioned over {world} B200; per weekday one NCCL "
-                    "all-gather of the packed 2-bit modes + norms and one all-reduce of the counters",
-        "agents": n, "agent_days_per_sec": n * args.steps / (max_ms * 1e-3), "weekdays": args.steps, "ms_per_weekday": max_ms / args.steps,
-        "ms_per_weekday_by_rank": [float(x.item()) / args.steps for x in per_rank],
-        "roofline_frac_per_gpu": alg * args.steps / (max_ms * 1e-3) / 1e9 / world / peak,
-        "create_seconds_rank0": t_create, "device_memory_in_use_gb_rank0": (total_b - free_b) / 1e9})
+
+    def timed(H):
+        d = mb.DevicePopulation(n, 4, H, 5, 10, seed=0, device=local_rank)
+        tab = mb.synth_tables(4, H, n, seed=0)
+        t0 = time.perf_counter()
+        sim = mb.Simulation.partitioned(d, tab, prm, device=local_rank, rank=rank, world=world, unique_id=uid())
+        t_create = time.perf_counter() - t0
+        alg = sim.algorithmic_bytes_per_day(0)
+        sim.run_async(w, 0, warm_end); sim.sync()
+        dist.barrier(); torch.cuda.synchronize()
+        sim.run_async(w, warm_end, n_days); sim.sync()
+        torch.cuda.synchronize(); dist.barrier()
+        ms, launches = sim.last_run_stats()
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        per_rank = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(per_rank, t)
+        max_ms = max(float(x.item()) for x in per_rank)
+        free_b, total_b = torch.cuda.mem_get_info(dev)
+        sim.close(); d.close()
+        return {"neighbourhoods": H, "agent_days_per_sec": n * args.steps / (max_ms * 1e-3), "weekdays": args.steps,
+                "ms_per_weekday": max_ms / args.steps, "ms_per_weekday_by_rank": [float(x.item()) / args.steps for x in per_rank],
+                "roofline_frac_per_gpu": alg * args.steps / (max_ms * 1e-3) / 1e9 / world / peak,
+                "create_seconds_rank0": t_create, "device_memory_in_use_gb_rank0": (total_b - free_b) / 1e9}
+
+    out["workload"] = (f"C4: ONE population of {n} agents (S=4, BA links 5+10) agent-partitioned over {world} B200; per weekday one NCCL "
+                       "all-gather of the packed 2-bit modes + norms and one all-reduce of the counters; populations generated on the GPUs")
+    out["agents"] = n
+    out.update(timed(10))
+    out["h64"] = timed(64)
     return out
 
 

@@ -637,6 +637,61 @@ static int create_impl(uint32_t R, const mvb_population* const* pops, const mvb_
         MVB_CUDA(s->d_bounds.alloc(4 * ((size_t)world + 1)));
         MVB_CUDA(cudaMemcpyAsync(s->d_bounds.p, s->bounds.data(), 4 * ((size_t)world + 1), cudaMemcpyHostToDevice, S));
     }
+    // LOCAL layout: the parts of a launch are neighbourhood-pure.  Every neighbourhood gets a share of the T parts per
+    // replica in proportion to the slices of it this rank updates (all of them unless agent-partitioned), so that parts
+    // cost about the same; T = a few rounds of the grid, enough slices per warp to amortise a part's staging.
+    {
+        const uint32_t n_pieces = (R + kMaxRepsPerLaunch - 1) / kMaxRepsPerLaunch;
+        s->local_P.assign(n_pieces, 0);
+        std::vector<uint4x> tables;
+        std::vector<size_t> table_at(R, 0);
+        for (uint32_t c = 0; c < n_pieces; ++c) {
+            const uint32_t r0 = c * kMaxRepsPerLaunch, r1 = std::min(R, r0 + kMaxRepsPerLaunch);
+            if (!s->h_reps[r0].local_mode) continue;
+            for (uint32_t r = r0; r < r1; ++r)
+                if (!s->h_reps[r].local_mode) { set_error("internal: replicas of one launch use different staging layouts"); return MVB_ERR_STATE; }
+            const RepDev& d0 = s->h_reps[r0];
+            const uint32_t own0 = d0.sell_end - d0.sell_begin;
+            uint32_t rounds = std::max<uint32_t>(1, std::min<uint32_t>(8, (uint32_t)((uint64_t)own0 * (r1 - r0) / ((uint64_t)s->grid * 32 * 8))));
+            uint32_t T = std::max<uint32_t>(d0.H, rounds * s->grid / (r1 - r0));
+            s->local_P[c] = T;
+            for (uint32_t r = r0; r < r1; ++r) {
+                const RepDev& d = s->h_reps[r];
+                const std::vector<uint32_t>& nb = s->reps[r].graph->L.nb_slice_begin;
+                std::vector<uint32_t> n_h(d.H), Q(d.H, 0);
+                uint64_t total = 0;
+                for (uint32_t h = 0; h < d.H; ++h) {
+                    const uint32_t b = std::max(nb[h], d.sell_begin), e = std::min(nb[h + 1], d.sell_end);
+                    n_h[h] = e > b ? e - b : 0; total += n_h[h];
+                }
+                uint32_t used = 0;
+                for (uint32_t h = 0; h < d.H; ++h)
+                    if (n_h[h]) { Q[h] = std::max<uint32_t>(1, (uint32_t)((uint64_t)T * n_h[h] / std::max<uint64_t>(total, 1))); used += Q[h]; }
+                // hand out what rounding left (or take back what the minimum of one part per neighbourhood overdrew)
+                for (uint32_t guard = 0; used != T && guard < 4 * T + 4 * d.H; ++guard) {
+                    uint32_t best = d.H; double best_v = used < T ? -1.0 : 1e300;
+                    for (uint32_t h = 0; h < d.H; ++h) {
+                        if (!n_h[h]) continue;
+                        const double per_part = (double)n_h[h] / Q[h];
+                        if (used < T ? per_part > best_v : (Q[h] > 1 && per_part < best_v)) { best_v = per_part; best = h; }
+                    }
+                    if (best == d.H) break;
+                    if (used < T) { ++Q[best]; ++used; } else { --Q[best]; --used; }
+                }
+                table_at[r] = tables.size();
+                for (uint32_t h = 0; h < d.H; ++h)
+                    for (uint32_t q = 0; q < Q[h]; ++q) tables.push_back(uint4x{h, q, Q[h], 0});
+                while (tables.size() - table_at[r] < T) tables.push_back(uint4x{0, 0xFFFFFFFFu, 1, 0});     // an empty part: class q beyond every slice count
+            }
+        }
+        if (!tables.empty()) {
+            MVB_CARVE(s->mem, s->part_tables, 16 * tables.size());
+            MVB_CUDA(cudaMemcpyAsync(s->part_tables.p, tables.data(), 16 * tables.size(), cudaMemcpyHostToDevice, S));
+            MVB_CUDA(cudaStreamSynchronize(S));                    // `tables` is pageable and goes out of scope
+            for (uint32_t r = 0; r < R; ++r)
+                if (s->h_reps[r].local_mode) s->h_reps[r].part_table = s->part_tables.as<uint4>() + table_at[r];
+        }
+    }
     s->rep_args.assign((R + kMaxRepsPerLaunch - 1) / kMaxRepsPerLaunch, RepArray{});
     for (uint32_t r = 0; r < R; ++r) s->rep_args[r / kMaxRepsPerLaunch].r[r % kMaxRepsPerLaunch] = s->h_reps[r];
     MVB_CUDA(s->d_reps.alloc(sizeof(RepDev) * R));

@@ -59,6 +59,7 @@ struct RepDev {                     // device-side descriptor of one replica
     const uint32_t* int2ext;        // [N_pad] internal slot -> caller's agent id (kInvalid = padding); not read by the day kernel
     const uint32_t* nb_slice_begin; // [H + 1] SELL slices of every neighbourhood (LOCAL layout: parts are neighbourhood-pure)
     uint32_t local_mode, pad_;      // layout.h LayoutMode
+    const uint4* part_table;        // LOCAL layout: part p of a launch = {neighbourhood, class q, classes Q of that neighbourhood, 0}
 };
 
 __host__ __device__ inline uint32_t rec_width(uint32_t S, uint32_t H) { return 4 * H + 7 + S; }
@@ -359,11 +360,12 @@ day_kernel(const __grid_constant__ RepArray reps, uint32_t R, uint32_t P, uint32
         uint32_t* s_rec = reinterpret_cast<uint32_t*>(s_des + 4 * S);
         const uint32_t* __restrict__ g_vec = reinterpret_cast<const uint32_t*>(r.vec[parity]);
 
-        // LOCAL layout: part p = (neighbourhood p / Q, class p % Q of its slices); the block stages the hub region and
+        // LOCAL layout: part p = (a neighbourhood, class q of Q of its slices on this rank: part_table); the block stages the hub region and
         // that neighbourhood's own prefix.  GLOBAL: class p of all slices; every range is staged.
         uint32_t Q = P, q = p, sell_b = r.sell_begin, sell_e = r.sell_end, nb_part = 0;
         if (r.local_mode) {
-            Q = P / H; nb_part = p / Q; q = p - nb_part * Q;
+            const uint4 pt = r.part_table[p];
+            nb_part = pt.x; q = pt.y; Q = pt.z;
             sell_b = max(sell_b, r.nb_slice_begin[nb_part]); sell_e = max(sell_b, min(sell_e, r.nb_slice_begin[nb_part + 1]));
         }
         if (tid == 0) {                               // 1. stage yesterday's modes (TMA bulk copies)

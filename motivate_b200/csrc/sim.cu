@@ -146,6 +146,8 @@ struct mvb_sim {
     DevBuf d_reps;                       // RepDev[R]
     std::vector<RepDev> h_reps;
     std::vector<RepArray> rep_args;      // h_reps cut into kernel-parameter sized pieces
+    std::vector<uint32_t> local_P;       // per piece: parts per replica when its replicas use the LOCAL layout (0 = GLOBAL)
+    DevBuf part_tables;
     uint32_t rec_stride = 0;             // u32 per record row (all replicas)
     uint32_t grid = 0;                   // persistent blocks (one per SM)
     uint32_t max_npad = 0;
@@ -227,10 +229,7 @@ uint32_t choose_parts(const mvb_sim* s, uint32_t first_rep, uint32_t R) {
     const double t_slice = 7.5, t_fixed = 10.0 + vec_bytes / 150e3;                    // microseconds (calibrated on B200)
     uint32_t best = 1;
     double best_t = 1e300;
-    // LOCAL layout (layout.h): parts are neighbourhood-pure, so P is a multiple of the number of neighbourhoods
-    const uint32_t step = s->h_reps[first_rep].local_mode ? s->h_reps[first_rep].H : 1u;
-    if (step > 1) best = step;
-    for (uint32_t P = step; P <= std::max(s->grid, step) * (step > 1 ? 4u : 1u); P += step) {
+    for (uint32_t P = 1; P <= s->grid; ++P) {
         const double rounds = std::ceil((double)R * P / s->grid);
         const double t = rounds * (t_fixed + (slices / P / 32.0 + 0.5) * t_slice);        // + half a round: the ragged end
         if (t < best_t * 0.999) { best_t = t; best = P; }
@@ -250,7 +249,7 @@ int launch_day(mvb_sim* s, uint8_t weather, uint8_t changed) {
         s->rep_args[c], R, P, s->parity, prev, next, weather, changed, uw, s->vec_cap_words)
     for (size_t c = 0; c < s->rep_args.size(); ++c) {
         const uint32_t R = std::min<uint32_t>(kMaxRepsPerLaunch, (uint32_t)s->reps.size() - (uint32_t)c * kMaxRepsPerLaunch);
-        const uint32_t P = choose_parts(s, (uint32_t)c * kMaxRepsPerLaunch, R);
+        const uint32_t P = s->local_P[c] ? s->local_P[c] : choose_parts(s, (uint32_t)c * kMaxRepsPerLaunch, R);
         // work items (slices) a warp of a part gets: with many, they are claimed four at a time, else two (day_kernels.cuh)
         const RepDev& r0 = s->h_reps[c * kMaxRepsPerLaunch];
         const uint32_t per_warp = ((r0.hub_end - r0.hub_begin) + (r0.sell_end - r0.sell_begin)) / P / 32;
