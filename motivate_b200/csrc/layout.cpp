@@ -342,18 +342,24 @@ int build_graph_layout(const mvb_population& pop, uint32_t H, uint32_t capacity_
 void partition_slices(const GraphLayout& L, uint32_t world, std::vector<uint32_t>& bounds) {
     const uint32_t n = L.n_hub_slices + L.n_sell_slices;
     std::vector<uint64_t> work(n);
+    // Work model, in units of one shared-memory gather.  A link read from L2 costs about 2 of them when few links are
+    // cold (GLOBAL layout on populations just above the shared-memory capacity) and about 4 in the LOCAL layout, where a
+    // third of the links are cold gathers (calibrated on 12M agents over 2 B200s with MVB_DEBUG_NO_EXCHANGE: the two ranks'
+    // kernels then take 0.65 and 0.62 ms; with weight 8 0.59 and 0.69); + per-agent work; a hub's links are walked in a
+    // phase of their own, between two block barriers (x 2.5, calibrated on 8M agents over 2 B200s).
+    uint64_t cold = L.mode == kLayoutLocal ? 4 : 2, per_agent = L.mode == kLayoutLocal ? 40 : 64;
+    if (const char* e = getenv("MVB_PART_COLD")) cold = (uint64_t)atoi(e);          // calibration experiments
+    if (const char* e = getenv("MVB_PART_AGENT")) per_agent = (uint64_t)atoi(e);
     for (uint32_t hs = 0; hs < L.n_hub_slices; ++hs) {
         uint64_t w = 0;
         for (uint32_t k = 0; k < 32; ++k) {
             const uint32_t* dg = &L.hub_deg[(size_t)4 * (hs * 32 + k)];
-            // cold links cost about twice a hot one; + per-agent work; x 2.5 because a hub's links are walked in a
-            // phase of their own, between two block barriers (calibrated on 8M agents over 2 B200s)
-            w += 5ull * ((uint64_t)dg[0] + dg[1] + 2ull * (dg[2] + dg[3])) / 2 + 64;
+            w += 5ull * ((uint64_t)dg[0] + dg[1] + cold * (dg[2] + dg[3])) / 2 + per_agent;
         }
         work[hs] = w;
     }
     for (uint32_t s = 0; s < L.n_sell_slices; ++s)
-        work[L.n_hub_slices + s] = 32ull * ((L.sell_K[s] & 0xFFFFu) + 2ull * (L.sell_K[s] >> 16) + 64);
+        work[L.n_hub_slices + s] = 32ull * ((L.sell_K[s] & 0xFFFFu) + cold * (L.sell_K[s] >> 16) + per_agent);
     uint64_t total = 0;
     for (uint64_t w : work) total += w;
     bounds.assign(world + 1, n);

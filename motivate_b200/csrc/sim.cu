@@ -261,7 +261,8 @@ int launch_day(mvb_sim* s, uint8_t weather, uint8_t changed) {
         s->last_launches++;
     }
 #undef MVB_LAUNCH
-    if (s->world > 1) {
+    static const bool skip_exchange = getenv("MVB_DEBUG_NO_EXCHANGE") != nullptr;      // timing experiments only: results are wrong
+    if (s->world > 1 && !skip_exchange) {
         // agent-partitioned: every rank now holds new modes / norms for its own slices and a partial record.  The
         // social network is global (simulation.rs:160), so tomorrow every rank needs everybody's modes: ONE all-gather
         // of the packed 2-bit words (each rank's piece: its mode words, then its norm words, padded to the longest
