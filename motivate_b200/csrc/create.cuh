@@ -380,6 +380,7 @@ static int create_impl(uint32_t R, const mvb_population* const* pops, const mvb_
 
     std::vector<char> built(G, 0);
     std::list<std::vector<float>> host_f;
+    const double tm_first = now();
     for (uint32_t r = 0; r < R; ++r) {
         const mvb_population* p = pops[r];
         const mvb_tables* t = tabs[r];
@@ -718,16 +719,20 @@ static int create_impl(uint32_t R, const mvb_population* const* pops, const mvb_
     MVB_CUDA(cudaStreamSynchronize(S));
     for (uint32_t r = 0; r < R; ++r)
         if (flags[r].code) { set_error("replica %u: agent %u: %s", r, flags[r].index, setup_error_text(flags[r].code)); return MVB_ERR_ARG; }
-    if (timing)
-        fprintf(stderr, "mvb_create: %u replicas, %u graphs: enqueue + layout %.3f s (of which waiting for the device %.3f s), drain %.3f s\n",
-                R, G, tm3 - tm0, tm_wait, now() - tm3);
-    {   // hand the scratch memory back
+    const double tm4 = now();
+    {   // Scratch stays in the device's stream-ordered pool for the next handle of the process, up to 2 GB (what 64
+        // populations of 1M agents need; giving it back costs ~6 ms per create and as much again to get it the next time).
+        // Anything above that goes back to the driver at the pool's next synchronisation; MVB_TRIM_POOL=1 returns all now.
         cudaMemPool_t pool;
         MVB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-        uint64_t keep = 0;
+        uint64_t keep = 2ull << 30;
+        if (getenv("MVB_TRIM_POOL")) { keep = 0; }
         MVB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-        MVB_CUDA(cudaMemPoolTrimTo(pool, 0));
+        if (!keep) MVB_CUDA(cudaMemPoolTrimTo(pool, 0));
     }
+    if (timing)
+        fprintf(stderr, "mvb_create: %u replicas, %u graphs: before the first replica %.3f s, enqueue + layout %.3f s (of which waiting for the device %.3f s), "
+                "drain %.3f s, pool trim %.3f s\n", R, G, tm_first - tm0, tm3 - tm_first, tm_wait, tm4 - tm3, now() - tm4);
     *out = sp.release();
     return MVB_OK;
 }

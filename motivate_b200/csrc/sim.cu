@@ -219,6 +219,7 @@ int launch_census(mvb_sim* s, uint32_t row) {
 // Few parts per replica leave blocks idle, many make the set-up and the last, partly filled round of slices dominate
 // (small populations); pick the count with the smallest modelled launch time.
 uint32_t choose_parts(const mvb_sim* s, uint32_t first_rep, uint32_t R) {
+    if (const char* e = getenv("MVB_PARTS")) return (uint32_t)std::max(1, atoi(e));       // tuning experiments
     double slices = 0, vec_bytes = 0;
     for (uint32_t r = 0; r < R; ++r) {
         const RepDev& d = s->h_reps[first_rep + r];
