@@ -20,18 +20,18 @@ struct SetupScalars {                 // device -> host after each stage
 struct Plan {
     uint32_t N = 0, H = 0, n_hubs = 0, hub_pad = 0, n_hs = 0, N_pad = 0, n2 = 0, staged_hub_slots = 0, hot_words = 0;
     bool all_hot = false;
-    uint32_t mode = kLayoutGlobal;
-    std::vector<uint32_t> gsize, gpad, gstart, gofs, take, nb_slice_begin;
+    uint32_t mode = kLayoutGlobal, n_common_ranges = 0, common_words = 0;
+    std::vector<uint32_t> gsize, gpad, gstart, gofs, take, take_common, nb_slice_begin;
     std::vector<StageRange> ranges;
 };
 inline uint32_t round_up_u32(uint32_t v, uint32_t m) { return (v + m - 1) / m * m; }
 
-int make_plan(uint32_t N, uint32_t H, uint32_t capacity_agents, const uint32_t* cnt, uint32_t n_hubs, Plan& P) {
+int make_plan(uint32_t N, uint32_t H, uint32_t capacity_agents, const uint32_t* cnt, uint32_t n_hubs, uint32_t n_replicas, Plan& P) {
     constexpr uint32_t B = kHubDegree + 1;
     if (capacity_agents < 64 || capacity_agents % 64) { set_error("internal: bad shared-memory capacity %u", capacity_agents); return MVB_ERR_ARG; }
     P = Plan();
     P.N = N; P.H = H; P.n_hubs = n_hubs;
-    P.gsize.assign(H, 0); P.gpad.resize(H); P.gstart.resize(H); P.gofs.resize(H); P.take.assign(H, 0);
+    P.gsize.assign(H, 0); P.gpad.resize(H); P.gstart.resize(H); P.gofs.resize(H); P.take.assign(H, 0); P.take_common.assign(H, 0);
     // cum[h][k] = agents of group h with degree >= kHubDegree - k
     std::vector<uint32_t> cum((size_t)H * B);
     for (uint32_t h = 0; h < H; ++h) {
@@ -52,13 +52,37 @@ int make_plan(uint32_t N, uint32_t H, uint32_t capacity_agents, const uint32_t* 
     P.N_pad = (uint32_t)total;
     P.n2 = N - n_hubs;
     P.all_hot = P.N_pad <= capacity_agents;
-    P.mode = pick_layout_mode(P.N_pad, capacity_agents);
+    P.mode = pick_layout_mode(P.N_pad, capacity_agents, n_replicas);
     P.staged_hub_slots = P.all_hot ? P.hub_pad : std::min(P.hub_pad, capacity_agents);
     if (P.mode == kLayoutLocal) {
-        // hubs get at most half of shared memory, the rest holds the prefix of the block's own neighbourhood
+        // hubs get at most half of shared memory; then as in layout_begin (layout.cpp): whole neighbourhoods behind the longest
+        // common prefix that leaves them room, or, if a neighbourhood does not fit, its prefix alone
         P.staged_hub_slots = std::min(P.hub_pad, capacity_agents / 2 / 64 * 64);
-        const uint32_t local = capacity_agents - P.staged_hub_slots;
-        for (uint32_t h = 0; h < H; ++h) P.take[h] = std::min(P.gsize[h], local);
+        const uint32_t room = capacity_agents - P.staged_hub_slots;
+        uint32_t max_gpad = 0;
+        for (uint32_t h = 0; h < H; ++h) max_gpad = std::max(max_gpad, P.gpad[h]);
+        if (max_gpad <= room) {
+            auto need_for = [&](uint64_t theta, std::vector<uint32_t>& out) {
+                uint64_t sum = 0, tail = 0;
+                for (uint32_t h = 0; h < H; ++h) {
+                    const uint32_t c = theta > kHubDegree ? 0u : cum[(size_t)h * B + (kHubDegree - (uint32_t)theta)];
+                    out[h] = std::min(round_up_u32(c, 64), P.gsize[h] / 64 * 64);
+                    sum += out[h];
+                    tail = std::max<uint64_t>(tail, P.gpad[h] - out[h]);
+                }
+                return sum + tail;
+            };
+            std::vector<uint32_t> tmp(H);
+            uint64_t lo = 0, hi = kHubDegree + 1;
+            while (hi - lo > 1) {
+                const uint64_t mid = (lo + hi) / 2;
+                if (need_for(mid, tmp) <= room) hi = mid; else lo = mid;
+            }
+            need_for(hi, P.take_common);
+            P.take = P.gsize;
+        } else {
+            for (uint32_t h = 0; h < H; ++h) P.take[h] = std::min(P.gsize[h], room);
+        }
     } else if (P.all_hot) {
         P.take = P.gsize;
     } else {
@@ -96,20 +120,29 @@ int make_plan(uint32_t N, uint32_t H, uint32_t capacity_agents, const uint32_t* 
         staged += count;
     };
     if (P.mode == kLayoutLocal) {
-        P.ranges.push_back(StageRange{0, P.staged_hub_slots / 16, 0, 0});
+        add_range(0, P.staged_hub_slots);
+        if (P.ranges.empty()) P.ranges.push_back(StageRange{0, 0, 0, 0});
+        for (uint32_t h = 0; h < H; ++h) {
+            P.ranges.push_back(StageRange{P.gstart[h] / 16, P.take_common[h] / 16, staged / 16, 0});
+            staged += P.take_common[h];
+        }
+        const uint32_t common = staged;
         uint32_t longest = 0;
         for (uint32_t h = 0; h < H; ++h) {
-            const uint32_t words = round_up_u32(P.take[h], 64) / 16;
-            P.ranges.push_back(StageRange{P.gstart[h] / 16, words, P.staged_hub_slots / 16, 0});
+            const uint32_t words = (round_up_u32(P.take[h], 64) - P.take_common[h]) / 16;
+            P.ranges.push_back(StageRange{(P.gstart[h] + P.take_common[h]) / 16, words, common / 16, 0});
             longest = std::max(longest, words);
         }
-        staged = P.staged_hub_slots + longest * 16;
+        P.n_common_ranges = 1 + H;
+        P.common_words = common / 16;
+        staged = common + longest * 16;
     } else if (P.all_hot) add_range(0, P.N_pad);
     else {
         add_range(0, std::min(P.hub_pad, capacity_agents));
         for (uint32_t h = 0; h < H; ++h) add_range(P.gstart[h], P.take[h]);
     }
     P.hot_words = staged / 16;
+    if (P.mode != kLayoutLocal) { P.n_common_ranges = (uint32_t)P.ranges.size(); P.common_words = P.hot_words; }
     return MVB_OK;
 }
 
@@ -358,7 +391,7 @@ static int create_impl(uint32_t R, const mvb_population* const* pops, const mvb_
 
     // pinned landing zone of the small device -> host reads (one graph at a time) and source of the plan uploads
     const size_t cnt_bytes = (sizeof(uint32_t) * (size_t)H_max * (kHubDegree + 1) + 255) & ~(size_t)255;
-    const size_t plan_bytes = sizeof(uint32_t) * (4 * (size_t)H_max + 1) + sizeof(StageRange) * ((size_t)H_max + 2);
+    const size_t plan_bytes = sizeof(uint32_t) * (5 * (size_t)H_max + 4) + sizeof(StageRange) * (2 * (size_t)H_max + 2);
     char* pin = nullptr; size_t pin_cap = 0;
     MVB_CUDA(pinned_cache().get(cnt_bytes + plan_bytes + 256, &pin, &pin_cap));
     struct PinGuard { char* p; size_t cap; ~PinGuard() { pinned_cache().put(p, cap); } } pin_guard{pin, pin_cap};
@@ -415,27 +448,30 @@ static int create_impl(uint32_t R, const mvb_population* const* pops, const mvb_
             if (int rc = host_wait()) return rc;
             if (h_scal->flag.code) { set_error("replica %u: agent %u: %s", r, h_scal->flag.index, setup_error_text(h_scal->flag.code)); return MVB_ERR_ARG; }
             Plan P;
-            if (int rc = make_plan(N, H, capacity_agents, h_cnt, h_scal->n_hubs, P)) return rc;
+            if (int rc = make_plan(N, H, capacity_agents, h_cnt, h_scal->n_hubs, R, P)) return rc;
             L = GraphLayout();
             L.N = N; L.N_pad = P.N_pad; L.Es = gi.Es; L.En = gi.En;
             L.n_hub_slices = P.n_hs; L.n_sell_slices = (P.N_pad - P.hub_pad) / 32; L.hot_words = P.hot_words;
-            L.ranges = P.ranges; L.mode = P.mode; L.nb_slice_begin = P.nb_slice_begin;
+            L.ranges = P.ranges; L.mode = P.mode; L.nb_slice_begin = P.nb_slice_begin; L.n_common_ranges = P.n_common_ranges;
+            g->common_words = P.common_words;
             if (L.hot_words + 4 > s->vec_cap_words) { set_error("internal: staged vector larger than its shared-memory slot"); return MVB_ERR_STATE; }
             const uint32_t n_hub_rows = P.n_hs * 32, n_sell = L.n_sell_slices, n2 = P.n2, n_hubs = P.n_hubs;
             // ---- stage B: the two orders, hot counts, slices, offsets ------------------------------------------
             uint32_t* hp = reinterpret_cast<uint32_t*>(h_plan);
             memcpy(hp, P.gofs.data(), 4 * (size_t)H); memcpy(hp + H, P.take.data(), 4 * (size_t)H); memcpy(hp + 2 * H, P.gstart.data(), 4 * (size_t)H);
-            memcpy(hp + 3 * H, P.nb_slice_begin.data(), 4 * ((size_t)H + 1));
-            uint32_t* hr = hp + 4 * H + 2;                                        // (8-byte aligned: StageRange is 16 bytes of u32)
+            memcpy(hp + 3 * H, P.take_common.data(), 4 * (size_t)H);
+            memcpy(hp + 4 * H, P.nb_slice_begin.data(), 4 * ((size_t)H + 1));
+            uint32_t* hr = hp + 5 * H + 4;
             memcpy(hr, P.ranges.data(), sizeof(StageRange) * P.ranges.size());
             UpBuf plan;
-            MVB_CUDA(plan.alloc(4 * 3 * (size_t)H, S));
-            MVB_CUDA(cudaMemcpyAsync(plan.p, hp, 4 * 3 * (size_t)H, cudaMemcpyHostToDevice, S));
+            MVB_CUDA(plan.alloc(4 * 4 * (size_t)H, S));
+            MVB_CUDA(cudaMemcpyAsync(plan.p, hp, 4 * 4 * (size_t)H, cudaMemcpyHostToDevice, S));
             const uint32_t* d_gofs = plan.as<uint32_t>(); const uint32_t* d_take = d_gofs + H; const uint32_t* d_gstart = d_gofs + 2 * H;
+            const uint32_t* d_take_common = d_gofs + 3 * H;
             MVB_CARVE(s->mem, g->ranges, sizeof(StageRange) * P.ranges.size());
             MVB_CUDA(cudaMemcpyAsync(g->ranges.p, hr, sizeof(StageRange) * P.ranges.size(), cudaMemcpyHostToDevice, S));
             MVB_CARVE(s->mem, g->nb_slice_begin, 4 * ((size_t)H + 1));
-            MVB_CUDA(cudaMemcpyAsync(g->nb_slice_begin.p, hp + 3 * H, 4 * ((size_t)H + 1), cudaMemcpyHostToDevice, S));
+            MVB_CUDA(cudaMemcpyAsync(g->nb_slice_begin.p, hp + 4 * H, 4 * ((size_t)H + 1), cudaMemcpyHostToDevice, S));
             MVB_CARVE(s->mem, g->int2ext, 4 * (size_t)P.N_pad);
             MVB_CARVE(s->mem, g->deg, 4 * (size_t)P.N_pad);
             MVB_CARVE(s->mem, g->hub_off, 8 * (size_t)n_hub_rows + 8);
@@ -461,19 +497,20 @@ static int create_impl(uint32_t R, const mvb_population* const* pops, const mvb_
                 MVB_CUDA(radix_sort_pairs(hkk, hvv, n_hubs, 32, scratch.as<uint32_t>(), &hc, S));
                 place_hubs_kernel<<<(n_hubs + 255) / 256, 256, 0, S>>>(n_hubs, P.n_hs, P.staged_hub_slots, hvv[hc], g->int2ext.as<uint32_t>(), is_hot.as<uint8_t>());
             }
-            if (n2) mark_hot_kernel<<<(n2 + 255) / 256, 256, 0, S>>>(n2, key1s, order1, d_gofs, d_take, P.mode == kLayoutLocal ? 2 : 1, is_hot.as<uint8_t>());
+            if (n2) mark_hot_kernel<<<(n2 + 255) / 256, 256, 0, S>>>(n2, key1s, order1, d_gofs, d_take, P.mode == kLayoutLocal ? d_take_common : nullptr, is_hot.as<uint8_t>());
             uint32_t* d_bad = &d_scal->flag.code;              // count_hot_kernel ORs 1 in: translated below
             MVB_CUDA(cudaMemsetAsync(d_bad, 0, 4, S));
             count_hot_kernel<<<(unsigned)std::min<uint64_t>(((uint64_t)N * 32 + 255) / 256, (uint64_t)sms * 32), 256, 0, S>>>(
                 N, gi.srp, gi.scol, gi.nrp, gi.ncol, is_hot.as<uint8_t>(), gi.nbhd, nsh.as<uint32_t>(), nnh.as<uint32_t>(), d_bad);
             MVB_CUDA(cudaGetLastError());
             if (n2) {
-                key2_kernel<<<(n2 + 255) / 256, 256, 0, S>>>(n2, key1s, order1, d_gofs, d_take, nsh.as<uint32_t>(), nnh.as<uint32_t>(), kk[cur ^ 1]);
+                key2_kernel<<<(n2 + 255) / 256, 256, 0, S>>>(n2, key1s, order1, d_gofs, d_take, P.mode == kLayoutLocal ? d_take_common : nullptr,
+                                                              nsh.as<uint32_t>(), nnh.as<uint32_t>(), kk[cur ^ 1]);
                 // second order: (group, hot part first, hot length desc), ties keep the first order
                 uint32_t* k2[2] = {kk[cur ^ 1], kk[cur]};
                 uint32_t* v2[2] = {vv[cur], vv[cur ^ 1]};
                 int c2 = 0;
-                MVB_CUDA(radix_sort_pairs(k2, v2, n2, 8 + bits_for(2 * H), scratch.as<uint32_t>(), &c2, S));
+                MVB_CUDA(radix_sort_pairs(k2, v2, n2, 8 + bits_for(4 * H), scratch.as<uint32_t>(), &c2, S));
                 place_agents_kernel<<<(n2 + 255) / 256, 256, 0, S>>>(n2, k2[c2], v2[c2], d_gofs, d_gstart, g->int2ext.as<uint32_t>());
             }
             UpBuf sell_K, sell_len, sell_off, hub_nu, hub_len, unit_base, sums;
@@ -537,7 +574,7 @@ static int create_impl(uint32_t R, const mvb_population* const* pops, const mvb_
             MVB_CUDA(tcode.alloc(4 * (size_t)N, S));
             if (P.mode == kLayoutLocal) MVB_CUDA(tcold.alloc(4 * (size_t)N, S));
             tcode_kernel<<<(P.N_pad + 255) / 256, 256, 0, S>>>(P.N_pad, g->int2ext.as<uint32_t>(), g->ranges.as<StageRange>(), (uint32_t)P.ranges.size(),
-                                                             is_hot.as<uint8_t>(), P.mode == kLayoutLocal ? gi.nbhd : nullptr, tcode.as<uint32_t>(), tcold.as<uint32_t>());
+                                                             is_hot.as<uint8_t>(), P.mode == kLayoutLocal ? gi.nbhd : nullptr, H, P.hub_pad, tcode.as<uint32_t>(), tcold.as<uint32_t>());
             MVB_CUDA(cudaGetLastError());
             FillArgs fa{gi.srp, gi.scol, gi.nrp, gi.ncol, tcode.as<uint32_t>(), g->int2ext.as<uint32_t>(), P.n_hs, n_sell,
                         g->sell_meta.as<uint4>(), g->sell_codes.as<uint32_t>(), g->deg.as<uint32_t>(),
@@ -600,7 +637,7 @@ static int create_impl(uint32_t R, const mvb_population* const* pops, const mvb_
         RepDev& d = s->h_reps[r];
         d.N = N; d.N_pad = NP; d.S = rp.S; d.H = rp.H; d.rec_off = rp.rec_off;
         d.n_hub_slices = L.n_hub_slices; d.n_sell_slices = L.n_sell_slices;
-        d.n_ranges = (uint32_t)L.ranges.size(); d.hot_words = L.hot_words;
+        d.n_ranges = L.n_common_ranges; d.hot_words = g->common_words;      // what every block stages (LOCAL: + one more range, of its neighbourhood)
         d.hub_begin = 0; d.hub_end = L.n_hub_slices; d.sell_begin = 0; d.sell_end = L.n_sell_slices;
         if (world > 1) { d.hub_begin = s->own[0]; d.hub_end = s->own[1]; d.sell_begin = s->own[2]; d.sell_end = s->own[3]; }
         d.state = rp.state.as<uint32_t>();
@@ -648,16 +685,19 @@ static int create_impl(uint32_t R, const mvb_population* const* pops, const mvb_
         std::vector<size_t> table_at(R, 0);
         for (uint32_t c = 0; c < n_pieces; ++c) {
             const uint32_t r0 = c * kMaxRepsPerLaunch, r1 = std::min(R, r0 + kMaxRepsPerLaunch);
-            if (!s->h_reps[r0].local_mode) continue;
-            for (uint32_t r = r0; r < r1; ++r)
-                if (!s->h_reps[r].local_mode) { set_error("internal: replicas of one launch use different staging layouts"); return MVB_ERR_STATE; }
-            const RepDev& d0 = s->h_reps[r0];
+            uint32_t first_local = r1;
+            for (uint32_t r = r1; r-- > r0;) if (s->h_reps[r].local_mode) first_local = r;
+            if (first_local == r1) continue;                     // no replica of this launch uses the LOCAL layout
+            // (replicas in the GLOBAL layout that share the launch take class p of the same P = T parts: any P works for them)
+            const RepDev& d0 = s->h_reps[first_local];
             const uint32_t own0 = d0.sell_end - d0.sell_begin;
             uint32_t rounds = std::max<uint32_t>(1, std::min<uint32_t>(8, (uint32_t)((uint64_t)own0 * (r1 - r0) / ((uint64_t)s->grid * 32 * 8))));
             uint32_t T = std::max<uint32_t>(d0.H, rounds * s->grid / (r1 - r0));
+            for (uint32_t r = r0; r < r1; ++r) if (s->h_reps[r].local_mode) T = std::max(T, s->h_reps[r].H);
             s->local_P[c] = T;
             for (uint32_t r = r0; r < r1; ++r) {
                 const RepDev& d = s->h_reps[r];
+                if (!d.local_mode) continue;
                 const std::vector<uint32_t>& nb = s->reps[r].graph->L.nb_slice_begin;
                 std::vector<uint32_t> n_h(d.H), Q(d.H, 0);
                 uint64_t total = 0;

@@ -370,12 +370,12 @@ day_kernel(const __grid_constant__ RepArray reps, uint32_t R, uint32_t P, uint32
         }
         if (tid == 0) {                               // 1. stage yesterday's modes (TMA bulk copies)
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            const uint32_t n_stage = r.local_mode ? 2u : r.n_ranges;
-            uint32_t words = r.hot_words;
-            if (r.local_mode) words = r.ranges[0].n_words + r.ranges[1 + nb_part].n_words;
-            mbar_expect_tx(s_bar, words * 4u);
+            // the ranges every block stages, then (LOCAL layout) the piece of this part's own neighbourhood behind them
+            const uint32_t n_stage = r.n_ranges + (r.local_mode ? 1u : 0u);
+            const StageRange own = r.local_mode ? r.ranges[r.n_ranges + nb_part] : StageRange{0, 0, 0, 0};
+            mbar_expect_tx(s_bar, (r.hot_words + own.n_words) * 4u);
             for (uint32_t k = 0; k < n_stage; ++k) {
-                const StageRange g = r.ranges[r.local_mode && k ? 1 + nb_part : k];
+                const StageRange g = k < r.n_ranges ? r.ranges[k] : own;
                 for (uint32_t o = 0; o < g.n_words; o += 16384) {          // <= 64 KB per copy
                     const uint32_t n = min(g.n_words - o, 16384u);
                     bulk_g2s(s_vec + g.dst_word + o, g_vec + g.src_word + o, n * 4u, s_bar);

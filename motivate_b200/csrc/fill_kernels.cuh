@@ -72,15 +72,15 @@ __global__ void count_hot_kernel(uint32_t N, const uint64_t* __restrict__ s_rowp
 // by its place in the staged vector (ranges), a cold one by its internal slot.  Same rule as layout_finish.
 __global__ void tcode_kernel(uint32_t N_pad, const uint32_t* __restrict__ int2ext, const StageRange* __restrict__ ranges,
                              uint32_t n_ranges, const uint8_t* __restrict__ is_hot, const uint16_t* __restrict__ nbhd_local,
-                             uint32_t* __restrict__ tcode, uint32_t* __restrict__ tcold) {
+                             uint32_t H, uint32_t hub_pad, uint32_t* __restrict__ tcode, uint32_t* __restrict__ tcold) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= N_pad) return;
     const uint32_t e = int2ext[t];
     if (e == kInvalid) return;
     uint32_t pos = t, hot = is_hot[e];
-    if (nbhd_local) {                                         // LOCAL layout: ranges[0] = hub region, ranges[1 + h] = prefix of neighbourhood h
+    if (nbhd_local) {      // LOCAL layout: ranges[0] = hub region, [1 + h] = common prefix of group h, [1 + H + h] = own piece of neighbourhood h
         tcold[e] = (t >> 4) << 7 | (30u - 2u * (t & 15u));
-        if (hot == 2u) { const StageRange r = ranges[1 + nbhd_local[e]]; pos = r.dst_word * 16u + (t - r.src_word * 16u); }
+        if (hot && t >= hub_pad) { const StageRange r = ranges[(hot == 2u ? 1u + H : 1u) + nbhd_local[e]]; pos = r.dst_word * 16u + (t - r.src_word * 16u); }
         tcode[e] = ((pos >> 4) << 7 | (30u - 2u * (pos & 15u))) | (hot ? 1u : 0u);
         return;
     }

@@ -27,17 +27,21 @@ void counting_sort_desc(std::vector<uint32_t>& v, size_t b, size_t e, uint32_t m
 }
 }  // namespace
 
-LayoutMode pick_layout_mode(uint32_t N_pad, uint32_t capacity_agents) {
+LayoutMode pick_layout_mode(uint32_t N_pad, uint32_t capacity_agents, uint32_t n_replicas) {
+    if (N_pad <= capacity_agents) return kLayoutGlobal;          // a population that fits is staged whole
     if (const char* e = getenv("MVB_LAYOUT")) {
-        if (!strcmp(e, "local")) return N_pad > capacity_agents ? kLayoutLocal : kLayoutGlobal;   // (a population that fits is staged whole)
+        if (!strcmp(e, "local")) return kLayoutLocal;
         if (!strcmp(e, "global")) return kLayoutGlobal;
     }
-    // measured on B200 (S=4, H=10, BA 5+10): GLOBAL wins up to ~2.5M agents (at 2M: 29.7 % vs 24.6 % of the HBM roofline),
-    // LOCAL beyond (3M: 25.8 vs 23.4; 8M: 27.3 vs 16.6; 50M in 64 neighbourhoods: 24.4 vs 12.8)
-    return (uint64_t)N_pad * 4 > (uint64_t)capacity_agents * 11 ? kLayoutLocal : kLayoutGlobal;
+    // Measured on B200 (S=4, H=10, BA 5+10), % of the HBM roofline, GLOBAL vs LOCAL:
+    //   one population:  1M 49.7 / 54.4   2M 29.7 / 41.9   3M 23.4 / 36.9   6M 17.9 / 30.7   8M 16.6 / 27.8   50M (H=64) 12.8 / 24.4
+    //   8 x 1M 81 / 64,  64 x 1M 83.5 / 64.4: LOCAL's parts are neighbourhood-pure, so a launch of many replicas has several
+    //   times more of them, and at 1M agents only 4 % of the links are cold to begin with.
+    if (n_replicas <= 4) return kLayoutLocal;
+    return (uint64_t)N_pad * 2 > (uint64_t)capacity_agents * 3 ? kLayoutLocal : kLayoutGlobal;
 }
 
-int layout_begin(const mvb_population& pop, uint32_t H, uint32_t capacity_agents, GraphLayout& L, LayoutWork& W) {
+int layout_begin(const mvb_population& pop, uint32_t H, uint32_t capacity_agents, GraphLayout& L, LayoutWork& W, uint32_t n_replicas) {
     const uint32_t N = pop.n_agents;
     const uint64_t* srp = pop.social_rowptr;
     const uint64_t* nrp = pop.neighbour_rowptr;
@@ -111,13 +115,40 @@ int layout_begin(const mvb_population& pop, uint32_t H, uint32_t capacity_agents
     L.N_pad = (uint32_t)total;
     const bool all_hot = W.all_hot = L.N_pad <= capacity_agents;
     W.capacity_agents = capacity_agents;
-    W.mode = L.mode = pick_layout_mode(L.N_pad, capacity_agents);
+    W.mode = L.mode = pick_layout_mode(L.N_pad, capacity_agents, n_replicas);
     W.staged_hub_slots = all_hot ? hub_pad : std::min(hub_pad, capacity_agents);
+    W.take_common.assign(H, 0);
     if (W.mode == kLayoutLocal) {
-        // hubs get at most half of shared memory, the rest holds the prefix of the block's own neighbourhood
+        // hubs get at most half of shared memory
         W.staged_hub_slots = std::min(hub_pad, capacity_agents / 2 / 64 * 64);
-        const uint32_t local = capacity_agents - W.staged_hub_slots;
-        for (uint32_t h = 0; h < H; ++h) take[h] = std::min((uint32_t)groups[h].size(), local);
+        const uint32_t room = capacity_agents - W.staged_hub_slots;
+        uint32_t max_gpad = 0;
+        for (uint32_t h = 0; h < H; ++h) max_gpad = std::max(max_gpad, gpad[h]);
+        if (max_gpad <= room) {
+            // every neighbourhood fits: its blocks stage all of it, and every block the longest degree-threshold prefix of
+            // all groups such that   sum_h common[h] + max_h (gpad[h] - common[h]) <= room
+            auto need_for = [&](uint64_t theta, std::vector<uint32_t>& out) {
+                uint64_t sum = 0, tail = 0;
+                for (uint32_t h = 0; h < H; ++h) {
+                    const auto& g = groups[h];
+                    const uint32_t c = (uint32_t)(std::partition_point(g.begin(), g.end(), [&](uint32_t a) { return d[a] >= theta; }) - g.begin());
+                    out[h] = std::min(round_up(c, 64), (uint32_t)g.size() / 64 * 64);
+                    sum += out[h];
+                    tail = std::max<uint64_t>(tail, gpad[h] - out[h]);
+                }
+                return sum + tail;
+            };
+            std::vector<uint32_t> tmp(H);
+            uint64_t lo = 0, hi = kHubDegree + 1;        // theta in (lo, hi]; hi always fits (no common prefix at all)
+            while (hi - lo > 1) {
+                const uint64_t mid = (lo + hi) / 2;
+                if (need_for(mid, tmp) <= room) hi = mid; else lo = mid;
+            }
+            need_for(hi, W.take_common);
+            for (uint32_t h = 0; h < H; ++h) take[h] = (uint32_t)groups[h].size();
+        } else {
+            for (uint32_t h = 0; h < H; ++h) take[h] = std::min((uint32_t)groups[h].size(), room);
+        }
     } else if (all_hot) {
         for (uint32_t h = 0; h < H; ++h) take[h] = (uint32_t)groups[h].size();
     } else {
@@ -151,7 +182,7 @@ int layout_begin(const mvb_population& pop, uint32_t H, uint32_t capacity_agents
     for (uint32_t k = 0; k < W.staged_hub_slots; ++k)     // hub slots that get staged
         if (hubs[k] != kInvalid) is_hot[hubs[k]] = 1;
     for (uint32_t h = 0; h < H; ++h)
-        for (uint32_t k = 0; k < take[h]; ++k) is_hot[groups[h][k]] = W.mode == kLayoutLocal ? 2 : 1;
+        for (uint32_t k = 0; k < take[h]; ++k) is_hot[groups[h][k]] = (W.mode == kLayoutLocal && k >= W.take_common[h]) ? 2 : 1;
     return MVB_OK;
 }
 
@@ -221,7 +252,8 @@ int layout_finish(const mvb_population& pop, LayoutWork& W, GraphLayout& L, bool
                 for (size_t i = b; i < e; ++i) tmp[cnt[kHubDegree - (uint32_t)((kv[i] >> 32) & 0xFFFFu)]++] = kv[i];
                 std::copy(tmp.begin(), tmp.end(), kv.begin() + b);
             };
-            sort_part(0, take[h]);
+            sort_part(0, W.take_common[h]);                    // (empty unless the LOCAL layout has a common prefix)
+            sort_part(W.take_common[h], take[h]);
             sort_part(take[h], g.size());
             for (size_t i = 0; i < kv.size(); ++i) L.int2ext[gstart[h] + i] = (uint32_t)kv[i];
             for (size_t b = 0; b < W.gpad[h]; b += 32, ++s) {   // the group's slices: its agents, 32 at a time, then padding
@@ -249,15 +281,23 @@ int layout_finish(const mvb_population& pop, LayoutWork& W, GraphLayout& L, bool
     for (uint32_t h = 0; h < H; ++h) L.nb_slice_begin[h] = (gstart[h] - hub_pad) / 32;
     L.nb_slice_begin[H] = L.n_sell_slices;
     if (W.mode == kLayoutLocal) {
-        // [0] the hub region; [1 + h] the prefix of neighbourhood h, every one of them placed right behind the hub region
-        L.ranges.push_back(StageRange{0, W.staged_hub_slots / 16, 0, 0});
+        // [0] the hub region, [1 + h] the common prefix of group h; then [1 + H + h] the piece of neighbourhood h that only its
+        // own blocks stage, every one of them placed right behind the common set
+        add_range(0, W.staged_hub_slots);
+        if (L.ranges.empty()) L.ranges.push_back(StageRange{0, 0, 0, 0});
+        for (uint32_t h = 0; h < H; ++h) {
+            L.ranges.push_back(StageRange{gstart[h] / 16, W.take_common[h] / 16, staged / 16, 0});
+            staged += W.take_common[h];
+        }
+        const uint32_t common = staged;
         uint32_t longest = 0;
         for (uint32_t h = 0; h < H; ++h) {
-            const uint32_t words = (take[h] + 63) / 64 * 64 / 16;
-            L.ranges.push_back(StageRange{gstart[h] / 16, words, W.staged_hub_slots / 16, 0});
+            const uint32_t words = ((take[h] + 63) / 64 * 64 - W.take_common[h]) / 16;
+            L.ranges.push_back(StageRange{(gstart[h] + W.take_common[h]) / 16, words, common / 16, 0});
             longest = std::max(longest, words);
         }
-        staged = W.staged_hub_slots + longest * 16;
+        L.n_common_ranges = 1 + H;
+        staged = common + longest * 16;
     } else if (W.all_hot) {
         add_range(0, L.N_pad);
     } else {
@@ -265,6 +305,7 @@ int layout_finish(const mvb_population& pop, LayoutWork& W, GraphLayout& L, bool
         for (uint32_t h = 0; h < H; ++h) add_range(gstart[h], take[h]);     // take[h] is a multiple of 64 here
     }
     L.hot_words = staged / 16;
+    if (W.mode != kLayoutLocal) L.n_common_ranges = (uint32_t)L.ranges.size();
 
     // ---- link codes ---------------------------------------------------------------------------
     // code of every possible target; the arrays of codes are filled on the device (fill_kernels.cuh).  With
@@ -276,7 +317,10 @@ int layout_finish(const mvb_population& pop, LayoutWork& W, GraphLayout& L, bool
             if (e == kInvalid) continue;
             L.tcold[e] = (t >> 4) << 7 | (30u - 2u * (t & 15u));
             uint32_t pos = t;                                    // a staged hub sits at its own slot in the hub region
-            if (W.is_hot[e] == 2) pos = W.staged_hub_slots + (t - gstart[pop.neighbourhood[e]]);
+            if (W.is_hot[e] && t >= hub_pad) {
+                const StageRange& r = L.ranges[(W.is_hot[e] == 2 ? 1 + H : 1) + pop.neighbourhood[e]];
+                pos = r.dst_word * 16 + (t - r.src_word * 16);
+            }
             L.tcode[e] = W.is_hot[e] ? (((pos >> 4) << 7 | (30u - 2u * (pos & 15u))) | 1u) : L.tcold[e];
         }
     } else if (want_tcode) {
@@ -332,9 +376,9 @@ int layout_finish(const mvb_population& pop, LayoutWork& W, GraphLayout& L, bool
     return MVB_OK;
 }
 
-int build_graph_layout(const mvb_population& pop, uint32_t H, uint32_t capacity_agents, GraphLayout& L) {
+int build_graph_layout(const mvb_population& pop, uint32_t H, uint32_t capacity_agents, GraphLayout& L, uint32_t n_replicas) {
     LayoutWork W;
-    if (int rc = layout_begin(pop, H, capacity_agents, L, W)) return rc;
+    if (int rc = layout_begin(pop, H, capacity_agents, L, W, n_replicas)) return rc;
     layout_count_hot(pop, W);
     return layout_finish(pop, W, L, true);
 }

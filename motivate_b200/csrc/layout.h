@@ -84,15 +84,20 @@ inline size_t rec_habit_word(uint32_t slot) { return (size_t)(slot >> 5) * kRecW
 // Which part of yesterday's mode vector a block stages in shared memory:
 //   GLOBAL  one set for the whole population: all hubs + a degree-descending prefix of every neighbourhood group
 //           (everything, if the population fits).  Every block stages the same set; a part is any subset of slices.
-//   LOCAL   for populations far larger than shared memory: the neighbour network never leaves the neighbourhood
+//   LOCAL   for populations larger than shared memory: the neighbour network never leaves the neighbourhood
 //           (simulation.rs:165-173: two thirds of all links), so a block working on slices of neighbourhood h stages
-//           the hubs (a fixed region) + the degree-descending prefix of h ITSELF, as much as fits.  A link is hot if its
-//           target is a staged hub, or if source and target live in the same neighbourhood and the target is in that
-//           neighbourhood's prefix (hub SOURCES are handled in mixed slices and only get the first kind).  Parts are
-//           neighbourhood-pure.  With 8M agents in 10 neighbourhoods this turns 71 % of the links into shared-memory
-//           gathers where the global set reaches 34 %.
+//           a set common to all blocks (the hubs + a degree-descending prefix of every group) AND a piece of h ITSELF
+//           right behind it.  If every neighbourhood fits in what the hubs leave, that piece is the whole rest of h (all
+//           neighbour links are shared-memory gathers) and the common prefix is as long as the room left allows;
+//           otherwise there is no common prefix and the piece is the degree-descending prefix of h, as much as fits.
+//           A link is hot if its target is in the common set, or if source and target live in the same neighbourhood and
+//           the target is in that neighbourhood's piece (hub SOURCES are handled in mixed slices and only get the first
+//           kind).  Parts are neighbourhood-pure.  With 8M agents in 10 neighbourhoods this turns 71 % of the links into
+//           shared-memory gathers where one global set reaches 34 %.
 enum LayoutMode : uint32_t { kLayoutGlobal = 0, kLayoutLocal = 1 };
-LayoutMode pick_layout_mode(uint32_t N_pad, uint32_t capacity_agents);      // MVB_LAYOUT=global|local overrides (tests)
+// n_replicas = replicas stepped by the same launches (the LOCAL layout has more, smaller parts: with many replicas their
+// fixed cost outweighs the cold links it saves on populations just above the capacity).  MVB_LAYOUT=global|local overrides.
+LayoutMode pick_layout_mode(uint32_t N_pad, uint32_t capacity_agents, uint32_t n_replicas);
 
 struct uint4x { uint32_t x, y, z, w; };   // host-side mirror of CUDA's uint4 (16 bytes)
 
@@ -115,7 +120,9 @@ struct GraphLayout {
                                    // (the low bit is free: the shift field of a code is even); input of the fill kernels.
                                    // Only filled by build_graph_layout: mvb_create* makes it on the device (tcode_kernel)
     std::vector<StageRange> ranges;   // GLOBAL: every range is staged by every block.  LOCAL: [0] = the hub region, [1 + h] = the
-                                      // prefix of neighbourhood h (a block stages [0] and the one of its neighbourhood)
+                                      // common prefix of group h (may be empty), [1 + H + h] = the piece of neighbourhood h that
+                                      // only its own blocks stage, placed behind the n_common = 1 + H common ranges
+    uint32_t n_common_ranges = 0;     // ranges every block stages (all of them in the GLOBAL layout)
     uint32_t mode = kLayoutGlobal;
     std::vector<uint32_t> nb_slice_begin;  // [H + 1] SELL slices of neighbourhood h: [nb_slice_begin[h], nb_slice_begin[h + 1])
     std::vector<uint32_t> tcold;      // LOCAL, with tcode: the cold code of every target (a neighbourhood-prefix target is hot
@@ -149,7 +156,8 @@ struct LayoutWork {                        // what layout_begin leaves for the l
     std::vector<uint64_t> d;               // [N] total links
     std::vector<uint32_t> hubs;            // [hub_pad] hub id per hub slot (kInvalid = free place), see layout.h on the order
     std::vector<std::vector<uint32_t>> groups;   // per neighbourhood: ids of the other agents, (degree desc, id asc)
-    std::vector<uint32_t> take, gpad;      // per group: hot agents (a prefix), size rounded up to 64
+    std::vector<uint32_t> take, gpad;      // per group: staged agents (a prefix), size rounded up to 64
+    std::vector<uint32_t> take_common;     // LOCAL: the part of that prefix every block stages (the rest only its own neighbourhood's)
     uint32_t hub_pad = 0, capacity_agents = 0;
     bool all_hot = false;
     uint32_t mode = kLayoutGlobal, staged_hub_slots = 0;
@@ -158,12 +166,13 @@ struct LayoutWork {                        // what layout_begin leaves for the l
     const uint32_t* nnh = nullptr;         // [N] neighbour links with a hot target  caller from the device's counts)
     std::vector<uint32_t> nsh_own, nnh_own;
 };
-int layout_begin(const mvb_population& pop, uint32_t n_neighbourhoods, uint32_t capacity_agents, GraphLayout& out, LayoutWork& work);
+int layout_begin(const mvb_population& pop, uint32_t n_neighbourhoods, uint32_t capacity_agents, GraphLayout& out, LayoutWork& work,
+                 uint32_t n_replicas = 1);
 void layout_count_hot(const mvb_population& pop, LayoutWork& work);
 int layout_finish(const mvb_population& pop, LayoutWork& work, GraphLayout& out, bool want_tcode);
 // all three on the host (mvb_partition_plan, mvb_create_partitioned)
 int build_graph_layout(const mvb_population& pop, uint32_t n_neighbourhoods, uint32_t capacity_agents,
-                       GraphLayout& out);
+                       GraphLayout& out, uint32_t n_replicas = 1);
 
 // Agent-partitioned mode: cut the slices (hub slices first, then SELL slices, i.e. internal slot order) into `world`
 // contiguous ranges of about equal link count.  bounds[r] .. bounds[r+1] are rank r's slices (global slice index:

@@ -260,28 +260,31 @@ __global__ void place_hubs_kernel(uint32_t n_hubs, uint32_t n_hs, uint32_t stage
 }
 // first order (neighbourhood, degree desc, id asc), compact position q: hot if its rank in the group is below take[h]
 __global__ void mark_hot_kernel(uint32_t n2, const uint32_t* __restrict__ key1_sorted, const uint32_t* __restrict__ order1,
-                                const uint32_t* __restrict__ gofs, const uint32_t* __restrict__ take, uint32_t cls, uint8_t* __restrict__ is_hot) {
+                                const uint32_t* __restrict__ gofs, const uint32_t* __restrict__ take,
+                                const uint32_t* __restrict__ take_common, uint8_t* __restrict__ is_hot) {
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n2) return;
-    const uint32_t h = key1_sorted[q] >> 8;
-    is_hot[order1[q]] = (q - gofs[h]) < take[h] ? cls : 0;      // 1 = staged for every block, 2 = for blocks of its own neighbourhood (LOCAL)
+    const uint32_t h = key1_sorted[q] >> 8, r = q - gofs[h];
+    // 1 = staged for every block, 2 = for blocks of its own neighbourhood (LOCAL layout: behind the common prefix)
+    is_hot[order1[q]] = r < take[h] ? ((take_common && r >= take_common[h]) ? 2 : 1) : 0;
 }
 // key of the second order: (group, hot part first, hot-list length desc); values keep the first order
 __global__ void key2_kernel(uint32_t n2, const uint32_t* __restrict__ key1_sorted, const uint32_t* __restrict__ order1,
-                            const uint32_t* __restrict__ gofs, const uint32_t* __restrict__ take, const uint32_t* __restrict__ nsh,
-                            const uint32_t* __restrict__ nnh, uint32_t* __restrict__ key2) {
+                            const uint32_t* __restrict__ gofs, const uint32_t* __restrict__ take, const uint32_t* __restrict__ take_common,
+                            const uint32_t* __restrict__ nsh, const uint32_t* __restrict__ nnh, uint32_t* __restrict__ key2) {
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n2) return;
-    const uint32_t h = key1_sorted[q] >> 8, e = order1[q];
-    const uint32_t part = (q - gofs[h]) < take[h] ? 0u : 1u;
-    key2[q] = (2u * h + part) << 8 | (kHubDegree - (nsh[e] + nnh[e]));
+    const uint32_t h = key1_sorted[q] >> 8, e = order1[q], r = q - gofs[h];
+    // three pieces per group, each ordered by hot-list length: common prefix | rest of the staged prefix | never staged
+    const uint32_t part = r < take[h] ? ((take_common && r >= take_common[h]) ? 1u : 0u) : 2u;
+    key2[q] = (4u * h + part) << 8 | (kHubDegree - (nsh[e] + nnh[e]));
 }
 // compact position q of the second order -> internal slot gstart[h] + (q - gofs[h])
 __global__ void place_agents_kernel(uint32_t n2, const uint32_t* __restrict__ key2_sorted, const uint32_t* __restrict__ order2,
                                     const uint32_t* __restrict__ gofs, const uint32_t* __restrict__ gstart, uint32_t* __restrict__ int2ext) {
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n2) return;
-    const uint32_t h = key2_sorted[q] >> 9;
+    const uint32_t h = key2_sorted[q] >> 10;
     int2ext[gstart[h] + (q - gofs[h])] = order2[q];
 }
 // one warp per SELL slice: K = longest hot list, Kc = longest cold list of its 32 agents

@@ -82,6 +82,7 @@ struct Graph {
     GraphLayout L;                 // host copy: permutation, sizes (code arrays are released after upload)
     DevBuf deg, ranges, hub_off, hub_deg, hub_codes, hub_units, hub_unit_begin, sell_meta, sell_codes, int2ext, nb_slice_begin;
     const void* key[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // caller pointers it was built from
+    uint32_t common_words = 0;     // words of the staged vector every block copies (layout.h)
 };
 
 struct Replica {
@@ -754,10 +755,10 @@ int mvbx_compare_layout_with_host(mvb_sim* s, uint32_t r, const mvb_population* 
     GraphLayout H;
     uint32_t capacity = staged_capacity_agents(s->vec_cap_words);
     if (const char* e = getenv("MVB_STAGE_AGENTS")) capacity = std::min<uint32_t>(capacity, std::max(64, atoi(e)) / 64 * 64);
-    if (build_graph_layout(*pop, rp.H, capacity, H)) return -2;
+    if (build_graph_layout(*pop, rp.H, capacity, H, (uint32_t)s->reps.size())) return -2;
     const GraphLayout& L = g.L;
     if (H.N_pad != L.N_pad || H.n_hub_slices != L.n_hub_slices || H.n_sell_slices != L.n_sell_slices || H.hot_words != L.hot_words) return say("sizes", 0);
-    if (H.ranges.size() != L.ranges.size()) return say("range count", 0);
+    if (H.ranges.size() != L.ranges.size() || H.n_common_ranges != L.n_common_ranges || H.mode != L.mode) return say("range count / layout mode", 0);
     for (size_t k = 0; k < H.ranges.size(); ++k)
         if (memcmp(&H.ranges[k], &L.ranges[k], 12)) return say("ranges", k);
     auto fetch = [&](const DevBuf& b, size_t bytes) { std::vector<char> v(bytes); cudaMemcpy(v.data(), b.p, bytes, cudaMemcpyDeviceToHost); return v; };

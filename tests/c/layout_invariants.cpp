@@ -64,22 +64,30 @@ int main(int argc, char** argv) {
     std::vector<uint8_t> hot_slot(L.N_pad, 0);            // 1 = staged for every block, 2 = for blocks of its own neighbourhood
     const bool local = L.mode == kLayoutLocal;
     if (local) {
-        CHECK(L.ranges.size() == (size_t)H + 1 && L.ranges[0].src_word == 0 && L.ranges[0].dst_word == 0, "local ranges");
+        // [0] hub region, [1 + h] common prefix of group h (staged by every block), [1 + H + h] the piece only blocks of h stage
+        CHECK(L.ranges.size() == 2 * (size_t)H + 1 && L.n_common_ranges == H + 1 && L.ranges[0].src_word == 0 && L.ranges[0].dst_word == 0, "local ranges");
         CHECK(L.ranges[0].n_words * 16 <= L.n_hub_slices * 32, "hub region");
-        uint32_t longest = 0;
         for (uint32_t t = 0; t < L.ranges[0].n_words * 16; ++t) hot_slot[t] = 1;
+        uint32_t common = L.ranges[0].n_words, longest = 0;
         for (uint32_t h = 0; h < H; ++h) {
             const StageRange& r = L.ranges[1 + h];
-            CHECK(r.n_words % 4 == 0 && r.dst_word == L.ranges[0].n_words, "local range geometry");
-            CHECK(((uint64_t)L.ranges[0].n_words + r.n_words) * 16 <= cap, "neighbourhood %u stages more than fits", h);
-            CHECK(r.src_word * 16 >= L.n_hub_slices * 32 && (r.src_word * 16 - L.n_hub_slices * 32) / 32 == L.nb_slice_begin[h], "local range start");
+            CHECK(r.n_words % 4 == 0 && r.dst_word == common, "common range geometry");
+            CHECK((r.src_word * 16 - L.n_hub_slices * 32) / 32 == L.nb_slice_begin[h] || r.n_words == 0, "common range start");
+            for (uint32_t t = r.src_word * 16; t < (r.src_word + r.n_words) * 16; ++t) { CHECK(L.int2ext[t] != kInvalid, "padding in a common prefix"); hot_slot[t] = 1; }
+            common += r.n_words;
+        }
+        for (uint32_t h = 0; h < H; ++h) {
+            const StageRange& r = L.ranges[1 + H + h];
+            CHECK(r.n_words % 4 == 0 && r.dst_word == common, "own range geometry");
+            CHECK(((uint64_t)common + r.n_words) * 16 <= cap, "neighbourhood %u stages more than fits", h);
+            CHECK(r.src_word == L.ranges[1 + h].src_word + L.ranges[1 + h].n_words, "own piece follows the common prefix");
             for (uint32_t t = r.src_word * 16; t < (r.src_word + r.n_words) * 16; ++t) {
-                CHECK(t < L.N_pad && (t - L.n_hub_slices * 32) / 32 < L.nb_slice_begin[h + 1], "local range end");
+                CHECK(t < L.N_pad && (t - L.n_hub_slices * 32) / 32 < L.nb_slice_begin[h + 1], "own range end");
                 if (L.int2ext[t] != kInvalid) hot_slot[t] = 2;
             }
             longest = std::max(longest, r.n_words);
         }
-        CHECK(L.hot_words == L.ranges[0].n_words + longest, "hot_words");
+        CHECK(L.hot_words == common + longest, "hot_words");
     } else {
         uint32_t staged = 0, prev_end = 0;
         for (const StageRange& r : L.ranges) {
@@ -101,7 +109,7 @@ int main(int argc, char** argv) {
         n_hot += hot;
         uint32_t pos = s;
         if (hot && !local) for (const StageRange& r : L.ranges) if (s >= r.src_word * 16 && s < (r.src_word + r.n_words) * 16) pos = r.dst_word * 16 + (s - r.src_word * 16);
-        if (hot_slot[s] == 2) { const StageRange& r = L.ranges[1 + pop.neighbourhood[e]]; pos = r.dst_word * 16 + (s - r.src_word * 16); }
+        if (local && hot && s >= L.n_hub_slices * 32) { const StageRange& r = L.ranges[(hot_slot[s] == 2 ? 1 + H : 1) + pop.neighbourhood[e]]; pos = r.dst_word * 16 + (s - r.src_word * 16); }
         CHECK(word == pos / 16 && shift == 30 - 2 * (pos % 16), "code of agent %u: word %u shift %u for position %u", e, word, shift, pos);
         if (local) CHECK(L.tcold[e] == ((s >> 4) << 7 | (30u - 2u * (s & 15u))), "cold code of agent %u", e);
     }

@@ -164,3 +164,22 @@ def test_device_resident_population_runs_like_its_host_copy():
         do, ro = o.run(w)
         assert np.array_equal(ra[0], ro)
         assert_state_equal(a.get_state(0), o.get_state(), "device-resident population")
+
+
+def test_batch_mixing_staging_layouts_equals_oracle(stage_env):
+    """One launch stepping a partly staged population (LOCAL layout: common set + own neighbourhood piece) next to populations
+    that fit shared memory whole (GLOBAL layout): every replica equals its own oracle run."""
+    stage_env(2048)
+    pops = [mb.synth_population(15000, 4, 6, 5, 10, seed=31), mb.synth_population(900, 3, 4, 4, 6, seed=32),
+            mb.synth_population(9000, 2, 12, 5, 10, seed=33)]
+    tabs = [mb.synth_tables(4, 6, 15000, seed=31), mb.synth_tables(3, 4, 900, seed=32), mb.synth_tables(2, 12, 9000, seed=33)]
+    w = mb.weather_pattern(45, seed=31)
+    with mb.Simulation(pops, tabs, mb.make_params()) as g:
+        for r in range(3):
+            compare_with_host(g, pops[r], r)
+        days, rows = g.run(w)
+        for r in range(3):
+            o = OracleSimulation(pops[r], tabs[r], mb.make_params())
+            d2, r2 = o.run(w)
+            assert np.array_equal(rows[r], r2), f"replica {r}"
+            assert_state_equal(g.get_state(r), o.get_state(), f"replica {r}")
