@@ -345,8 +345,15 @@ day_kernel(const __grid_constant__ RepArray reps, uint32_t R, uint32_t P, uint32
     uint32_t* s_next = s_tail + 2;                    // work-item counter of the current part
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 
+    // Programmatic dependent launch (the on-device face of the day loop, simulation.rs:101-136): tomorrow's launch may
+    // start its blocks as soon as every block of today's has passed this line and an SM is free, i.e. while today's last
+    // blocks still run.  Tomorrow's blocks do everything that does not depend on today (barrier set-up, static tables, their
+    // first slice records, L2 prefetches of link codes) and then wait at griddepcontrol.wait (below) for today to be
+    // complete and visible.  Without the launch attribute both instructions are no-ops.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (tid == 0) { mbar_init(s_bar, 1); s_vec[vec_cap_words - 1] = 0; }   // the word padding codes point at (pad_code)
     uint32_t phase = 0;
+    bool first_part = true;
 
     for (uint32_t part = blockIdx.x; part < R * P; part += gridDim.x) {
         const uint32_t p = part % P;
@@ -368,26 +375,6 @@ day_kernel(const __grid_constant__ RepArray reps, uint32_t R, uint32_t P, uint32
             nb_part = pt.x; q = pt.y; Q = pt.z;
             sell_b = max(sell_b, r.nb_slice_begin[nb_part]); sell_e = max(sell_b, min(sell_e, r.nb_slice_begin[nb_part + 1]));
         }
-        if (tid == 0) {                               // 1. stage yesterday's modes (TMA bulk copies)
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            // the ranges every block stages, then (LOCAL layout) the piece of this part's own neighbourhood behind them
-            const uint32_t n_stage = r.n_ranges + (r.local_mode ? 1u : 0u);
-            const StageRange own = r.local_mode ? r.ranges[r.n_ranges + nb_part] : StageRange{0, 0, 0, 0};
-            mbar_expect_tx(s_bar, (r.hot_words + own.n_words) * 4u);
-            for (uint32_t k = 0; k < n_stage; ++k) {
-                const StageRange g = k < r.n_ranges ? r.ranges[k] : own;
-                for (uint32_t o = 0; o < g.n_words; o += 16384) {          // <= 64 KB per copy
-                    const uint32_t n = min(g.n_words - o, 16384u);
-                    bulk_g2s(s_vec + g.dst_word + o, g_vec + g.src_word + o, n * 4u, s_bar);
-                }
-            }
-            *s_next = 0;
-        }
-        for (uint32_t k = tid; k < 4 * H; k += THREADS) {                 // neighbourhood.rs:57-89
-            const float c = congestion_entry(rec_prev[r.rec_off + k], r.cap[k], r.nres[k >> 2]);
-            s_cong[k] = c;
-            if (p == 0) r.cong[k] = c;
-        }
         for (uint32_t k = tid; k < 12 * H; k += THREADS) {                // agent.rs:185-196
             const uint32_t hh = k / 12, c = (k >> 2) % 3, m = k & 3;
             s_cost[k] = cost_base_entry(r.supp[4 * hh + m], c, m);
@@ -400,6 +387,31 @@ day_kernel(const __grid_constant__ RepArray reps, uint32_t R, uint32_t P, uint32
             if (c == 2u) { cc[2] = __int_as_float(0x7f800000); cc[3] = cc[2]; }
             s_crank[k] = cost_ranks(cc);
         }
+        // 1. stage yesterday's modes (TMA bulk copies) and build the congestion table from yesterday's histogram.  A block's
+        // FIRST part does this further down, after griddepcontrol.wait: until then only launch-independent data is touched.
+        auto stage_and_congestion = [&]() {
+            if (tid == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                // the ranges every block stages, then (LOCAL layout) the piece of this part's own neighbourhood behind them
+                const uint32_t n_stage = r.n_ranges + (r.local_mode ? 1u : 0u);
+                const StageRange own = r.local_mode ? r.ranges[r.n_ranges + nb_part] : StageRange{0, 0, 0, 0};
+                mbar_expect_tx(s_bar, (r.hot_words + own.n_words) * 4u);
+                for (uint32_t k = 0; k < n_stage; ++k) {
+                    const StageRange g = k < r.n_ranges ? r.ranges[k] : own;
+                    for (uint32_t o = 0; o < g.n_words; o += 16384) {          // <= 64 KB per copy
+                        const uint32_t n = min(g.n_words - o, 16384u);
+                        bulk_g2s(s_vec + g.dst_word + o, g_vec + g.src_word + o, n * 4u, s_bar);
+                    }
+                }
+            }
+            for (uint32_t k = tid; k < 4 * H; k += THREADS) {                 // neighbourhood.rs:57-89
+                const float c = congestion_entry(rec_prev[r.rec_off + k], r.cap[k], r.nres[k >> 2]);
+                s_cong[k] = c;                                                // (read after the block barrier that ends the hub phase)
+                if (p == 0) r.cong[k] = c;
+            }
+        };
+        if (tid == 0) *s_next = 0;
+        if (!first_part) stage_and_congestion();
         for (uint32_t k = tid; k < 4 * S; k += THREADS) s_des[k] = r.desir[k];
         for (uint32_t k = tid; k < rec_width(S, H); k += THREADS) s_rec[k] = 0;
         __syncthreads();
@@ -464,6 +476,11 @@ day_kernel(const __grid_constant__ RepArray reps, uint32_t R, uint32_t P, uint32
         }
         uint4 unit0 = load_unit(), unit1 = load_unit();
         prefetch_unit(unit0);
+        if (first_part) {                             // everything from here on reads what yesterday's launch wrote
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            stage_and_congestion();
+            first_part = false;
+        }
         mbar_wait(s_bar, phase);
         phase ^= 1u;
 

@@ -247,8 +247,18 @@ int launch_day(mvb_sim* s, uint8_t weather, uint8_t changed) {
     AgentWeights uw{s->prm.consistency, s->prm.social_connectivity, s->prm.subculture_connectivity,
                     s->prm.neighbourhood_connectivity, s->prm.average_weight};
     // replica descriptors travel as kernel parameters, kMaxRepsPerLaunch at a time
-#define MVB_LAUNCH(PA, T, G) day_kernel<PA, T, G><<<s->grid, T, s->smem_bytes, s->stream>>>( \
-        s->rep_args[c], R, P, s->parity, prev, next, weather, changed, uw, s->vec_cap_words)
+    // Programmatic dependent launch: the next weekday's blocks may start (and run their day-independent prologue) while
+    // this one's last blocks finish; the kernel waits with griddepcontrol.wait before it touches anything a previous
+    // launch wrote (day_kernels.cuh).  Not in the agent-partitioned mode, where NCCL kernels sit between the days.
+    static const bool no_pdl = getenv("MVB_NO_PDL") != nullptr;
+    cudaLaunchAttribute pdl_attr[1];
+    pdl_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    pdl_attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(s->grid); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = s->smem_bytes; cfg.stream = s->stream;
+    cfg.attrs = pdl_attr; cfg.numAttrs = (s->world == 1 && !no_pdl) ? 1 : 0;
+#define MVB_LAUNCH(PA, T, G) MVB_CUDA(cudaLaunchKernelEx(&cfg, day_kernel<PA, T, G>, s->rep_args[c], R, P, s->parity, prev, (uint32_t*)next, \
+        (uint32_t)weather, (uint32_t)changed, uw, s->vec_cap_words))
     for (size_t c = 0; c < s->rep_args.size(); ++c) {
         const uint32_t R = std::min<uint32_t>(kMaxRepsPerLaunch, (uint32_t)s->reps.size() - (uint32_t)c * kMaxRepsPerLaunch);
         const uint32_t P = s->local_P[c] ? s->local_P[c] : choose_parts(s, (uint32_t)c * kMaxRepsPerLaunch, R);
