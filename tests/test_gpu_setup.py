@@ -183,3 +183,37 @@ def test_batch_mixing_staging_layouts_equals_oracle(stage_env):
             d2, r2 = o.run(w)
             assert np.array_equal(rows[r], r2), f"replica {r}"
             assert_state_equal(g.get_state(r), o.get_state(), f"replica {r}")
+
+
+def test_many_neighbourhoods_local_layout_equals_oracle(stage_env):
+    """LOCAL layout with more neighbourhoods than a launch would otherwise have parts (H = 40), hubs included."""
+    stage_env(4096, "local")
+    n = 30000
+    pop = mb.synth_population(n, 3, 40, 5, 10, seed=41)
+    tab = mb.synth_tables(3, 40, n, seed=41)
+    w = mb.weather_pattern(25, seed=41)
+    with mb.Simulation(pop, tab, mb.make_params()) as g:
+        compare_with_host(g, pop)
+        days, rows = g.run(w)
+        o = OracleSimulation(pop, tab, mb.make_params())
+        d2, r2 = o.run(w)
+        assert np.array_equal(rows[0], r2)
+        assert_state_equal(g.get_state(0), o.get_state(), "H = 40, LOCAL layout")
+
+
+def test_more_replicas_than_one_launch_holds():
+    """70 replicas = two launches per weekday (64 replica descriptors fit the kernel parameters), chained by programmatic
+    dependent launch like the weekdays themselves: every replica equals its own oracle run."""
+    R, n = 70, 1500
+    pops = [mb.synth_population(n, 3, 4, 4, 6, seed=100 + r) for r in range(R)]
+    tabs = [mb.synth_tables(3, 4, n, seed=100 + r) for r in range(R)]
+    w = mb.weather_pattern(20, seed=9)
+    with mb.Simulation(pops, tabs, mb.make_params()) as g:
+        days, rows = g.run(w)
+        ms, launches = g.last_run_stats()
+        assert launches == 2 * (len(days) - 1)
+        for r in (0, 1, 63, 64, 69):
+            o = OracleSimulation(pops[r], tabs[r], mb.make_params())
+            d2, r2 = o.run(w)
+            assert np.array_equal(rows[r], r2), f"replica {r}"
+            assert_state_equal(g.get_state(r), o.get_state(), f"replica {r}")
