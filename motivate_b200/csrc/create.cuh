@@ -664,7 +664,7 @@ static int create_impl(uint32_t R, const mvb_population* const* pops, const mvb_
     if (s->census_smem > 48 * 1024)
         MVB_CUDA(cudaFuncSetAttribute(census_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->census_smem));
     s->rank = rank; s->world = world;
-    if (world > 1) {
+    if (world > 1 && !getenv("MVB_DEBUG_NO_EXCHANGE")) {      // (the debug switch lets ONE process time any rank's share of the work)
         Nccl* n = nccl();
         if (!n) { set_error("agent-partitioned mode needs NCCL (libnccl.so.2 could not be loaded: %s)", dlerror()); return MVB_ERR_COMM; }
         ncclUniqueId id;
@@ -699,11 +699,21 @@ static int create_impl(uint32_t R, const mvb_population* const* pops, const mvb_
                 const RepDev& d = s->h_reps[r];
                 if (!d.local_mode) continue;
                 const std::vector<uint32_t>& nb = s->reps[r].graph->L.nb_slice_begin;
-                std::vector<uint32_t> n_h(d.H), Q(d.H, 0);
+                // share of a neighbourhood = modelled work of the slices of it this rank updates (the slice dimensions are on the
+                // host in the agent-partitioned mode, where ranges cut through neighbourhoods and a neighbourhood's first
+                // slices cost far less than its last, cold-heavy ones); whole neighbourhoods: their slice counts
+                const GraphLayout& GL = s->reps[r].graph->L;
+                std::vector<uint64_t> n_h(d.H);
+                std::vector<uint32_t> Q(d.H, 0);
                 uint64_t total = 0;
                 for (uint32_t h = 0; h < d.H; ++h) {
                     const uint32_t b = std::max(nb[h], d.sell_begin), e = std::min(nb[h + 1], d.sell_end);
-                    n_h[h] = e > b ? e - b : 0; total += n_h[h];
+                    n_h[h] = 0;
+                    if (e > b) {
+                        if (GL.sell_K.size() == GL.n_sell_slices) for (uint32_t k = b; k < e; ++k) n_h[h] += sell_slice_work(GL, k);
+                        else n_h[h] = e - b;
+                    }
+                    total += n_h[h];
                 }
                 uint32_t used = 0;
                 for (uint32_t h = 0; h < d.H; ++h)

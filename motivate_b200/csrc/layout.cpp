@@ -383,27 +383,43 @@ int build_graph_layout(const mvb_population& pop, uint32_t H, uint32_t capacity_
     return layout_finish(pop, W, L, true);
 }
 
+namespace {
+// Work model, in units of one shared-memory gather.  A link read from L2 costs about 2 of them when few links are cold
+// (GLOBAL layout on populations just above the shared-memory capacity) and about 8 in the LOCAL layout, where a third of
+// the links are cold gathers and the L2 gather path (~0.4 per clock per SM against ~3.4 from shared memory) sets the
+// pace; + per-agent work; a hub's links are walked in a phase of their own, between two block barriers (x 2.5 GLOBAL,
+// calibrated on 8M agents over 2 B200s; x 1.5 LOCAL).  LOCAL values from tools/partition_balance.py (every rank's share
+// of 50M agents timed on one GPU for a grid of weights): 8 ranks, H = 10: 1.16-1.20 ms per rank with these values
+// (0.83-1.71 with the GLOBAL ones), H = 64: 0.73-0.79 ms (0.66-1.10).  The same model hands every neighbourhood its share
+// of a rank's parts (create.cuh): a neighbourhood's last, cold-heavy slices cost several times its first ones.
+struct WorkModel { uint64_t cold, per_agent, hub10; };
+WorkModel work_model(const GraphLayout& L) {
+    WorkModel m = L.mode == kLayoutLocal ? WorkModel{8, 40, 15} : WorkModel{2, 64, 25};
+    if (const char* e = getenv("MVB_PART_COLD")) m.cold = (uint64_t)atoi(e);          // calibration experiments
+    if (const char* e = getenv("MVB_PART_AGENT")) m.per_agent = (uint64_t)atoi(e);
+    if (const char* e = getenv("MVB_PART_HUB10")) m.hub10 = (uint64_t)atoi(e);
+    return m;
+}
+}  // namespace
+
+uint64_t sell_slice_work(const GraphLayout& L, uint32_t s) {
+    const WorkModel m = work_model(L);
+    return 32ull * ((L.sell_K[s] & 0xFFFFu) + m.cold * (L.sell_K[s] >> 16) + m.per_agent);
+}
+
 void partition_slices(const GraphLayout& L, uint32_t world, std::vector<uint32_t>& bounds) {
     const uint32_t n = L.n_hub_slices + L.n_sell_slices;
     std::vector<uint64_t> work(n);
-    // Work model, in units of one shared-memory gather.  A link read from L2 costs about 2 of them when few links are
-    // cold (GLOBAL layout on populations just above the shared-memory capacity) and about 4 in the LOCAL layout, where a
-    // third of the links are cold gathers (calibrated on 12M agents over 2 B200s with MVB_DEBUG_NO_EXCHANGE: the two ranks'
-    // kernels then take 0.65 and 0.62 ms; with weight 8 0.59 and 0.69); + per-agent work; a hub's links are walked in a
-    // phase of their own, between two block barriers (x 2.5, calibrated on 8M agents over 2 B200s).
-    uint64_t cold = L.mode == kLayoutLocal ? 4 : 2, per_agent = L.mode == kLayoutLocal ? 40 : 64;
-    if (const char* e = getenv("MVB_PART_COLD")) cold = (uint64_t)atoi(e);          // calibration experiments
-    if (const char* e = getenv("MVB_PART_AGENT")) per_agent = (uint64_t)atoi(e);
+    const WorkModel m = work_model(L);
     for (uint32_t hs = 0; hs < L.n_hub_slices; ++hs) {
         uint64_t w = 0;
         for (uint32_t k = 0; k < 32; ++k) {
             const uint32_t* dg = &L.hub_deg[(size_t)4 * (hs * 32 + k)];
-            w += 5ull * ((uint64_t)dg[0] + dg[1] + cold * (dg[2] + dg[3])) / 2 + per_agent;
+            w += m.hub10 * ((uint64_t)dg[0] + dg[1] + m.cold * (dg[2] + dg[3])) / 10 + m.per_agent;
         }
         work[hs] = w;
     }
-    for (uint32_t s = 0; s < L.n_sell_slices; ++s)
-        work[L.n_hub_slices + s] = 32ull * ((L.sell_K[s] & 0xFFFFu) + cold * (L.sell_K[s] >> 16) + per_agent);
+    for (uint32_t s = 0; s < L.n_sell_slices; ++s) work[L.n_hub_slices + s] = sell_slice_work(L, s);
     uint64_t total = 0;
     for (uint64_t w : work) total += w;
     bounds.assign(world + 1, n);

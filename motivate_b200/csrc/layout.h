@@ -178,5 +178,7 @@ int build_graph_layout(const mvb_population& pop, uint32_t n_neighbourhoods, uin
 // contiguous ranges of about equal link count.  bounds[r] .. bounds[r+1] are rank r's slices (global slice index:
 // hub slice hs -> hs, SELL slice s -> n_hub_slices + s); bounds has world + 1 entries.
 void partition_slices(const GraphLayout& L, uint32_t world, std::vector<uint32_t>& bounds);
+// The work model behind it: modelled cost of SELL slice s (needs L.sell_K) in units of one shared-memory gather.
+uint64_t sell_slice_work(const GraphLayout& L, uint32_t s);
 
 }  // namespace mvb
