@@ -226,11 +226,12 @@ uint64_t mvb_algorithmic_bytes_per_day(const mvb_sim* sim, uint32_t replica);
  * BASELINE config 4 / SURVEY.md §8e: the reference cannot do this (one replica is single-threaded,
  * src/simulation.rs:64); it is the "number_of_people" axis scaled over GPUs.  One process per GPU.  Every rank
  * passes the SAME population and tables; the library cuts the agents into `world` contiguous ranges of its internal
- * order, balanced by link count, and each rank updates its own agents.  After every weekday the ranks exchange, over
- * NCCL, the packed 2-bit current_mode / norm words they own (the social network is global, src/simulation.rs:160:
- * tomorrow every rank needs every agent's mode) and all-reduce the day's counters (hist + statistics).  Afterwards
- * every rank holds the full mode / norm vectors and identical statistics rows; habits are current only for the agents
- * a rank owns (mvb_partition_owner).  All other entry points (mvb_step, mvb_run, mvb_set_*, mvb_get_state, ...) work
+ * order, balanced by modelled work, and each rank updates its own agents (and stores the link codes of those only).
+ * After every weekday the ranks exchange, over NCCL, the packed 2-bit current_mode words they own in ONE all-gather (the
+ * social network is global, src/simulation.rs:160: tomorrow every rank needs every agent's mode) and all-reduce the
+ * day's counters (hist + statistics); the norm words, which no other agent's update reads, travel with the last weekday
+ * of a mvb_run / mvb_run_async call (and with every mvb_step).  Afterwards every rank holds the full mode / norm
+ * vectors and identical statistics rows; habits are current only for the agents a rank owns (mvb_partition_owner).  All other entry points (mvb_step, mvb_run, mvb_set_*, mvb_get_state, ...) work
  * as for a one-replica handle and must be called by all ranks in the same order. */
 #define MVB_UNIQUE_ID_BYTES 128
 /* Rank 0 calls this and hands the 128 bytes to the other ranks (file, socket, torch.distributed broadcast ...). */

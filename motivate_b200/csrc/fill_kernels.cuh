@@ -230,18 +230,18 @@ __global__ void set_ownership_kernel(const uint32_t* int2ext, uint32_t N_pad, co
 __global__ void pack_exchange_kernel(const uint2* __restrict__ vec, const uint2* __restrict__ normvec, uint32_t b, uint32_t e, uint32_t M,
                                      uint2* __restrict__ send) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b + k < e) { send[k] = vec[b + k]; send[M + k] = normvec[b + k]; }
+    if (b + k < e) { send[k] = vec[b + k]; if (normvec) send[M + k] = normvec[b + k]; }
 }
 __global__ void unpack_exchange_kernel(const uint2* __restrict__ recv, const uint32_t* __restrict__ bounds, uint32_t world, uint32_t rank,
-                                       uint32_t M, uint32_t n_slices, uint2* __restrict__ vec, uint2* __restrict__ normvec) {
+                                       uint32_t M, uint32_t piece, uint32_t n_slices, uint2* __restrict__ vec, uint2* __restrict__ normvec) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_slices) return;
     uint32_t r = 0;
     while (r + 1 < world && bounds[r + 1] <= s) ++r;
     if (r == rank) return;
-    const uint2* piece = recv + (size_t)r * 2 * M;
-    vec[s] = piece[s - bounds[r]];
-    normvec[s] = piece[M + (s - bounds[r])];
+    const uint2* p = recv + (size_t)r * piece;             // rank r's piece: [M mode words | M norm words (if sent)]
+    vec[s] = p[s - bounds[r]];
+    if (normvec) normvec[s] = p[M + (s - bounds[r])];
 }
 
 // `intervene` (simulation.rs:304-464) as ONE launch for every replica whose intervention falls on the day: the host

@@ -239,7 +239,9 @@ uint32_t choose_parts(const mvb_sim* s, uint32_t first_rep, uint32_t R) {
     return best;
 }
 
-int launch_day(mvb_sim* s, uint8_t weather, uint8_t changed) {
+// with_norms (agent-partitioned mode): also exchange the norm words.  No rank's update reads another agent's norm
+// (statistics.rs counts each agent's own), so a run sends them once, with its last weekday, not every day.
+int launch_day(mvb_sim* s, uint8_t weather, uint8_t changed, bool with_norms = true) {
     int rc = ensure_rows(s, 1);
     if (rc) return rc;
     const uint32_t* prev = s->rec.as<uint32_t>() + (size_t)s->cursor * s->rec_stride;
@@ -277,20 +279,21 @@ int launch_day(mvb_sim* s, uint8_t weather, uint8_t changed) {
     if (s->world > 1 && !skip_exchange) {
         // agent-partitioned: every rank now holds new modes / norms for its own slices and a partial record.  The
         // social network is global (simulation.rs:160), so tomorrow every rank needs everybody's modes: ONE all-gather
-        // of the packed 2-bit words (each rank's piece: its mode words, then its norm words, padded to the longest
-        // range) and ONE all-reduce of the day's counters.
+        // of the packed 2-bit words (each rank's piece: its mode words, padded to the longest range, and on the last
+        // weekday of a run its norm words behind them) and ONE all-reduce of the day's counters.
         Replica& rp = s->reps[0];
         Nccl* n = nccl();
         uint2* vec_next = rp.vec[s->parity ^ 1u].as<uint2>();
         uint2* normvec = rp.normvec.as<uint2>();
         const uint32_t M = s->xchg_words;
-        uint2* send = s->xchg.as<uint2>() + (size_t)s->rank * 2 * M;
+        const uint32_t piece = with_norms ? 2 * M : M;               // u64 words per rank in the all-gather buffer
+        uint2* send = s->xchg.as<uint2>() + (size_t)s->rank * piece;
         const uint32_t n_slices = s->bounds[s->world];
         pack_exchange_kernel<<<(s->bounds[s->rank + 1] - s->bounds[s->rank] + 255) / 256, 256, 0, s->stream>>>(
-            vec_next, normvec, s->bounds[s->rank], s->bounds[s->rank + 1], M, send);
-        MVB_NCCL(n->AllGather(send, s->xchg.p, (size_t)2 * M * sizeof(uint2), ncclUint8, s->comm, s->stream));      // in place
-        unpack_exchange_kernel<<<(n_slices + 255) / 256, 256, 0, s->stream>>>(s->xchg.as<uint2>(), s->d_bounds.as<uint32_t>(), s->world, s->rank, M,
-                                                                            n_slices, vec_next, normvec);
+            vec_next, with_norms ? normvec : nullptr, s->bounds[s->rank], s->bounds[s->rank + 1], M, send);
+        MVB_NCCL(n->AllGather(send, s->xchg.p, (size_t)piece * sizeof(uint2), ncclUint8, s->comm, s->stream));      // in place
+        unpack_exchange_kernel<<<(n_slices + 255) / 256, 256, 0, s->stream>>>(s->xchg.as<uint2>(), s->d_bounds.as<uint32_t>(), s->world, s->rank, M, piece,
+                                                                            n_slices, vec_next, with_norms ? normvec : nullptr);
         MVB_CUDA(cudaGetLastError());
         MVB_NCCL(n->AllReduce(next, next, s->rec_stride, ncclUint32, ncclSum, s->comm, s->stream));
     }
@@ -621,6 +624,8 @@ int mvb_run_async(mvb_sim* s, const uint8_t* weather, uint32_t first_day, uint32
         d_ivs = reinterpret_cast<const IvDev*>(d + list_at);
     }
     s->last_launches = 0;
+    uint32_t last_weekday = 0;
+    for (uint32_t d = d0; d < end_day; ++d) if (d % 7 < 5) last_weekday = d;
     MVB_CUDA(cudaEventRecord(s->ev0, s->stream));
     size_t next_fire = 0;
     for (uint32_t day = d0; day < end_day; ++day) {
@@ -637,7 +642,7 @@ int mvb_run_async(mvb_sim* s, const uint8_t* weather, uint32_t first_day, uint32
         if (day % 7 < 5) {                                                  // simulation.rs:108, 297-299
             const uint8_t w = weather[day];
             if (w > 1) { set_error("weather[%u] = %u is not a weather code", day, w); return MVB_ERR_ARG; }
-            if ((rc = launch_day(s, w, (uint8_t)(s->prev_weather != w)))) return rc;   // :113-128
+            if ((rc = launch_day(s, w, (uint8_t)(s->prev_weather != w), day == last_weekday))) return rc;   // :113-128
             s->prev_weather = w;                                            // :131
             s->row_days.push_back(day);
         }
