@@ -332,6 +332,20 @@ __device__ __forceinline__ void finish_slice(const RepDev& r, uint32_t slice, ui
     if (++st.n == 255) flush_stats(lane, r.H, r.S, s_rec, st);
 }
 
+// Debug (mvbx_launch_stamps, tools/launch_gaps.py): {start of the first block, end of the last block} per launch, in ns.
+// The slot of a launch follows from the record row it writes, so the kernel needs no extra parameter (one would cost a
+// register for the whole kernel); g_stamps.slots is null unless the hook has been called.
+struct StampCfg { unsigned long long* slots; const uint32_t* rec_base; uint32_t rec_stride, first_row, n; };
+__device__ StampCfg g_stamps = {nullptr, nullptr, 0, 0, 0};
+__device__ __noinline__ void stamp_launch(const uint32_t* rec_next, int end) {
+    const StampCfg c = g_stamps;
+    const uint32_t row = (uint32_t)((rec_next - c.rec_base) / c.rec_stride);
+    if (row < c.first_row || row - c.first_row >= c.n) return;
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (end) atomicMax(&c.slots[2 * (size_t)(row - c.first_row) + 1], t); else atomicMin(&c.slots[2 * (size_t)(row - c.first_row)], t);
+}
+
 // ---- the weekday kernel ----------------------------------------------------------------------------
 template <bool PER_AGENT, int THREADS, uint32_t G>
 __global__ void __launch_bounds__(THREADS, 1)
@@ -351,6 +365,7 @@ day_kernel(const __grid_constant__ RepArray reps, uint32_t R, uint32_t P, uint32
     // first slice records, L2 prefetches of link codes) and then wait at griddepcontrol.wait (below) for today to be
     // complete and visible.  Without the launch attribute both instructions are no-ops.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (tid == 0 && g_stamps.slots) stamp_launch(rec_next, 0);     // debug (tools/launch_gaps.py): when this launch's first block started
     if (tid == 0) { mbar_init(s_bar, 1); s_vec[vec_cap_words - 1] = 0; }   // the word padding codes point at (pad_code)
     uint32_t phase = 0;
     bool first_part = true;
@@ -569,6 +584,7 @@ day_kernel(const __grid_constant__ RepArray reps, uint32_t R, uint32_t P, uint32
         for (uint32_t k = tid; k < rec_width(S, H); k += THREADS)
             if (s_rec[k]) atomicAdd(&rec_next[r.rec_off + k], s_rec[k]);
     }
+    if (tid == 0 && g_stamps.slots) stamp_launch(rec_next, 1);     // ... and when its last block ended
 }
 
 // Census of the current state: fills one record row (day-0 row, mvb_stats_row).  Runs once per create.

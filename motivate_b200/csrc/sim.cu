@@ -170,6 +170,8 @@ struct mvb_sim {
     ncclComm_t comm = nullptr;
     std::vector<uint32_t> bounds;        // [world+1] global slice index where each rank's range starts
     uint32_t own[4] = {0, 0, 0, 0};      // this rank's hub slices [0],[1]) and SELL slices [2],[3])
+    DevBuf stamps;                       // debug (MVB_DEBUG_STAMPS): {first block start, last block end} in ns per day-kernel launch
+    uint32_t stamp_first = 0, stamp_cap = 0;
     DevBuf xchg, d_bounds;               // exchange buffer [world][2][xchg_words] u64 words (modes, norms); bounds on the device
     uint32_t xchg_words = 0;             // longest rank range, in slices
     // interventions of the current run, staged before the day loop (apply_interventions_kernel)
@@ -756,6 +758,30 @@ int mvb_get_state(mvb_sim* s, uint32_t r, float* habit, uint8_t* cur, uint8_t* l
                                    sizeof(uint32_t) * 4 * rp.H, cudaMemcpyDeviceToHost));
     if (cong)  MVB_CUDA(cudaMemcpy(cong, rp.cong.p, sizeof(float) * 4 * rp.H, cudaMemcpyDeviceToHost));
     return MVB_OK;
+}
+
+// Debug hook (not part of the ABI): record {start of the first block, end of the last block} (globaltimer, ns) of the next
+// `n` day-kernel launches; a second call with out != nullptr copies what was recorded.  tools/launch_gaps.py.
+int mvbx_launch_stamps(mvb_sim* s, uint32_t n, unsigned long long* out, uint32_t* n_out) {
+    if (!s) return -1;
+    cudaSetDevice(s->device);
+    cudaStreamSynchronize(s->stream);
+    if (out) {
+        const uint32_t done = std::min<uint32_t>(s->stamp_cap, s->cursor > s->stamp_first ? s->cursor - s->stamp_first : 0);
+        cudaMemcpy(out, s->stamps.p, 16 * (size_t)done, cudaMemcpyDeviceToHost);
+        if (n_out) *n_out = done;
+        StampCfg off{nullptr, nullptr, 0, 0, 0};
+        cudaMemcpyToSymbol(g_stamps, &off, sizeof off);
+        return 0;
+    }
+    if (ensure_rows(s, n + 1)) return -3;                          // the record buffer must not move while launches are stamped
+    if (s->stamps.alloc(16 * (size_t)n) != cudaSuccess) return -2;
+    std::vector<unsigned long long> init(2 * (size_t)n);
+    for (uint32_t k = 0; k < n; ++k) { init[2 * k] = ~0ull; init[2 * k + 1] = 0; }
+    cudaMemcpy(s->stamps.p, init.data(), 16 * (size_t)n, cudaMemcpyHostToDevice);
+    s->stamp_cap = n; s->stamp_first = s->cursor;
+    StampCfg cfg{s->stamps.as<unsigned long long>(), s->rec.as<uint32_t>(), s->rec_stride, s->cursor + 1, n};
+    return cudaMemcpyToSymbol(g_stamps, &cfg, sizeof cfg) == cudaSuccess ? 0 : -4;
 }
 
 // Test hook (not part of the ABI in include/): the layout the GPU built for replica r against the host builder
