@@ -506,17 +506,22 @@ def leg_c4(args, rank, local_rank, world, torch, dist, mb, peak):
     d2, r2 = o.run(w, intervention=iv)
     so = o.get_state()
     ok = True
-    for env in ({}, {"MVB_LAYOUT": "local", "MVB_STAGE_AGENTS": "2048"}):
+    modes_seen = set()
+    # both layouts over the default exchange (peer-to-peer stores fused into the weekday kernel where the GPUs can map each
+    # other's memory), and the LOCAL layout once more over the NCCL all-gather / all-reduce path
+    for env in ({}, {"MVB_LAYOUT": "local", "MVB_STAGE_AGENTS": "2048"}, {"MVB_LAYOUT": "local", "MVB_STAGE_AGENTS": "2048", "MVB_EXCHANGE": "nccl"}):
         os.environ.update(env)
         sim = mb.Simulation.partitioned(d, tab, prm, device=local_rank, rank=rank, world=world, unique_id=uid())
         for k in env:
             os.environ.pop(k)
+        modes_seen.add(sim.exchange_mode())
         days, rows = sim.run(w, interventions=iv)
         st = sim.get_state(0)
         mine = sim.partition_owner() == rank
         sim.close()
         ok = ok and np.array_equal(days, d2) and np.array_equal(rows[0], r2) and same_state(st, so, mine)
     out["partitioned_parity_vs_oracle"] = {"agents": n, "weekdays": len(days) - 1, "world": world, "layouts": ["global", "local"],
+                                            "exchange_paths": sorted(modes_seen),
                                             "result": "bit-exact" if all_ok(ok) else "MISMATCH",
                                             "compared": "statistics rows, every agent's mode and norm, habit bits of the agents each rank owns"}
     d.close()
@@ -526,6 +531,7 @@ def leg_c4(args, rank, local_rank, world, torch, dist, mb, peak):
     tab = mb.synth_tables(4, 10, n, seed=12)
     w = mb.weather_pattern(17, seed=12)
     sim = mb.Simulation.partitioned(d, tab, prm, device=local_rank, rank=rank, world=world, unique_id=uid())
+    exchange_8m = sim.exchange_mode()
     days, rows = sim.run(w)
     st = sim.get_state(0)
     mine = sim.partition_owner() == rank
@@ -536,7 +542,7 @@ def leg_c4(args, rank, local_rank, world, torch, dist, mb, peak):
     one.close()
     ok = np.array_equal(days, d1) and np.array_equal(rows[0], r1[0]) and same_state(st, s1, mine)
     import zlib
-    out["partitioned_parity_vs_one_gpu"] = {"agents": n, "weekdays": len(days) - 1, "world": world,
+    out["partitioned_parity_vs_one_gpu"] = {"agents": n, "weekdays": len(days) - 1, "world": world, "exchange": exchange_8m,
                                              "result": "bit-exact" if all_ok(ok) else "MISMATCH",
                                              "mode_vector_crc32": zlib.crc32(st["current_mode"].tobytes()),
                                              "norm_vector_crc32": zlib.crc32(st["norm"].tobytes())}
@@ -551,13 +557,17 @@ def leg_c4(args, rank, local_rank, world, torch, dist, mb, peak):
     w = mb.weather_pattern(n_days, seed=0)
     warm_end = weekdays_calendar(args.warmup)
 
-    def timed(H):
+    def timed(H, exchange=None):
         d = mb.DevicePopulation(n, 4, H, 5, 10, seed=0, device=local_rank)
         tab = mb.synth_tables(4, H, n, seed=0)
         t0 = time.perf_counter()
+        if exchange:
+            os.environ["MVB_EXCHANGE"] = exchange
         sim = mb.Simulation.partitioned(d, tab, prm, device=local_rank, rank=rank, world=world, unique_id=uid())
+        os.environ.pop("MVB_EXCHANGE", None)
         t_create = time.perf_counter() - t0
         alg = sim.algorithmic_bytes_per_day(0)
+        mode = sim.exchange_mode()
         sim.run_async(w, 0, warm_end); sim.sync()
         dist.barrier(); torch.cuda.synchronize()
         sim.run_async(w, warm_end, n_days); sim.sync()
@@ -569,16 +579,20 @@ def leg_c4(args, rank, local_rank, world, torch, dist, mb, peak):
         max_ms = max(float(x.item()) for x in per_rank)
         free_b, total_b = torch.cuda.mem_get_info(dev)
         sim.close(); d.close()
-        return {"neighbourhoods": H, "agent_days_per_sec": n * args.steps / (max_ms * 1e-3), "weekdays": args.steps,
+        return {"neighbourhoods": H, "exchange": mode, "agent_days_per_sec": n * args.steps / (max_ms * 1e-3), "weekdays": args.steps,
                 "ms_per_weekday": max_ms / args.steps, "ms_per_weekday_by_rank": [float(x.item()) / args.steps for x in per_rank],
                 "roofline_frac_per_gpu": alg * args.steps / (max_ms * 1e-3) / 1e9 / world / peak,
                 "create_seconds_rank0": t_create, "device_memory_in_use_gb_rank0": (total_b - free_b) / 1e9}
 
-    out["workload"] = (f"C4: ONE population of {n} agents (S=4, BA links 5+10) agent-partitioned over {world} B200; per weekday one NCCL "
-                       "all-gather of the packed 2-bit modes + norms and one all-reduce of the counters; populations generated on the GPUs")
+    out["workload"] = (f"C4: ONE population of {n} agents (S=4, BA links 5+10) agent-partitioned over {world} B200; the exchange of "
+                       "the packed 2-bit modes and of the day's counters is fused into the weekday kernel (stores into every rank's "
+                       "vector over NVLink peer memory, flags; `exchange` = p2p) or, as the baseline beside it, one NCCL all-gather + "
+                       "one all-reduce per weekday (`exchange_nccl`); populations generated on the GPUs")
     out["agents"] = n
     out.update(timed(10))
     out["h64"] = timed(64)
+    nccl = timed(64, "nccl")
+    out["h64"]["exchange_nccl"] = {k: nccl[k] for k in ("exchange", "agent_days_per_sec", "ms_per_weekday", "roofline_frac_per_gpu")}
     return out
 
 

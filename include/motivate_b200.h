@@ -227,12 +227,20 @@ uint64_t mvb_algorithmic_bytes_per_day(const mvb_sim* sim, uint32_t replica);
  * src/simulation.rs:64); it is the "number_of_people" axis scaled over GPUs.  One process per GPU.  Every rank
  * passes the SAME population and tables; the library cuts the agents into `world` contiguous ranges of its internal
  * order, balanced by modelled work, and each rank updates its own agents (and stores the link codes of those only).
- * After every weekday the ranks exchange, over NCCL, the packed 2-bit current_mode words they own in ONE all-gather (the
- * social network is global, src/simulation.rs:160: tomorrow every rank needs every agent's mode) and all-reduce the
- * day's counters (hist + statistics); the norm words, which no other agent's update reads, travel with the last weekday
- * of a mvb_run / mvb_run_async call (and with every mvb_step).  Afterwards every rank holds the full mode / norm
- * vectors and identical statistics rows; habits are current only for the agents a rank owns (mvb_partition_owner).  All other entry points (mvb_step, mvb_run, mvb_set_*, mvb_get_state, ...) work
- * as for a one-replica handle and must be called by all ranks in the same order. */
+ * The social network is global (src/simulation.rs:160): tomorrow every rank needs every agent's mode, and the congestion
+ * needs the whole population's histogram.  Two exchange paths, same results bit for bit (mvb_exchange_mode says which):
+ *   MVB_EXCHANGE_P2P   (default where the ranks' GPUs can map each other's memory: CUDA IPC over NVLink / NVSwitch)
+ *       the exchange is fused into the weekday kernel: the warp that packs 32 new modes into a word stores that word
+ *       into EVERY rank's vector with one store instruction (one lane per rank); the last block of a rank to finish
+ *       copies the rank's partial counters into every rank's landing zone and raises the rank's flag there; a one-block
+ *       kernel waits for all flags and adds the partial counters up.  No collective, no pack / unpack pass.
+ *   MVB_EXCHANGE_NCCL  (fallback, or MVB_EXCHANGE=nccl) after every weekday ONE ncclAllGather of the packed 2-bit
+ *       current_mode words each rank owns and ONE ncclAllReduce of the day's counters (hist + statistics).
+ * The norm words, which no other agent's update reads, travel with the last weekday of a mvb_run / mvb_run_async call
+ * (and with every mvb_step).  Afterwards every rank holds the full mode / norm vectors and identical statistics rows;
+ * habits are current only for the agents a rank owns (mvb_partition_owner).  NCCL always carries the set-up (memory
+ * handles, barriers).  All other entry points (mvb_step, mvb_run, mvb_set_*, mvb_get_state, ...) work as for a
+ * one-replica handle and must be called by all ranks in the same order. */
 #define MVB_UNIQUE_ID_BYTES 128
 /* Rank 0 calls this and hands the 128 bytes to the other ranks (file, socket, torch.distributed broadcast ...). */
 int  mvb_comm_unique_id(void* id_out);
@@ -243,6 +251,11 @@ int  mvb_partition_owner(const mvb_sim* sim, uint32_t* rank_out);
 /* The same plan without creating anything (no device needed): how `world` ranks would split this population. */
 int  mvb_partition_plan(const mvb_population* pop, uint32_t n_subcultures, uint32_t n_neighbourhoods,
                         uint32_t world, uint32_t* rank_out);
+/* How this handle's ranks exchange modes and counters after a weekday (MVB_EXCHANGE_NONE: not partitioned). */
+#define MVB_EXCHANGE_NONE 0
+#define MVB_EXCHANGE_NCCL 1
+#define MVB_EXCHANGE_P2P  2
+int  mvb_exchange_mode(const mvb_sim* sim);
 
 /* ---- synthetic populations (host-side utility, seeded, no device needed) --- */
 

@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmotivate_b200.so")
+# MVB_LIB_PATH: a debug build of the same library (tools/launch_gaps.py uses libmotivate_b200_stamps.so)
+LIB_PATH = os.environ.get("MVB_LIB_PATH") or os.path.join(_HERE, "libmotivate_b200.so")
 
 u8p, u16p, u32p, u64p, f32p = (C.POINTER(C.c_uint8), C.POINTER(C.c_uint16), C.POINTER(C.c_uint32),
                                C.POINTER(C.c_uint64), C.POINTER(C.c_float))
@@ -82,6 +83,7 @@ SIGNATURES = {
     "mvb_create_partitioned": (C.c_int, [PopP, TabP, PrmP, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(SimP)]),
     "mvb_partition_owner": (C.c_int, [SimP, u32p]),
     "mvb_partition_plan": (C.c_int, [PopP, C.c_uint32, C.c_uint32, C.c_uint32, u32p]),
+    "mvb_exchange_mode": (C.c_int, [SimP]),
     "mvb_synth_create": (C.c_int, [C.POINTER(SynthSpec), C.POINTER(C.c_void_p)]),
     "mvb_synth_create_device": (C.c_int, [C.POINTER(SynthSpec), C.c_int, C.POINTER(C.c_void_p)]),
     "mvb_synth_copy_to_host": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),

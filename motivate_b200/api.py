@@ -347,6 +347,11 @@ class Simulation:
         self.widths = [int(self._lib.mvb_stats_width(self._h, 0))]
         return self
 
+    def exchange_mode(self) -> str:
+        """How the ranks of an agent-partitioned handle exchange modes and counters after a weekday (mvb_exchange_mode):
+        "p2p" = fused into the weekday kernel over peer memory, "nccl" = all-gather + all-reduce, "none" = not partitioned."""
+        return {0: "none", 1: "nccl", 2: "p2p"}[int(self._lib.mvb_exchange_mode(self._h))]
+
     def partition_owner(self):
         out = np.zeros(self.pops[0].n_agents, np.uint32)
         _check(self._lib.mvb_partition_owner(self._h, _ptr(out, _ffi.u32p)))

@@ -261,6 +261,7 @@ static int create_impl(uint32_t R, const mvb_population* const* pops, const mvb_
         set_error("too many neighbourhoods/subcultures: the per-block tables need %u bytes of shared memory", tail_max * 4);
         return MVB_ERR_ARG;
     }
+    size_t vec_piece = 0;                          // agent-partitioned: stride of vec[0], vec[1], normvec inside s->px_vec
     s->smem_bytes = (size_t)smem_optin;
     s->vec_cap_words = ((uint32_t)smem_optin / 4 - tail_max) & ~3u;
     s->census_smem = sizeof(uint32_t) * census_words;
@@ -603,10 +604,18 @@ static int create_impl(uint32_t R, const mvb_population* const* pops, const mvb_
         if (rp.per_agent) s->any_per_agent = true;
         {
             const size_t hub_cnt_bytes = sizeof(uint32_t) * 8 * 32 * (size_t)L.n_hub_slices;
+            vec_piece = Arena::piece(NP / 4 + 64);
             MVB_CARVE(s->mem, rp.state, (size_t)(NP / 32) * kRecWords * 4);
             // + 64 bytes: the early gather of a padded cold-list entry reads the word a padding code names (at most
             // 16 bytes past a vector that only just exceeds the shared-memory capacity); its value is never used
-            MVB_CARVE(s->mem, rp.vec[0], NP / 4 + 64); MVB_CARVE(s->mem, rp.vec[1], NP / 4 + 64); MVB_CARVE(s->mem, rp.normvec, NP / 4);
+            if (world > 1) {
+                // agent-partitioned: the vectors get an allocation of their own, which the other ranks can map (setup_peer_exchange)
+                MVB_CUDA(s->px_vec.alloc(3 * vec_piece));
+                rp.vec[0].view(s->px_vec.p, NP / 4 + 64); rp.vec[1].view(s->px_vec.as<char>() + vec_piece, NP / 4 + 64);
+                rp.normvec.view(s->px_vec.as<char>() + 2 * vec_piece, NP / 4);
+            } else {
+                MVB_CARVE(s->mem, rp.vec[0], NP / 4 + 64); MVB_CARVE(s->mem, rp.vec[1], NP / 4 + 64); MVB_CARVE(s->mem, rp.normvec, NP / 4);
+            }
             if (rp.per_agent) MVB_CARVE(s->mem, rp.pa, 20 * (size_t)NP);
             MVB_CARVE(s->mem, rp.tables_f, sizeof(float) * 4 * (rp.H + rp.S));
             MVB_CARVE(s->mem, rp.tables_u, sizeof(uint32_t) * 5 * rp.H);
@@ -654,6 +663,10 @@ static int create_impl(uint32_t R, const mvb_population* const* pops, const mvb_
         d.cong = rp.cong.as<float>();
         d.int2ext = g->int2ext.as<uint32_t>();
         d.local_mode = L.mode == kLayoutLocal ? 1u : 0u;
+        // cold gathers bypass L1 when the vector is several times what shared memory + L1 hold (day_kernels.cuh: ld_cold;
+        // tools/ab_cold_cg.sh: 8M agents -4.8 %, 2M +0.6 %, 1M +1 % with the bypass)
+        d.cold_cg = (size_t)NP / 4 > (1u << 20) ? 1u : 0u;
+        if (const char* e = getenv("MVB_COLD_CG")) d.cold_cg = atoi(e) ? 1u : 0u;
         d.nb_slice_begin = g->nb_slice_begin.as<uint32_t>();
     }
     const double tm3 = now();
@@ -661,6 +674,12 @@ static int create_impl(uint32_t R, const mvb_population* const* pops, const mvb_
     MVB_CUDA(cudaFuncSetAttribute(day_kernel<true, 1024, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
     MVB_CUDA(cudaFuncSetAttribute(day_kernel<false, 1024, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
     MVB_CUDA(cudaFuncSetAttribute(day_kernel<false, 1024, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
+    if (world > 1) {
+        MVB_CUDA(cudaFuncSetAttribute(day_kernel<true, 1024, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
+        MVB_CUDA(cudaFuncSetAttribute(day_kernel<true, 1024, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
+        MVB_CUDA(cudaFuncSetAttribute(day_kernel<false, 1024, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
+        MVB_CUDA(cudaFuncSetAttribute(day_kernel<false, 1024, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
+    }
     if (s->census_smem > 48 * 1024)
         MVB_CUDA(cudaFuncSetAttribute(census_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->census_smem));
     s->rank = rank; s->world = world;
@@ -670,8 +689,10 @@ static int create_impl(uint32_t R, const mvb_population* const* pops, const mvb_
         ncclUniqueId id;
         memcpy(&id, unique_id, sizeof id);
         MVB_NCCL(n->CommInitRank(&s->comm, (int)world, id, (int)rank));
+        if (int rc = setup_peer_exchange(s, vec_piece, S)) return rc;      // sets s->exchange_mode: P2P, or NCCL if any rank could not map the others
+        if (s->exchange_mode == MVB_EXCHANGE_P2P) s->h_reps[0].px = s->d_px.as<PeerExchange>();
         for (uint32_t k = 0; k < world; ++k) s->xchg_words = std::max(s->xchg_words, s->bounds[k + 1] - s->bounds[k]);
-        MVB_CUDA(s->xchg.alloc((size_t)world * 2 * s->xchg_words * sizeof(uint2)));
+        if (s->exchange_mode == MVB_EXCHANGE_NCCL) MVB_CUDA(s->xchg.alloc((size_t)world * 2 * s->xchg_words * sizeof(uint2)));
         MVB_CUDA(s->d_bounds.alloc(4 * ((size_t)world + 1)));
         MVB_CUDA(cudaMemcpyAsync(s->d_bounds.p, s->bounds.data(), 4 * ((size_t)world + 1), cudaMemcpyHostToDevice, S));
     }

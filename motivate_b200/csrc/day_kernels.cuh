@@ -39,6 +39,21 @@ namespace mvb {
 constexpr uint32_t kCodeAddrMask = 0x07FFFFFCu;     // byte offset of the vector word (shared or global)
 constexpr uint32_t kStatValid = 0x80000000u;        // bit 31 of the packed static word: a real agent
 
+// Agent-partitioned mode with the exchange fused into the day kernel (sim.cu: exchange over peer memory).  Every rank
+// maps every other rank's buffers (CUDA IPC over NVLink / NVSwitch); the day kernel stores each new mode word into ALL
+// ranks' vectors, the last block to finish copies the rank's partial record into every rank's landing zone and then
+// raises this rank's flag on every rank; exchange_finish_kernel waits for all flags and adds the partial records up.
+constexpr uint32_t kMaxPeers = 16;
+struct PeerExchange {
+    uint32_t world, rank, rec_stride, pad_;
+    uint2* vec[2][kMaxPeers];       // every rank's mode vectors by day parity ([..][rank] = this rank's own)
+    uint2* normvec[kMaxPeers];
+    uint32_t* xrec[kMaxPeers];      // every rank's landing zone for partial records: [2 (epoch parity)][world][rec_stride]
+    uint32_t* flags[kMaxPeers];     // every rank's flags [world]: flags[p][q] = last epoch rank q has finished, as seen on rank p
+    uint32_t* done;                 // this rank: blocks of the current launch that have finished
+    uint32_t* error;                // this rank: set if a wait for the other ranks timed out
+};
+
 struct RepDev {                     // device-side descriptor of one replica
     uint32_t N, N_pad, S, H, rec_off;
     uint32_t n_hub_slices, n_sell_slices, n_ranges, hot_words;
@@ -58,8 +73,10 @@ struct RepDev {                     // device-side descriptor of one replica
     float* cong;                    // [H][4] modifier used by the last step (for mvb_get_state)
     const uint32_t* int2ext;        // [N_pad] internal slot -> caller's agent id (kInvalid = padding); not read by the day kernel
     const uint32_t* nb_slice_begin; // [H + 1] SELL slices of every neighbourhood (LOCAL layout: parts are neighbourhood-pure)
-    uint32_t local_mode, pad_;      // layout.h LayoutMode
+    uint32_t local_mode, cold_cg;   // layout.h LayoutMode; cold gathers bypass L1 (ld_cold)
     const uint4* part_table;        // LOCAL layout: part p of a launch = {neighbourhood, class q, classes Q of that neighbourhood, 0}
+    const PeerExchange* px;         // agent-partitioned mode, exchange over peer memory (day_kernel<.., XCHG = true>), else nullptr
+    uint32_t px_epoch, px_norms;    // this launch's epoch (flag value raised when the rank has finished); also store the norm words
 };
 
 __host__ __device__ inline uint32_t rec_width(uint32_t S, uint32_t H) { return 4 * H + 7 + S; }
@@ -115,6 +132,21 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// System-scope flag traffic of the peer-to-peer exchange.
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t* p) {              // from L2: written by other blocks / other GPUs
+    uint32_t v;
+    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
 // Shared-memory atomics issued by ONE lane of a warp.  Plain atomicAdd makes the compiler wrap the instruction in its
 // warp-aggregation sequence (vote, find-leader, popc, shuffle: ~12 instructions) because it cannot know that.
 __device__ __forceinline__ uint32_t smem_fetch_add(uint32_t* p, uint32_t v) {
@@ -133,9 +165,17 @@ __device__ __forceinline__ uint32_t top2_hot(const uint32_t* s_vec, uint32_t cod
     const uint32_t w = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(s_vec) + (code >> 5));
     return __funnelshift_l(0u, w, code);                       // w << (code & 31)
 }
-__device__ __forceinline__ uint32_t top2_cold(const uint32_t* g_vec, uint32_t code) {
-    const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(g_vec) + (code >> 5)));
-    return __funnelshift_l(0u, w, code);
+// The word a cold code names, from the L2-resident global vector.  Divergent gathers that miss L1 are bound by the
+// L1TEX wavefront rate (one 128-byte line per ~2 clocks, profiles/r02_microbench_cold.txt: 0.46 gathers per clock per SM
+// through ld.global.nc, 0.52 through ld.global.cg, the same through the texture path or 16-byte TMA copies), so when the
+// cold part of the vector is larger than what L1 keeps next to 227 KB of shared memory the loads bypass L1 (`cg`, a
+// launch-uniform flag: -4.5 % on 8M agents); a cold part of a few KB (1M agents) stays on the L1-cached path.
+__device__ __forceinline__ uint32_t ld_cold(const uint32_t* g_vec, uint32_t code, bool cg) {
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(g_vec) + (code >> 5));
+    uint32_t w;
+    if (cg) asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(w) : "l"(p));
+    else w = __ldg(p);
+    return w;
 }
 __device__ __forceinline__ uint32_t push2(uint32_t bits, uint32_t top) {      // (bits << 2) | (top >> 30)
     return __funnelshift_l(top, bits, 2u);
@@ -179,7 +219,7 @@ __device__ __forceinline__ uint32_t car_counts(uint32_t acc, uint32_t n) {
 // every list below 256 links).
 __device__ __forceinline__ void accumulate_block(const uint32_t* __restrict__ blk, uint32_t K, uint32_t Kc, uint32_t lane,
                                                  int ds_h, int ds_c, int d_c, const uint32_t* s_vec,
-                                                 const uint32_t* __restrict__ g_vec, uint32_t& acc_s, uint32_t& acc_n) {
+                                                 const uint32_t* __restrict__ g_vec, bool cold_cg, uint32_t& acc_s, uint32_t& acc_n) {
     uint32_t hs = 0, ht = 0;                                    // hot list: social / all
     const uint32_t K4 = K >> 2, Kt = K & 3u;
     const uint4* body = reinterpret_cast<const uint4*>(blk) + lane;
@@ -198,8 +238,8 @@ __device__ __forceinline__ void accumulate_block(const uint32_t* __restrict__ bl
     uint32_t c0 = 0, c1 = 0, w0 = 0, w1 = 0;
     if (Kc > 0) c0 = ld_stream_u32(cold);
     if (Kc > 1) c1 = ld_stream_u32(cold + 32);
-    if (Kc > 0) w0 = __ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(g_vec) + (c0 >> 5)));
-    if (Kc > 1) w1 = __ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(g_vec) + (c1 >> 5)));
+    if (Kc > 0) w0 = ld_cold(g_vec, c0, cold_cg);
+    if (Kc > 1) w1 = ld_cold(g_vec, c1, cold_cg);
     uint32_t q = 0, bits = 0;
     for (; q + 4 <= K4; q += 4) {                               // 16 links per lane, two rows kept in flight
         r2 = ld_stream_v4(body + (size_t)(q + 2) * 32);
@@ -240,7 +280,7 @@ __device__ __forceinline__ void accumulate_block(const uint32_t* __restrict__ bl
 #pragma unroll
         for (int u = 0; u < 8; ++u) c[u] = k + u < Kc ? ld_stream_u32(cold + (size_t)(k + u) * 32) : 0u;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) w[u] = __ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(g_vec) + (c[u] >> 5)));
+        for (int u = 0; u < 8; ++u) w[u] = ld_cold(g_vec, c[u], cold_cg);
 #pragma unroll
         for (int u = 0; u < 8; ++u)
             if ((int)(k + u) < d_c) {
@@ -284,7 +324,7 @@ __device__ __forceinline__ void flush_stats(uint32_t lane, uint32_t H, uint32_t 
 }
 
 // Everything that happens once the link counts of 32 agents (one per lane) are known.
-template <bool PER_AGENT>
+template <bool PER_AGENT, bool XCHG>
 __device__ __forceinline__ void finish_slice(const RepDev& r, uint32_t slice, uint32_t lane, bool uniform_nbhd,
                                              const uint32_t cs[4], uint32_t ds, const uint32_t cn[4], uint32_t dn,
                                              uint32_t stat, float wsv, float4 hv, uint32_t last,
@@ -314,8 +354,17 @@ __device__ __forceinline__ void finish_slice(const RepDev& r, uint32_t slice, ui
     const uint32_t mhi = __reduce_or_sync(0xFFFFFFFFu, lane < 16 ? 0u : mode << sh);
     const uint32_t nlo = __reduce_or_sync(0xFFFFFFFFu, lane < 16 ? norm << sh : 0u);
     const uint32_t nhi = __reduce_or_sync(0xFFFFFFFFu, lane < 16 ? 0u : norm << sh);
-    if (lane == 0) r.vec[parity ^ 1u][slice] = make_uint2(mlo, mhi);
-    if (lane == 1) r.normvec[slice] = make_uint2(nlo, nhi);
+    if (XCHG) {
+        // exchange fused into the update: lane p stores the word into rank p's vector (its own included), one store
+        // instruction for all ranks; norm words only travel when asked (no rank's update reads another agent's norm)
+        const PeerExchange* px = r.px;
+        const uint32_t world = px->world;
+        if (lane < world) px->vec[parity ^ 1u][lane][slice] = make_uint2(mlo, mhi);
+        if (lane >= 16u && lane - 16u < world && (r.px_norms || lane - 16u == px->rank)) px->normvec[lane - 16u][slice] = make_uint2(nlo, nhi);
+    } else {
+        if (lane == 0) r.vec[parity ^ 1u][slice] = make_uint2(mlo, mhi);
+        if (lane == 1) r.normvec[slice] = make_uint2(nlo, nhi);
+    }
     // statistics (statistics.rs:14-93): every lane counts its own agent; the warp adds its lanes up at a flush
     const uint32_t a = valid && mode >= 2u, an = valid && norm >= 2u;
     if (uniform_nbhd) {
@@ -332,12 +381,15 @@ __device__ __forceinline__ void finish_slice(const RepDev& r, uint32_t slice, ui
     if (++st.n == 255) flush_stats(lane, r.H, r.S, s_rec, st);
 }
 
-// Debug (mvbx_launch_stamps, tools/launch_gaps.py): {start of the first block, end of the last block} per launch, in ns.
-// The slot of a launch follows from the record row it writes, so the kernel needs no extra parameter (one would cost a
-// register for the whole kernel); g_stamps.slots is null unless the hook has been called.
+// Debug build only (make stamps: -DMVB_DEBUG_STAMPS, libmotivate_b200_stamps.so; mvbx_launch_stamps, tools/launch_gaps.py):
+// {start of the first block, end of the last block} per launch, in ns.  Not in the product library: the two calls keep
+// rec_next alive across the kernel and cost it 92 bytes of spills at its 64-register budget.
+// The slot of a launch follows from the record row it writes, so the kernel needs no extra parameter;
+// g_stamps.slots is null unless the hook has been called.
+#ifdef MVB_DEBUG_STAMPS
 struct StampCfg { unsigned long long* slots; const uint32_t* rec_base; uint32_t rec_stride, first_row, n; };
 __device__ StampCfg g_stamps = {nullptr, nullptr, 0, 0, 0};
-__device__ __noinline__ void stamp_launch(const uint32_t* rec_next, int end) {
+__device__ __forceinline__ void stamp_launch(const uint32_t* rec_next, int end) {
     const StampCfg c = g_stamps;
     const uint32_t row = (uint32_t)((rec_next - c.rec_base) / c.rec_stride);
     if (row < c.first_row || row - c.first_row >= c.n) return;
@@ -345,9 +397,13 @@ __device__ __noinline__ void stamp_launch(const uint32_t* rec_next, int end) {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     if (end) atomicMax(&c.slots[2 * (size_t)(row - c.first_row) + 1], t); else atomicMin(&c.slots[2 * (size_t)(row - c.first_row)], t);
 }
+#define MVB_STAMP(end) do { if (tid == 0 && g_stamps.slots) stamp_launch(rec_next, end); } while (0)
+#else
+#define MVB_STAMP(end) do { } while (0)
+#endif
 
 // ---- the weekday kernel ----------------------------------------------------------------------------
-template <bool PER_AGENT, int THREADS, uint32_t G>
+template <bool PER_AGENT, int THREADS, uint32_t G, bool XCHG = false>
 __global__ void __launch_bounds__(THREADS, 1)
 day_kernel(const __grid_constant__ RepArray reps, uint32_t R, uint32_t P, uint32_t parity,
            const uint32_t* __restrict__ rec_prev, uint32_t* __restrict__ rec_next, uint32_t weather,
@@ -365,7 +421,7 @@ day_kernel(const __grid_constant__ RepArray reps, uint32_t R, uint32_t P, uint32
     // first slice records, L2 prefetches of link codes) and then wait at griddepcontrol.wait (below) for today to be
     // complete and visible.  Without the launch attribute both instructions are no-ops.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    if (tid == 0 && g_stamps.slots) stamp_launch(rec_next, 0);     // debug (tools/launch_gaps.py): when this launch's first block started
+    MVB_STAMP(0);                                   // debug build: when this launch's first block started
     if (tid == 0) { mbar_init(s_bar, 1); s_vec[vec_cap_words - 1] = 0; }   // the word padding codes point at (pad_code)
     uint32_t phase = 0;
     bool first_part = true;
@@ -514,7 +570,7 @@ day_kernel(const __grid_constant__ RepArray reps, uint32_t R, uint32_t P, uint32
             uint32_t acc_s = 0, acc_n = 0;
             accumulate_block(blk, K, Kc, lane, min(max((int)(unit0.z >> 16) - oh, 0), (int)K),
                              min(max((int)(unit0.w & 0xFFFFu) - oc, 0), (int)Kc), min(max((int)(unit0.w >> 16) - oc, 0), (int)Kc),
-                             s_vec, g_vec, acc_s, acc_n);
+                             s_vec, g_vec, r.cold_cg != 0, acc_s, acc_n);
             uint32_t mine = 0;                         // lane 1..3: social count of mode lane; lane 5..7: neighbour count
 #pragma unroll
             for (int m = 1; m < 4; ++m) {
@@ -549,7 +605,7 @@ day_kernel(const __grid_constant__ RepArray reps, uint32_t R, uint32_t P, uint32
                 const uint32_t stat = rec[kRecStat + lane];
                 const uint2 own = r.vec[parity][hs];
                 const uint32_t last = ((lane < 16 ? own.x : own.y) >> ((lane & 15u) * 2u)) & 3u;
-                finish_slice<PER_AGENT>(r, hs, lane, false, hcs, ad.x + ad.z, hcn, ad.y + ad.w, stat, __uint_as_float(rec[kRecWs + lane]),
+                finish_slice<PER_AGENT, XCHG>(r, hs, lane, false, hcs, ad.x + ad.z, hcn, ad.y + ad.w, stat, __uint_as_float(rec[kRecWs + lane]),
                                         reinterpret_cast<const float4*>(rec + kRecHabit)[lane], last, uw, s_cong, s_cost, s_crank, s_des, s_rec, weather, changed, parity, st);
             } else {
             const uint32_t s = sell_b + q + Q * (it0 - n_my_hub_slices);
@@ -567,14 +623,14 @@ day_kernel(const __grid_constant__ RepArray reps, uint32_t R, uint32_t P, uint32
             const uint2 own = ld_stream_v2(r.vec[parity] + slice);
             const int ds_h = (int)(dg & 0xFFu), dn_h = (int)((dg >> 8) & 0xFFu), ds_c = (int)((dg >> 16) & 0xFFu), dn_c = (int)(dg >> 24);
             uint32_t acc_s = 0, acc_n = 0;
-            accumulate_block(blk, KK & 0xFFFFu, KK >> 16, lane, ds_h, ds_c, ds_c + dn_c, s_vec, g_vec, acc_s, acc_n);
+            accumulate_block(blk, KK & 0xFFFFu, KK >> 16, lane, ds_h, ds_c, ds_c + dn_c, s_vec, g_vec, r.cold_cg != 0, acc_s, acc_n);
             acc_s = car_counts(acc_s, (uint32_t)(ds_h + ds_c));
             acc_n = car_counts(acc_n, (uint32_t)(dn_h + dn_c));
             uint32_t cs[4], cn[4];
 #pragma unroll
             for (int m = 0; m < 4; ++m) { cs[m] = (acc_s >> (8 * m)) & 0xFFu; cn[m] = (acc_n >> (8 * m)) & 0xFFu; }
             const uint32_t last = ((lane < 16 ? own.x : own.y) >> ((lane & 15u) * 2u)) & 3u;
-            finish_slice<PER_AGENT>(r, slice, lane, true, cs, (uint32_t)(ds_h + ds_c), cn, (uint32_t)(dn_h + dn_c), stat, wsv, hv,
+            finish_slice<PER_AGENT, XCHG>(r, slice, lane, true, cs, (uint32_t)(ds_h + ds_c), cn, (uint32_t)(dn_h + dn_c), stat, wsv, hv,
                                     last, uw, s_cong, s_cost, s_crank, s_des, s_rec, weather, changed, parity, st);
             }
             it0 = it1; it1 = it2; meta = meta1; meta1 = meta2;
@@ -584,7 +640,54 @@ day_kernel(const __grid_constant__ RepArray reps, uint32_t R, uint32_t P, uint32
         for (uint32_t k = tid; k < rec_width(S, H); k += THREADS)
             if (s_rec[k]) atomicAdd(&rec_next[r.rec_off + k], s_rec[k]);
     }
-    if (tid == 0 && g_stamps.slots) stamp_launch(rec_next, 1);     // ... and when its last block ended
+    if (XCHG) {
+        // Peer-to-peer exchange, second half.  The mode words are already on their way (finish_slice); when the LAST block
+        // of this rank has finished, it hands the rank's partial record to every rank and raises the rank's flag there.
+        const PeerExchange* px = reps.r[0].px;
+        const uint32_t epoch = reps.r[0].px_epoch, world = px->world, W = px->rec_stride;
+        uint32_t* s_last = s_tail + 3;                 // (a free word next to the work counter: no static shared memory here)
+        __threadfence_system();                        // this thread's stores to the other ranks have been performed
+        __syncthreads();
+        if (tid == 0) *s_last = atomicAdd(px->done, 1u) == gridDim.x - 1u;
+        __syncthreads();
+        if (*s_last) {
+            __threadfence();                           // the other blocks' additions to rec_next
+            for (uint32_t k = tid; k < world * W; k += THREADS) {
+                const uint32_t p = k / W, j = k - p * W;
+                px->xrec[p][((epoch & 1u) * world + px->rank) * W + j] = ld_cg_u32(rec_next + j);
+            }
+            __threadfence_system();
+            __syncthreads();
+            if (tid < world) st_release_sys(px->flags[tid] + px->rank, epoch);
+            if (tid == 0) *px->done = 0;               // the next launch's blocks get here only after this one is complete
+        }
+    }
+    MVB_STAMP(1);                                   // ... and when its last block ended
+}
+
+// Peer-to-peer exchange, closing step of a weekday (one small block, stream-ordered behind the day kernel): wait until
+// every rank has raised its flag for this epoch (all mode words and partial records have then landed in this rank's
+// memory), then add the partial records up into the day's record row, which tomorrow's congestion and the statistics read.
+// A rank that never arrives (a dead process) must not hang the GPU: after ~20 s the wait gives up and sets px->error.
+__global__ void exchange_finish_kernel(const PeerExchange* px, uint32_t epoch, uint32_t* rec_row) {
+    const uint32_t world = px->world, W = px->rec_stride, tid = threadIdx.x;
+    if (tid < world) {
+        const uint32_t* f = px->flags[px->rank] + tid;
+        unsigned long long t0, t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while ((int32_t)(ld_acquire_sys(f) - epoch) < 0) {
+            __nanosleep(200);
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (t - t0 > 20000000000ull) { *px->error = 1u; break; }
+        }
+    }
+    __syncthreads();
+    const uint32_t* part = px->xrec[px->rank] + (size_t)(epoch & 1u) * world * W;
+    for (uint32_t j = tid; j < W; j += blockDim.x) {
+        uint32_t sum = 0;
+        for (uint32_t p = 0; p < world; ++p) sum += ld_cg_u32(part + (size_t)p * W + j);
+        rec_row[j] = sum;
+    }
 }
 
 // Census of the current state: fills one record row (day-0 row, mvb_stats_row).  Runs once per create.

@@ -174,6 +174,11 @@ struct mvb_sim {
     uint32_t stamp_first = 0, stamp_cap = 0;
     DevBuf xchg, d_bounds;               // exchange buffer [world][2][xchg_words] u64 words (modes, norms); bounds on the device
     uint32_t xchg_words = 0;             // longest rank range, in slices
+    // exchange over peer memory (MVB_EXCHANGE_P2P): this rank's exported buffers, the other ranks' buffers mapped here
+    int exchange_mode = MVB_EXCHANGE_NONE;
+    DevBuf px_vec, px_ctl, d_px;         // {vec[0], vec[1], normvec}; {landing zone for partial records, flags, done, error, scratch}; PeerExchange
+    std::vector<void*> px_open;          // cudaIpcOpenMemHandle results, closed by mvb_destroy
+    uint32_t epoch = 0;                  // day-kernel launches so far: the flag value a rank raises when it has finished one
     // interventions of the current run, staged before the day loop (apply_interventions_kernel)
     DevBuf d_ivreps;                     // IvRep[R]
     char* iv_pinned = nullptr;           // library-owned pinned staging: the caller's arrays are only borrowed for the call
@@ -261,8 +266,14 @@ int launch_day(mvb_sim* s, uint8_t weather, uint8_t changed, bool with_norms = t
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(s->grid); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = s->smem_bytes; cfg.stream = s->stream;
     cfg.attrs = pdl_attr; cfg.numAttrs = (s->world == 1 && !no_pdl) ? 1 : 0;
-#define MVB_LAUNCH(PA, T, G) MVB_CUDA(cudaLaunchKernelEx(&cfg, day_kernel<PA, T, G>, s->rep_args[c], R, P, s->parity, prev, (uint32_t*)next, \
+    const bool p2p = s->exchange_mode == MVB_EXCHANGE_P2P;
+    if (p2p) {                                                   // (one replica, one launch per weekday in this mode)
+        RepDev& r0 = s->rep_args[0].r[0];
+        r0.px_epoch = ++s->epoch; r0.px_norms = with_norms ? 1u : 0u;
+    }
+#define MVB_LAUNCH_X(PA, T, G, X) MVB_CUDA(cudaLaunchKernelEx(&cfg, day_kernel<PA, T, G, X>, s->rep_args[c], R, P, s->parity, prev, (uint32_t*)next, \
         (uint32_t)weather, (uint32_t)changed, uw, s->vec_cap_words))
+#define MVB_LAUNCH(PA, T, G) do { if (p2p) MVB_LAUNCH_X(PA, T, G, true); else MVB_LAUNCH_X(PA, T, G, false); } while (0)
     for (size_t c = 0; c < s->rep_args.size(); ++c) {
         const uint32_t R = std::min<uint32_t>(kMaxRepsPerLaunch, (uint32_t)s->reps.size() - (uint32_t)c * kMaxRepsPerLaunch);
         const uint32_t P = s->local_P[c] ? s->local_P[c] : choose_parts(s, (uint32_t)c * kMaxRepsPerLaunch, R);
@@ -277,9 +288,16 @@ int launch_day(mvb_sim* s, uint8_t weather, uint8_t changed, bool with_norms = t
         s->last_launches++;
     }
 #undef MVB_LAUNCH
+#undef MVB_LAUNCH_X
+    if (p2p) {
+        // the exchange itself happened inside the day kernel (stores into every rank's vectors); what is left is to wait
+        // for the other ranks' flags and to add the partial records up (day_kernels.cuh)
+        exchange_finish_kernel<<<1, 256, 0, s->stream>>>(s->d_px.as<PeerExchange>(), s->epoch, next);
+        MVB_CUDA(cudaGetLastError());
+    }
     static const bool skip_exchange = getenv("MVB_DEBUG_NO_EXCHANGE") != nullptr;      // timing experiments only: results are wrong
-    if (s->world > 1 && !skip_exchange) {
-        // agent-partitioned: every rank now holds new modes / norms for its own slices and a partial record.  The
+    if (s->world > 1 && !skip_exchange && !p2p) {
+        // agent-partitioned, NCCL path: every rank now holds new modes / norms for its own slices and a partial record.  The
         // social network is global (simulation.rs:160), so tomorrow every rank needs everybody's modes: ONE all-gather
         // of the packed 2-bit words (each rank's piece: its mode words, padded to the longest range, and on the last
         // weekday of a run its norm words behind them) and ONE all-reduce of the day's counters.
@@ -407,6 +425,14 @@ void mvb_destroy(mvb_sim* s) {
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     const double t1 = now();
+    if (s->exchange_mode == MVB_EXCHANGE_P2P) {
+        // nobody writes into this rank's memory any more (its last exchange_finish_kernel saw every rank's flag); unmap the
+        // other ranks' buffers, and free the exported ones only when every rank has done so
+        for (void* p : s->px_open) cudaIpcCloseMemHandle(p);
+        uint32_t* scratch = s->px_ctl.as<uint32_t>() + (s->px_ctl.bytes - 256) / 4;
+        if (s->comm && nccl() && nccl()->AllReduce(scratch, scratch, 1, ncclUint32, ncclSum, s->comm, s->stream) == ncclSuccess)
+            cudaStreamSynchronize(s->stream);
+    }
     if (s->comm && nccl()) nccl()->CommDestroy(s->comm);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
@@ -423,6 +449,85 @@ void mvb_destroy(mvb_sim* s) {
 }
 
 }  // extern "C"
+
+namespace {
+
+// Agent-partitioned mode, exchange over peer memory: export this rank's vectors and control block, map everybody else's
+// (handles travel through one ncclAllGather), agree that it worked on EVERY rank (else all fall back to the NCCL
+// exchange) and describe the result to the kernels (PeerExchange).  Also the barrier after which every rank's vectors are
+// initialised and may be written by the others.  s->px_vec holds vec[0], vec[1], normvec at `vec_piece` strides.
+int setup_peer_exchange(mvb_sim* s, size_t vec_piece, cudaStream_t S) {
+    Nccl* n = nccl();
+    const uint32_t world = s->world, rank = s->rank, W = s->rec_stride;
+    const char* force = getenv("MVB_EXCHANGE");
+    bool ok = world <= kMaxPeers && !(force && !strcmp(force, "nccl"));
+    const size_t xrec_bytes = Arena::piece(sizeof(uint32_t) * 2 * (size_t)world * W);
+    MVB_CUDA(s->px_ctl.alloc(xrec_bytes + 4 * 256));              // + flags, done, error, scratch (a 256-byte line each)
+    MVB_CUDA(cudaMemsetAsync(s->px_ctl.p, 0, s->px_ctl.bytes, S));
+    struct Handles { cudaIpcMemHandle_t vec, ctl; };
+    Handles mine{};
+    if (ok && (cudaIpcGetMemHandle(&mine.vec, s->px_vec.p) != cudaSuccess || cudaIpcGetMemHandle(&mine.ctl, s->px_ctl.p) != cudaSuccess)) {
+        ok = false; cudaGetLastError();
+    }
+    DevBuf d_h;
+    MVB_CUDA(d_h.alloc(sizeof(Handles) * world + 256));
+    std::vector<Handles> all(world);
+    MVB_CUDA(cudaMemcpyAsync(d_h.as<Handles>() + rank, &mine, sizeof mine, cudaMemcpyHostToDevice, S));
+    MVB_NCCL(n->AllGather(d_h.as<Handles>() + rank, d_h.p, sizeof(Handles), ncclUint8, s->comm, S));
+    MVB_CUDA(cudaMemcpyAsync(all.data(), d_h.p, sizeof(Handles) * world, cudaMemcpyDeviceToHost, S));
+    MVB_CUDA(cudaStreamSynchronize(S));
+    std::vector<char*> vecs(world, nullptr), ctls(world, nullptr);
+    vecs[rank] = s->px_vec.as<char>(); ctls[rank] = s->px_ctl.as<char>();
+    for (uint32_t p = 0; ok && p < world; ++p) {
+        if (p == rank) continue;
+        void *a = nullptr, *b = nullptr;
+        if (cudaIpcOpenMemHandle(&a, all[p].vec, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = false; cudaGetLastError(); break; }
+        s->px_open.push_back(a);
+        if (cudaIpcOpenMemHandle(&b, all[p].ctl, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = false; cudaGetLastError(); break; }
+        s->px_open.push_back(b);
+        vecs[p] = (char*)a; ctls[p] = (char*)b;
+    }
+    // every rank or none (also the barrier: all ranks' set-up kernels, enqueued on S before this, have finished)
+    uint32_t* d_ok = reinterpret_cast<uint32_t*>(d_h.as<char>() + sizeof(Handles) * world);
+    uint32_t h_ok = ok ? 1u : 0u;
+    MVB_CUDA(cudaMemcpyAsync(d_ok, &h_ok, 4, cudaMemcpyHostToDevice, S));
+    MVB_NCCL(n->AllReduce(d_ok, d_ok, 1, ncclUint32, ncclMin, s->comm, S));
+    MVB_CUDA(cudaMemcpyAsync(&h_ok, d_ok, 4, cudaMemcpyDeviceToHost, S));
+    MVB_CUDA(cudaStreamSynchronize(S));
+    if (!h_ok) {
+        for (void* p : s->px_open) cudaIpcCloseMemHandle(p);
+        s->px_open.clear();
+        s->exchange_mode = MVB_EXCHANGE_NCCL;
+        return MVB_OK;
+    }
+    PeerExchange px{};
+    px.world = world; px.rank = rank; px.rec_stride = W;
+    for (uint32_t p = 0; p < world; ++p) {
+        px.vec[0][p] = reinterpret_cast<uint2*>(vecs[p]);
+        px.vec[1][p] = reinterpret_cast<uint2*>(vecs[p] + vec_piece);
+        px.normvec[p] = reinterpret_cast<uint2*>(vecs[p] + 2 * vec_piece);
+        px.xrec[p] = reinterpret_cast<uint32_t*>(ctls[p]);
+        px.flags[p] = reinterpret_cast<uint32_t*>(ctls[p] + xrec_bytes);
+    }
+    px.done = reinterpret_cast<uint32_t*>(ctls[rank] + xrec_bytes + 256);
+    px.error = reinterpret_cast<uint32_t*>(ctls[rank] + xrec_bytes + 512);
+    MVB_CUDA(s->d_px.alloc(sizeof px));
+    MVB_CUDA(cudaMemcpyAsync(s->d_px.p, &px, sizeof px, cudaMemcpyHostToDevice, S));
+    MVB_CUDA(cudaStreamSynchronize(S));                            // `px` is pageable and goes out of scope
+    s->exchange_mode = MVB_EXCHANGE_P2P;
+    return MVB_OK;
+}
+
+// A rank that never raised its flag (exchange_finish_kernel gave up waiting): the results are not valid.
+int check_peer_exchange(mvb_sim* s) {
+    if (s->exchange_mode != MVB_EXCHANGE_P2P) return MVB_OK;
+    uint32_t err = 0;
+    MVB_CUDA(cudaMemcpy(&err, s->px_ctl.as<char>() + s->px_ctl.bytes - 512, 4, cudaMemcpyDeviceToHost));
+    if (err) { set_error("agent-partitioned run: a rank did not finish a weekday within 20 s (peer-to-peer exchange)"); return MVB_ERR_COMM; }
+    return MVB_OK;
+}
+
+}  // namespace
 #include "create.cuh"
 #include "synth_device.cuh"
 extern "C" {
@@ -484,6 +589,7 @@ int mvb_partition_plan(const mvb_population* pop, uint32_t S, uint32_t H, uint32
     return MVB_OK;
 }
 
+int mvb_exchange_mode(const mvb_sim* s) { return s ? s->exchange_mode : MVB_EXCHANGE_NONE; }
 uint32_t mvb_n_replicas(const mvb_sim* s) { return s ? (uint32_t)s->reps.size() : 0; }
 uint32_t mvb_stats_width(const mvb_sim* s, uint32_t r) {
     return (s && r < s->reps.size()) ? MVB_STATS_FIXED + s->reps[r].S + s->reps[r].H : 0;
@@ -494,7 +600,7 @@ int mvb_sync(mvb_sim* s) {
     if (!s) { set_error("null handle"); return MVB_ERR_ARG; }
     MVB_CUDA(cudaSetDevice(s->device));
     MVB_CUDA(cudaStreamSynchronize(s->stream));
-    return MVB_OK;
+    return check_peer_exchange(s);
 }
 
 int mvb_step(mvb_sim* s, uint8_t weather_today, uint8_t weather_changed) {
@@ -671,6 +777,7 @@ int mvb_fetch_rows(mvb_sim* s, uint32_t* n_rows, uint32_t* days_out, uint32_t* r
     if (!s) { set_error("null handle"); return MVB_ERR_ARG; }
     MVB_CUDA(cudaSetDevice(s->device));
     MVB_CUDA(cudaStreamSynchronize(s->stream));
+    if (int rc = check_peer_exchange(s)) return rc;
     const uint32_t rows = s->cursor + 1;
     if (n_rows) *n_rows = rows;
     if (days_out) memcpy(days_out, s->row_days.data(), sizeof(uint32_t) * rows);
@@ -760,6 +867,7 @@ int mvb_get_state(mvb_sim* s, uint32_t r, float* habit, uint8_t* cur, uint8_t* l
     return MVB_OK;
 }
 
+#ifdef MVB_DEBUG_STAMPS
 // Debug hook (not part of the ABI): record {start of the first block, end of the last block} (globaltimer, ns) of the next
 // `n` day-kernel launches; a second call with out != nullptr copies what was recorded.  tools/launch_gaps.py.
 int mvbx_launch_stamps(mvb_sim* s, uint32_t n, unsigned long long* out, uint32_t* n_out) {
@@ -783,6 +891,7 @@ int mvbx_launch_stamps(mvb_sim* s, uint32_t n, unsigned long long* out, uint32_t
     StampCfg cfg{s->stamps.as<unsigned long long>(), s->rec.as<uint32_t>(), s->rec_stride, s->cursor + 1, n};
     return cudaMemcpyToSymbol(g_stamps, &cfg, sizeof cfg) == cudaSuccess ? 0 : -4;
 }
+#endif
 
 // Test hook (not part of the ABI in include/): the layout the GPU built for replica r against the host builder
 // (layout.cpp, the specification) on the same population (host pointers).  0 = identical; otherwise msg says what differs.

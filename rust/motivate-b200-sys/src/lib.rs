@@ -29,6 +29,9 @@ pub const MVB_N_COMMUTES: usize = 3;
 pub const MVB_STATS_FIXED: usize = 7;
 pub const MVB_UNIQUE_ID_BYTES: usize = 128;
 pub const MVB_FLAG_NONE: u32 = 0;
+pub const MVB_EXCHANGE_NONE: c_int = 0;
+pub const MVB_EXCHANGE_NCCL: c_int = 1;
+pub const MVB_EXCHANGE_P2P: c_int = 2;
 
 /// Everything `extern "C"`: names, argument order and struct field order follow the header exactly.
 pub mod raw {
@@ -134,6 +137,7 @@ pub mod raw {
         pub fn mvb_create_partitioned(pop: *const mvb_population, tab: *const mvb_tables, prm: *const mvb_params, device: c_int, rank: u32, world: u32, unique_id: *const c_void, out: *mut *mut mvb_sim) -> c_int;
         pub fn mvb_partition_owner(sim: *const mvb_sim, rank_out: *mut u32) -> c_int;
         pub fn mvb_partition_plan(pop: *const mvb_population, n_subcultures: u32, n_neighbourhoods: u32, world: u32, rank_out: *mut u32) -> c_int;
+        pub fn mvb_exchange_mode(sim: *const mvb_sim) -> c_int;
         pub fn mvb_synth_create(spec: *const mvb_synth_spec, out: *mut *mut mvb_synth) -> c_int;
         pub fn mvb_synth_create_device(spec: *const mvb_synth_spec, device: c_int, out: *mut *mut mvb_synth) -> c_int;
         pub fn mvb_synth_copy_to_host(device_population: *const mvb_synth, host_out: *mut *mut mvb_synth) -> c_int;
@@ -360,6 +364,12 @@ impl Sim {
         let mut out = vec![0u32; pop.n_agents()];
         check(unsafe { raw::mvb_partition_plan(&p, n_subcultures, n_neighbourhoods, world, out.as_mut_ptr()) })?;
         Ok(out)
+    }
+
+    /// How the ranks of an agent-partitioned handle exchange modes and counters: MVB_EXCHANGE_P2P (fused into the
+    /// weekday kernel, over peer memory), MVB_EXCHANGE_NCCL (all-gather + all-reduce) or MVB_EXCHANGE_NONE.
+    pub fn exchange_mode(&self) -> c_int {
+        unsafe { raw::mvb_exchange_mode(self.h) }
     }
 
     pub fn n_replicas(&self) -> usize {

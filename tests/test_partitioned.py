@@ -3,7 +3,7 @@ agents; after every weekday the ranks exchange packed modes and all-reduce the c
 
 CPU part: the partition plan (host logic of the library, no device) and a world_size-2 gloo emulation of the exchange
 protocol on the oracle.  GPU part (needs 2 devices; run with `gpurun --gpus 2 -- python -m pytest tests -m gpu -k partitioned`):
-2 NCCL ranks against one oracle run, bit for bit."""
+2 ranks against one oracle run, bit for bit, over both exchange paths (peer-to-peer stores fused into the weekday kernel; NCCL)."""
 import os
 import socket
 
@@ -95,26 +95,47 @@ def test_exchange_protocol_two_gloo_ranks(tmp_path):
     assert np.array_equal(np.load(out), rows)
 
 
-def nccl_worker(rank, world, idfile, out):
-    pop, tab, prm, w = inputs()
+def wait_for_id(rank, idfile):
     if rank == 0:
         open(idfile + ".tmp", "wb").write(mb.comm_unique_id()); os.rename(idfile + ".tmp", idfile)
     import time
     while not os.path.exists(idfile):
         time.sleep(0.05)
-    uid = open(idfile, "rb").read()
-    sim = mb.Simulation.partitioned(pop, tab, prm, device=rank, rank=rank, world=world, unique_id=uid)
+    return open(idfile, "rb").read()
+
+
+def nccl_worker(rank, world, idfile, out, exchange):
+    if exchange == "nccl":
+        os.environ["MVB_EXCHANGE"] = "nccl"                       # force the NCCL all-gather / all-reduce path
+    pop, tab, prm, w = inputs()
+    sim = mb.Simulation.partitioned(pop, tab, prm, device=rank, rank=rank, world=world, unique_id=wait_for_id(rank, idfile))
     days, rows = sim.run(w)
     st = sim.get_state(0)
-    np.savez(out + f".{rank}.npz", days=days, rows=rows[0], owner=sim.partition_owner(), **st)
+    np.savez(out + f".{rank}.npz", days=days, rows=rows[0], owner=sim.partition_owner(), exchange=sim.exchange_mode(), **st)
+    sim.close()
+    # a second handle (its own communicator), driven in pieces: a run, single steps, another run.  Epochs and flags of
+    # the peer-to-peer exchange carry over from call to call; the norm words travel with the last weekday of each piece
+    sim = mb.Simulation.partitioned(pop, tab, prm, device=rank, rank=rank, world=world, unique_id=wait_for_id(rank, idfile + "2"))
+    sim.run_async(w, 0, 6)
+    prev = w[max(d for d in range(1, 6) if d % 7 < 5)]            # the weather of the last weekday stepped
+    for day in range(6, 10):
+        if day % 7 < 5:
+            sim.step(w[day], prev != w[day]); prev = w[day]
+    sim.sync()
+    mid = sim.get_state(0)
+    sim.run_async(w, 10, N_DAYS)
+    sim.sync()
+    st2 = sim.get_state(0)
+    np.savez(out + f".pieces.{rank}.npz", mid_mode=mid["current_mode"], mid_norm=mid["norm"], **st2)
     sim.close()
 
 
 @pytest.mark.gpu
 @pytest.mark.skipif(_ffi.load().mvb_device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
-def test_partitioned_two_gpus_equal_oracle(tmp_path):
+@pytest.mark.parametrize("exchange", ["p2p", "nccl"])
+def test_partitioned_two_gpus_equal_oracle(tmp_path, exchange):
     out, idfile = str(tmp_path / "state"), str(tmp_path / "nccl_id")
-    mp.spawn(nccl_worker, args=(2, idfile, out), nprocs=2, join=True)
+    mp.spawn(nccl_worker, args=(2, idfile, out, exchange), nprocs=2, join=True)
     pop, tab, prm, w = inputs()
     o = OracleSimulation(pop, tab, prm)
     days, rows = o.run(w)
@@ -122,11 +143,26 @@ def test_partitioned_two_gpus_equal_oracle(tmp_path):
     z = [np.load(out + f".{r}.npz") for r in range(2)]
     assert np.array_equal(z[0]["owner"], z[1]["owner"]) and set(np.unique(z[0]["owner"])) == {0, 1}
     for r in range(2):
+        assert str(z[r]["exchange"]) == exchange, "the GPUs of one B200 box can map each other's memory"
         assert np.array_equal(z[r]["days"], days) and np.array_equal(z[r]["rows"], rows), f"rows on rank {r}"
         for k in ("current_mode", "norm", "hist"):
             assert np.array_equal(z[r][k], ref[k]), (r, k)              # every rank holds the full vectors
         mine = z[r]["owner"] == r
         assert np.array_equal(z[r]["habit"][mine].view(np.uint32), ref["habit"][mine].view(np.uint32))   # own habits
+    # the handle driven in pieces: state after day 9 and at the end
+    o2 = OracleSimulation(pop, tab, prm)
+    prev = w[0]
+    for day in range(1, 10):
+        if day % 7 < 5:
+            o2.step(w[day], prev != w[day]); prev = w[day]
+    mid = o2.get_state()
+    for r in range(2):
+        zp = np.load(out + f".pieces.{r}.npz")
+        assert np.array_equal(zp["mid_mode"], mid["current_mode"]) and np.array_equal(zp["mid_norm"], mid["norm"]), r
+        for k in ("current_mode", "norm", "hist"):
+            assert np.array_equal(zp[k], ref[k]), (r, k, "pieces")
+        mine = z[r]["owner"] == r
+        assert np.array_equal(zp["habit"][mine].view(np.uint32), ref["habit"][mine].view(np.uint32))
 
 
 @pytest.mark.gpu

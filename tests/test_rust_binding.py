@@ -119,7 +119,8 @@ def test_rust_constants_match_the_header():
     _, _, hc = parse_header()
     _, _, rc = parse_rust()
     for k in ("MVB_ABI_VERSION", "MVB_OK", "MVB_ERR_ARG", "MVB_ERR_CUDA", "MVB_ERR_NOMEM", "MVB_ERR_STATE", "MVB_ERR_DOMAIN",
-              "MVB_ERR_COMM", "MVB_N_MODES", "MVB_N_COMMUTES", "MVB_STATS_FIXED", "MVB_UNIQUE_ID_BYTES", "MVB_FLAG_NONE"):
+              "MVB_ERR_COMM", "MVB_N_MODES", "MVB_N_COMMUTES", "MVB_STATS_FIXED", "MVB_UNIQUE_ID_BYTES", "MVB_FLAG_NONE",
+              "MVB_EXCHANGE_NONE", "MVB_EXCHANGE_NCCL", "MVB_EXCHANGE_P2P"):
         assert hc[k] == rc[k], (k, hc.get(k), rc.get(k))
 
 

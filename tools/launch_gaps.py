@@ -4,7 +4,10 @@ and its last block ended (%globaltimer, ns; debug hook mvbx_launch_stamps).  gap
 the GPU idles between two weekdays, negative = tomorrow's first blocks were already running their launch-independent
 prologue while today's last blocks finished (programmatic dependent launch).  Re-executes itself with MVB_NO_PDL=1."""
 import ctypes as C, os, subprocess, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+# the stamps live in a debug build of the library (make -C motivate_b200/csrc stamps, here, before gpurun)
+os.environ.setdefault("MVB_LIB_PATH", os.path.join(ROOT, "motivate_b200", "libmotivate_b200_stamps.so"))
 if len(sys.argv) > 1 and sys.argv[1] == "arm":
     import numpy as np
     import motivate_b200 as mb

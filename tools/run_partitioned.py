@@ -36,7 +36,7 @@ dist.all_gather(allc, cnt)
 if rank == 0:
     m = max(float(x) for x in allt)
     print("per rank ms/weekday", [round(float(x), 3) for x in allt])
-    print(f"{n} agents H={H} world={world}: {m:.3f} ms/weekday = {n / m * 1e3:.3e} agent-days/s, "
+    print(f"{n} agents H={H} world={world} exchange={sim.exchange_mode()}: {m:.3f} ms/weekday = {n / m * 1e3:.3e} agent-days/s, "
           f"{100 * sim.algorithmic_bytes_per_day(0) / world / m * 1e3 / 1e9 / 6560.3:.1f}% of roofline per GPU; agents per rank {[int(c) for c in allc]}")
 sim.close()
 dist.destroy_process_group()
