@@ -14,6 +14,7 @@ struct SetupScalars {                 // device -> host after each stage
     SetupFlag flag;                   // first error of the graph-side checks
     uint32_t n_hubs, n_units;
     uint64_t sell_total, hub_total;
+    uint32_t push_total, push_chunks; // push mode: cold links of the owned SELL agents, chunks they are cut into
 };
 
 // layout_begin's decisions (layout.cpp) from the degree histogram cnt[h][kHubDegree - d] of the non-hub agents.
@@ -454,6 +455,7 @@ static int create_impl(uint32_t R, const mvb_population* const* pops, const mvb_
             L.N = N; L.N_pad = P.N_pad; L.Es = gi.Es; L.En = gi.En;
             L.n_hub_slices = P.n_hs; L.n_sell_slices = (P.N_pad - P.hub_pad) / 32; L.hot_words = P.hot_words;
             L.ranges = P.ranges; L.mode = P.mode; L.nb_slice_begin = P.nb_slice_begin; L.n_common_ranges = P.n_common_ranges;
+            L.push = !P.all_hot && pick_push_mode(P.N_pad, R);      // cold links of SELL agents through push_kernel (layout.h)
             g->common_words = P.common_words;
             if (L.hot_words + 4 > s->vec_cap_words) { set_error("internal: staged vector larger than its shared-memory slot"); return MVB_ERR_STATE; }
             const uint32_t n_hub_rows = P.n_hs * 32, n_sell = L.n_sell_slices, n2 = P.n2, n_hubs = P.n_hubs;
@@ -520,7 +522,7 @@ static int create_impl(uint32_t R, const mvb_population* const* pops, const mvb_
             MVB_CUDA(sums.alloc(8 * ((size_t)scan_blocks(std::max<uint64_t>(n_sell, n_hub_rows)) + 8), S));
             if (n_sell) {
                 slice_dims_kernel<<<(unsigned)(((uint64_t)n_sell * 32 + 255) / 256), 256, 0, S>>>(P.n_hs, n_sell, g->int2ext.as<uint32_t>(), deg.as<uint32_t>(),
-                                                                                                nsh.as<uint32_t>(), nnh.as<uint32_t>(), sell_K.as<uint32_t>(), sell_len.as<uint64_t>());
+                                                                                                nsh.as<uint32_t>(), nnh.as<uint32_t>(), L.push ? 1u : 0u, sell_K.as<uint32_t>(), sell_len.as<uint64_t>());
                 MVB_CUDA(exclusive_scan<uint64_t>(sell_len.as<uint64_t>(), sell_off.as<uint64_t>(), n_sell, sums.as<uint64_t>(), &d_scal->sell_total, S));
             }
             if (n_hub_rows) {
@@ -554,7 +556,7 @@ static int create_impl(uint32_t R, const mvb_population* const* pops, const mvb_
                 own_hub_b = std::min(b, nh); own_hub_e = std::min(e, nh);
                 own_sell_b = std::max(b, nh) - nh; own_sell_e = std::max(e, nh) - nh;
                 std::vector<uint64_t> off((size_t)n_sell + 1, 0);
-                for (uint32_t k = 0; k < n_sell; ++k) off[k + 1] = off[k] + 32ull * ((L.sell_K[k] & 0xFFFFu) + (L.sell_K[k] >> 16));
+                for (uint32_t k = 0; k < n_sell; ++k) off[k + 1] = off[k] + 32ull * ((L.sell_K[k] & 0xFFFFu) + (L.push ? 0u : L.sell_K[k] >> 16));
                 sell_rebase = off[own_sell_b]; sell_own_len = off[own_sell_e] - off[own_sell_b];
                 hub_rebase = h_hub_off[(size_t)own_hub_b * 32]; hub_own_len = h_hub_off[(size_t)own_hub_e * 32] - hub_rebase;
             }
@@ -564,7 +566,7 @@ static int create_impl(uint32_t R, const mvb_population* const* pops, const mvb_
             MVB_CARVE(s->mem, g->hub_units, 16 * ((size_t)n_units + 1));
             MVB_CARVE(s->mem, g->hub_codes, 4 * L.hub_codes_len);
             MVB_CARVE(s->mem, g->sell_codes, 4 * L.sell_codes_len);
-            sell_meta_kernel<<<(n_sell + 64 + 255) / 256, 256, 0, S>>>(n_sell, sell_off.as<uint64_t>(), sell_K.as<uint32_t>(), sell_rebase, own_sell_b, own_sell_e, g->sell_meta.as<uint4>());
+            sell_meta_kernel<<<(n_sell + 64 + 255) / 256, 256, 0, S>>>(n_sell, sell_off.as<uint64_t>(), sell_K.as<uint32_t>(), sell_rebase, own_sell_b, own_sell_e, L.push ? 1u : 0u, g->sell_meta.as<uint4>());
             hub_units_kernel<<<(n_hub_rows + 1 + 255) / 256, 256, 0, S>>>(n_hub_rows, g->hub_deg.as<uint4>(), unit_base.as<uint32_t>(), g->hub_off.as<uint64_t>(), hub_rebase,
                                                                         g->hub_units.as<uint4>(), g->hub_unit_begin.as<uint32_t>(), n_units);
             if (hub_rebase && n_hub_rows) rebase_u64_kernel<<<(n_hub_rows + 255) / 256, 256, 0, S>>>(g->hub_off.as<uint64_t>(), n_hub_rows, hub_rebase);
@@ -577,19 +579,63 @@ static int create_impl(uint32_t R, const mvb_population* const* pops, const mvb_
             tcode_kernel<<<(P.N_pad + 255) / 256, 256, 0, S>>>(P.N_pad, g->int2ext.as<uint32_t>(), g->ranges.as<StageRange>(), (uint32_t)P.ranges.size(),
                                                              is_hot.as<uint8_t>(), P.mode == kLayoutLocal ? gi.nbhd : nullptr, H, P.hub_pad, tcode.as<uint32_t>(), tcold.as<uint32_t>());
             MVB_CUDA(cudaGetLastError());
+            // ---- push mode: where every owned SELL agent's cold links go in the (still unsorted) list ------------------
+            UpBuf pcnt, poff, pk[2], pv[2], pscratch, psums, pfirst;
+            const uint32_t n_own_slots = (own_sell_e - own_sell_b) * 32;
+            uint32_t n_push = 0, n_chunks = 0;
+            const uint32_t push_max_agents = push_chunk_agents(~0ull, s->grid);       // (the cap itself: kPushChunkMax unless a test lowers it)
+            if (L.push && n_own_slots) {
+                const uint32_t chunk_cap = std::min<uint64_t>(65535, 4 * ((uint64_t)n_own_slots / push_max_agents + s->grid) + 8);
+                MVB_CUDA(pcnt.alloc(4 * (size_t)n_own_slots, S)); MVB_CUDA(poff.alloc(4 * (size_t)n_own_slots + 4, S));
+                MVB_CUDA(psums.alloc(4 * ((size_t)scan_blocks(n_own_slots) + 8), S));
+                MVB_CUDA(pfirst.alloc(4 * ((size_t)chunk_cap + 1), S));
+                push_count_kernel<<<(n_own_slots + 255) / 256, 256, 0, S>>>(P.n_hs, own_sell_b * 32, n_own_slots, g->int2ext.as<uint32_t>(), deg.as<uint32_t>(),
+                                                                           nsh.as<uint32_t>(), nnh.as<uint32_t>(), pcnt.as<uint32_t>());
+                MVB_CUDA(exclusive_scan<uint32_t>(pcnt.as<uint32_t>(), poff.as<uint32_t>(), n_own_slots, psums.as<uint32_t>(), &d_scal->push_total, S));
+                push_plan_kernel<<<1, 32, 0, S>>>(n_own_slots, poff.as<uint32_t>(), &d_scal->push_total, s->grid, push_max_agents, chunk_cap,
+                                                 pfirst.as<uint32_t>(), &d_scal->push_chunks);
+                MVB_CUDA(cudaMemcpyAsync(h_scal, scal.p, sizeof(SetupScalars), cudaMemcpyDeviceToHost, S));
+                if (int rc = host_wait()) return rc;
+                n_push = h_scal->push_total; n_chunks = h_scal->push_chunks;
+                if (n_chunks == 0xFFFFFFFFu) { set_error("internal: too many push chunks for %u agents", n_own_slots); return MVB_ERR_STATE; }
+                for (int k = 0; k < 2; ++k) { MVB_CUDA(pk[k].alloc(4 * (size_t)n_push + 4, S)); MVB_CUDA(pv[k].alloc(4 * (size_t)n_push + 4, S)); }
+                MVB_CUDA(pscratch.alloc(4 * radix_scratch_u32(n_push), S));
+            }
             FillArgs fa{gi.srp, gi.scol, gi.nrp, gi.ncol, tcode.as<uint32_t>(), g->int2ext.as<uint32_t>(), P.n_hs, n_sell,
                         g->sell_meta.as<uint4>(), g->sell_codes.as<uint32_t>(), g->deg.as<uint32_t>(),
                         g->hub_off.as<uint64_t>(), g->hub_deg.as<uint4>(), g->hub_codes.as<uint32_t>(),
                         own_hub_b, own_hub_e, own_sell_b, own_sell_e,
-                        P.mode == kLayoutLocal ? tcold.as<uint32_t>() : nullptr, is_hot.as<uint8_t>(), gi.nbhd};
+                        P.mode == kLayoutLocal ? tcold.as<uint32_t>() : nullptr, is_hot.as<uint8_t>(), gi.nbhd,
+                        n_chunks ? pk[0].as<uint32_t>() : nullptr, pv[0].as<uint32_t>(), poff.as<uint32_t>(), pfirst.as<uint32_t>(), n_chunks};
             MVB_CUDA(cudaMemsetAsync(g->deg.p, 0, g->deg.bytes, S));
             if (n_sell) fill_sell_kernel<<<(unsigned)(((uint64_t)n_sell * 32 + 255) / 256), 256, 0, S>>>(fa);
             if (P.n_hs) fill_hub_kernel<<<(unsigned)(((uint64_t)n_hub_rows * 32 + 255) / 256), 256, 0, S>>>(fa, n_hub_rows);
             MVB_CUDA(cudaGetLastError());
             if (world > 1) { s->own[0] = own_hub_b; s->own[1] = own_hub_e; s->own[2] = own_sell_b; s->own[3] = own_sell_e; }
+            if (n_chunks) {
+                // ---- push mode: sort every chunk's entries by target word (the chunks are contiguous already: a stable sort
+                // by word, then by chunk), and keep {code u32, source u16} + the chunk boundaries
+                uint32_t* kk2[2] = {pk[0].as<uint32_t>(), pk[1].as<uint32_t>()};
+                uint32_t* vv2[2] = {pv[0].as<uint32_t>(), pv[1].as<uint32_t>()};
+                int pc = 0;
+                MVB_CUDA(radix_sort_pairs(kk2, vv2, n_push, bits_for(P.N_pad / 16), pscratch.as<uint32_t>(), &pc, S, 7));          // code >> 7 = word of the vector
+                MVB_CUDA(radix_sort_pairs(vv2, kk2, n_push, bits_for(n_chunks - 1), pscratch.as<uint32_t>(), &pc, S, 16, pc));    // roles swapped: key = chunk << 16 | source
+                MVB_CARVE(s->mem, g->push_code, 4 * (size_t)n_push + 64 * 1024);     // + slack: the kernel reads rows of 4 096 entries
+                MVB_CARVE(s->mem, g->push_src, 2 * (size_t)n_push + 32 * 1024);
+                MVB_CARVE(s->mem, g->push_chunk_begin, 4 * ((size_t)n_chunks + 1));
+                MVB_CARVE(s->mem, g->push_chunk_first, 4 * ((size_t)n_chunks + 1));
+                MVB_CUDA(cudaMemcpyAsync(g->push_chunk_first.p, pfirst.p, 4 * ((size_t)n_chunks + 1), cudaMemcpyDeviceToDevice, S));
+                MVB_CUDA(cudaMemcpyAsync(g->push_code.p, kk2[pc], 4 * (size_t)n_push, cudaMemcpyDeviceToDevice, S));
+                if (n_push) push_src_kernel<<<sms * 8, 256, 0, S>>>(n_push, vv2[pc], g->push_src.as<uint16_t>());
+                push_chunk_begin_kernel<<<(n_chunks + 1 + 255) / 256, 256, 0, S>>>(n_chunks, n_own_slots, pfirst.as<uint32_t>(), poff.as<uint32_t>(), &d_scal->push_total,
+                                                                                  g->push_chunk_begin.as<uint32_t>());
+                MVB_CUDA(cudaGetLastError());
+                g->push_chunks = n_chunks; g->push_chunk_agents = push_max_agents; g->push_own_slots = n_own_slots; g->push_links = n_push;
+                g->push_first_slot = (P.n_hs + own_sell_b) * 32;
+            }
             // everything temporary goes back to the pool in stream order
             for (UpBuf* b : {&deg, &key[0], &key[1], &val[0], &val[1], &cnt, &scal, &scratch, &is_hot, &nsh, &nnh, &plan, &hk[0], &hk[1], &hv[0], &hv[1],
-                             &sell_K, &sell_len, &sell_off, &hub_nu, &hub_len, &unit_base, &sums, &tcode, &tcold})
+                             &sell_K, &sell_len, &sell_off, &hub_nu, &hub_len, &unit_base, &sums, &tcode, &tcold, &pcnt, &poff, &pk[0], &pk[1], &pv[0], &pv[1], &pscratch, &psums, &pfirst})
                 b->release(S);
             for (UpBuf& b : gi.b) b.release(S);
         }
@@ -621,6 +667,7 @@ static int create_impl(uint32_t R, const mvb_population* const* pops, const mvb_
             MVB_CARVE(s->mem, rp.tables_u, sizeof(uint32_t) * 5 * rp.H);
             MVB_CARVE(s->mem, rp.cong, sizeof(float) * 4 * rp.H);
             MVB_CARVE(s->mem, rp.hub_cnt, hub_cnt_bytes);
+            if (g->push_chunks) MVB_CARVE(s->mem, rp.push_cnt, 8 * (size_t)g->push_own_slots);
             if (si.ev) MVB_CUDA(cudaStreamWaitEvent(S, si.ev, 0));
             // tables + residents per neighbourhood (counted on the device, neighbourhood.rs:71)
             if (int rc = upload_tables(s, rp, t)) return rc;
@@ -662,6 +709,7 @@ static int create_impl(uint32_t R, const mvb_population* const* pops, const mvb_
         d.cap = rp.tables_u.as<uint32_t>(); d.nres = rp.tables_u.as<uint32_t>() + 4 * rp.H;
         d.cong = rp.cong.as<float>();
         d.int2ext = g->int2ext.as<uint32_t>();
+        d.push_cnt = g->push_chunks ? rp.push_cnt.as<uint2>() - g->push_first_slot : nullptr;      // indexed by internal slot
         d.local_mode = L.mode == kLayoutLocal ? 1u : 0u;
         // cold gathers bypass L1 when the vector is several times what shared memory + L1 hold (day_kernels.cuh: ld_cold;
         // tools/ab_cold_cg.sh: 8M agents -4.8 %, 2M +0.6 %, 1M +1 % with the bypass)
@@ -680,6 +728,7 @@ static int create_impl(uint32_t R, const mvb_population* const* pops, const mvb_
         MVB_CUDA(cudaFuncSetAttribute(day_kernel<false, 1024, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
         MVB_CUDA(cudaFuncSetAttribute(day_kernel<false, 1024, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
     }
+    MVB_CUDA(cudaFuncSetAttribute(push_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * kPushChunkMax)));
     if (s->census_smem > 48 * 1024)
         MVB_CUDA(cudaFuncSetAttribute(census_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->census_smem));
     s->rank = rank; s->world = world;

@@ -75,6 +75,8 @@ struct RepDev {                     // device-side descriptor of one replica
     const uint32_t* nb_slice_begin; // [H + 1] SELL slices of every neighbourhood (LOCAL layout: parts are neighbourhood-pure)
     uint32_t local_mode, cold_cg;   // layout.h LayoutMode; cold gathers bypass L1 (ld_cold)
     const uint4* part_table;        // LOCAL layout: part p of a launch = {neighbourhood, class q, classes Q of that neighbourhood, 0}
+    const uint2* push_cnt;          // push mode (layout.h): per-mode counts {social, neighbour} of an agent's cold links, filled by
+                                    // push_kernel before the day kernel, indexed by internal slot (pointer pre-offset); else nullptr
     const PeerExchange* px;         // agent-partitioned mode, exchange over peer memory (day_kernel<.., XCHG = true>), else nullptr
     uint32_t px_epoch, px_norms;    // this launch's epoch (flag value raised when the rank has finished); also store the norm words
 };
@@ -623,7 +625,12 @@ day_kernel(const __grid_constant__ RepArray reps, uint32_t R, uint32_t P, uint32
             const uint2 own = ld_stream_v2(r.vec[parity] + slice);
             const int ds_h = (int)(dg & 0xFFu), dn_h = (int)((dg >> 8) & 0xFFu), ds_c = (int)((dg >> 16) & 0xFFu), dn_c = (int)(dg >> 24);
             uint32_t acc_s = 0, acc_n = 0;
-            accumulate_block(blk, KK & 0xFFFFu, KK >> 16, lane, ds_h, ds_c, ds_c + dn_c, s_vec, g_vec, r.cold_cg != 0, acc_s, acc_n);
+            int d_c = ds_c + dn_c;
+            if (r.push_cnt) {                          // the cold links were counted by push_kernel; the block has hot rows only
+                const uint2 pc = ld_stream_v2(r.push_cnt + (size_t)slice * 32 + lane);
+                acc_s = pc.x; acc_n = pc.y; d_c = 0;
+            }
+            accumulate_block(blk, KK & 0xFFFFu, KK >> 16, lane, ds_h, ds_c, d_c, s_vec, g_vec, r.cold_cg != 0, acc_s, acc_n);
             acc_s = car_counts(acc_s, (uint32_t)(ds_h + ds_c));
             acc_n = car_counts(acc_n, (uint32_t)(dn_h + dn_c));
             uint32_t cs[4], cn[4];
@@ -687,6 +694,60 @@ __global__ void exchange_finish_kernel(const PeerExchange* px, uint32_t epoch, u
         uint32_t sum = 0;
         for (uint32_t p = 0; p < world; ++p) sum += ld_cg_u32(part + (size_t)p * W + j);
         rec_row[j] = sum;
+    }
+}
+
+// ---- push mode: the cold links of the SELL agents, turned round (layout.h) ---------------------------------------
+// One launch per weekday BEFORE the day kernel.  A block takes chunks b, b + grid, ...; a chunk = up to kPushChunkMax
+// consecutive SELL agents this handle updates, their packed counters {social, neighbour} (bytes 1..3 = modes 1..3, as in
+// accumulate_block) in shared memory.  The chunk's cold links come as two coalesced streams sorted by target (code u32,
+// source u16): a warp's 32 gathers fall into a few 128-byte lines of the L2-resident vector, and each gathered mode is
+// added to its source's counter by a shared-memory reduction (Car, mode 0, is derived from the list length and skipped).
+struct PushDesc {
+    const uint32_t* code; const uint16_t* src;      // [n cold links], chunk by chunk, sorted by target inside a chunk
+    const uint32_t* chunk_begin;                    // [n_chunks + 1] first list entry of every chunk
+    const uint32_t* chunk_first;                    // [n_chunks + 1] first owned SELL slot of every chunk (chunks hold about the same number of links)
+    uint2* cnt;                                     // [n_own_slots] out: counts of every owned SELL agent
+    uint32_t n_chunks, cold_cg;
+};
+__global__ void __launch_bounds__(1024, 1) push_kernel(const PushDesc d, const uint32_t* __restrict__ g_vec) {
+    extern __shared__ __align__(16) uint32_t s_cnt[];                    // [chunk_agents][2]
+    const uint32_t tid = threadIdx.x;
+    constexpr uint32_t U = 4;
+    for (uint32_t c = blockIdx.x; c < d.n_chunks; c += gridDim.x) {
+        const uint32_t first = d.chunk_first[c], n_ag = d.chunk_first[c + 1] - first;
+        for (uint32_t k = tid; k < 2 * n_ag; k += 1024) s_cnt[k] = 0;
+        __syncthreads();
+        const uint32_t b = d.chunk_begin[c], e = d.chunk_begin[c + 1];
+        // software pipeline: the next U entries of both streams are on their way from HBM while the current ones are
+        // gathered and reduced (a thread has one dependent chain code -> gather -> reduction per entry otherwise)
+        uint32_t code_n[U], src_n[U];
+        auto fetch = [&](uint32_t i0) {
+#pragma unroll
+            for (uint32_t u = 0; u < U; ++u) {
+                const uint32_t i = i0 + 1024 * u;
+                const bool ok = i < e;
+                code_n[u] = ok ? ld_stream_u32(d.code + i) : 0u;
+                src_n[u] = ok ? (uint32_t)__ldg(d.src + i) : 0xFFFFFFFFu;
+            }
+        };
+        if (b + tid < e) fetch(b + tid);
+        for (uint32_t i0 = b + tid; i0 < e; i0 += 1024 * U) {
+            uint32_t code[U], src[U], w[U];
+#pragma unroll
+            for (uint32_t u = 0; u < U; ++u) { code[u] = code_n[u]; src[u] = src_n[u]; }
+            if (i0 + 1024 * U < e) fetch(i0 + 1024 * U);
+#pragma unroll
+            for (uint32_t u = 0; u < U; ++u) w[u] = src[u] != 0xFFFFFFFFu ? ld_cold(g_vec, code[u], d.cold_cg != 0) : 0u;
+#pragma unroll
+            for (uint32_t u = 0; u < U; ++u) {
+                const uint32_t m = __funnelshift_l(0u, w[u], code[u]) >> 30;
+                if (m) smem_add(&s_cnt[2u * (src[u] & 0x7FFFu) + ((src[u] >> 15) & 1u)], 1u << (8u * m));
+            }
+        }
+        __syncthreads();
+        for (uint32_t k = tid; k < n_ag; k += 1024) d.cnt[first + k] = make_uint2(s_cnt[2 * k], s_cnt[2 * k + 1]);
+        __syncthreads();
     }
 }
 

@@ -24,6 +24,10 @@ struct FillArgs {
     const uint32_t* tcold;                               // LOCAL layout: [N] cold code of a target (nullptr: GLOBAL layout)
     const uint8_t* cls;                                  // [N] 0 never staged, 1 staged for every block, 2 for blocks of its own neighbourhood
     const uint16_t* nbhd;                                // [N] caller's neighbourhood array
+    // push mode (layout.h): the cold links of owned SELL agents go to a list instead of the block's cold rows
+    uint32_t* push_code; uint32_t* push_val;             // [n cold links] target code; chunk << 16 | neighbour-list bit << 15 | agent index in the chunk
+    const uint32_t* push_off;                            // [owned SELL slots] first list entry of the agent
+    const uint32_t* push_first; uint32_t push_chunks;    // [push_chunks + 1] first owned SELL slot of every chunk
 };
 // Code of the link src -> t (| 1 if hot).  LOCAL layout: a target staged with its neighbourhood's prefix is hot only for
 // sources of that neighbourhood that are not hubs (hub slices mix neighbourhoods); everybody else reads it from L2.
@@ -31,6 +35,13 @@ __device__ __forceinline__ uint32_t link_code(const FillArgs& a, uint32_t src_nb
     uint32_t c = a.tcode[t];
     if (a.tcold && (c & 1u) && a.cls[t] == 2 && (src_is_hub || a.nbhd[t] != src_nbhd)) c = a.tcold[t];
     return c;
+}
+
+// chunk of every owned SELL slot's agent: c << 16 | index in the chunk
+__device__ __forceinline__ uint32_t push_chunk_of(const uint32_t* __restrict__ first, uint32_t n_chunks, uint32_t own_k) {
+    uint32_t lo = 0, hi = n_chunks;                                              // the last chunk starting at or before own_k
+    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (first[mid] <= own_k) lo = mid; else hi = mid; }
+    return lo << 16 | (own_k - first[lo]);
 }
 
 __global__ void fill_u32_kernel(uint32_t* __restrict__ p, uint64_t n, uint32_t v) {
@@ -115,14 +126,22 @@ __global__ void fill_sell_kernel(FillArgs a) {
     const uint32_t K = meta.z & 0xFFFFu;
     uint32_t kh = 0, kc = 0;
     const uint32_t my_nb = a.nbhd[e];
+    const uint32_t own_k = slot_in_sell - a.own_sell_begin * 32;                  // push mode: place among the owned SELL slots
+    const uint32_t pv = a.push_code ? push_chunk_of(a.push_first, a.push_chunks, own_k) : 0u;
+    const uint32_t po = a.push_code ? a.push_off[own_k] : 0u;
+    auto cold = [&](uint32_t c, uint32_t list) {
+        if (a.push_code) { a.push_code[po + kc] = c; a.push_val[po + kc] = pv | list << 15; }
+        else put_cold(blk, K, lane, kc, c);
+        ++kc;
+    };
     for (uint64_t x = a.s_rowptr[e]; x < a.s_rowptr[e + 1]; ++x) {
         const uint32_t c = link_code(a, my_nb, false, a.s_col[x]);
-        if (c & 1u) put_hot(blk, K, lane, kh++, c & ~1u); else put_cold(blk, K, lane, kc++, c);
+        if (c & 1u) put_hot(blk, K, lane, kh++, c & ~1u); else cold(c, 0u);
     }
     const uint32_t c_sh = kh, c_sc = kc;
     for (uint64_t x = a.n_rowptr[e]; x < a.n_rowptr[e + 1]; ++x) {
         const uint32_t c = link_code(a, my_nb, false, a.n_col[x]);
-        if (c & 1u) put_hot(blk, K, lane, kh++, c & ~1u); else put_cold(blk, K, lane, kc++, c);
+        if (c & 1u) put_hot(blk, K, lane, kh++, c & ~1u); else cold(c, 1u);
     }
     a.deg[slot] = c_sh | (kh - c_sh) << 8 | c_sc << 16 | (kc - c_sc) << 24;
 }

@@ -41,6 +41,23 @@ LayoutMode pick_layout_mode(uint32_t N_pad, uint32_t capacity_agents, uint32_t n
     return (uint64_t)N_pad * 2 > (uint64_t)capacity_agents * 3 ? kLayoutLocal : kLayoutGlobal;
 }
 
+bool pick_push_mode(uint32_t N_pad, uint32_t n_replicas) {
+    if (const char* e = getenv("MVB_PUSH")) return atoi(e) != 0;
+    // one large population per handle (BASELINE config 4): measured on B200, see layout.h; with several replicas per
+    // launch the populations are small enough for the pull path
+    return n_replicas == 1 && N_pad > 4u * 1000u * 1000u;
+}
+uint32_t push_chunk_agents(uint64_t own_slots, uint32_t grid) {
+    uint32_t cap = kPushChunkMax;
+    if (const char* e = getenv("MVB_PUSH_CHUNK")) cap = std::min<uint32_t>(kPushChunkMax, std::max(32, atoi(e)) / 32 * 32);   // tests: several chunks on small populations
+    if (!own_slots) return 32;
+    if (own_slots == ~0ull) return cap;
+    uint64_t rounds = 1;
+    while ((own_slots + rounds * grid - 1) / (rounds * grid) > cap) ++rounds;
+    const uint64_t c = (own_slots + rounds * grid - 1) / (rounds * grid);
+    return (uint32_t)std::min<uint64_t>(cap, (c + 31) / 32 * 32);
+}
+
 int layout_begin(const mvb_population& pop, uint32_t H, uint32_t capacity_agents, GraphLayout& L, LayoutWork& W, uint32_t n_replicas) {
     const uint32_t N = pop.n_agents;
     const uint64_t* srp = pop.social_rowptr;
@@ -116,6 +133,7 @@ int layout_begin(const mvb_population& pop, uint32_t H, uint32_t capacity_agents
     const bool all_hot = W.all_hot = L.N_pad <= capacity_agents;
     W.capacity_agents = capacity_agents;
     W.mode = L.mode = pick_layout_mode(L.N_pad, capacity_agents, n_replicas);
+    L.push = !all_hot && pick_push_mode(L.N_pad, n_replicas);
     W.staged_hub_slots = all_hot ? hub_pad : std::min(hub_pad, capacity_agents);
     W.take_common.assign(H, 0);
     if (W.mode == kLayoutLocal) {
@@ -265,7 +283,7 @@ int layout_finish(const mvb_population& pop, LayoutWork& W, GraphLayout& L, bool
                 }
                 L.sell_off[s] = off;
                 L.sell_K[s] = K | Kc << 16;
-                off += (uint64_t)32 * (K + Kc);
+                off += (uint64_t)32 * (K + (L.push ? 0u : Kc));     // push mode: the block holds hot rows only
             }
         }
     }
@@ -372,7 +390,7 @@ int layout_finish(const mvb_population& pop, LayoutWork& W, GraphLayout& L, bool
     // one 16-byte record per slice; 64 zero records of slack let the kernel prefetch past the end
     L.sell_meta.assign((size_t)L.n_sell_slices + 64, uint4x{0, 0, 0, 0});
     for (uint32_t s = 0; s < L.n_sell_slices; ++s)
-        L.sell_meta[s] = uint4x{(uint32_t)L.sell_off[s], (uint32_t)(L.sell_off[s] >> 32), L.sell_K[s], 0};
+        L.sell_meta[s] = uint4x{(uint32_t)L.sell_off[s], (uint32_t)(L.sell_off[s] >> 32), L.push ? L.sell_K[s] & 0xFFFFu : L.sell_K[s], 0};
     return MVB_OK;
 }
 
@@ -392,9 +410,12 @@ namespace {
 // of 50M agents timed on one GPU for a grid of weights): 8 ranks, H = 10: 1.16-1.20 ms per rank with these values
 // (0.83-1.71 with the GLOBAL ones), H = 64: 0.73-0.79 ms (0.66-1.10).  The same model hands every neighbourhood its share
 // of a rank's parts (create.cuh): a neighbourhood's last, cold-heavy slices cost several times its first ones.
-struct WorkModel { uint64_t cold, per_agent, hub10; };
+struct WorkModel { uint64_t cold, per_agent, hub10, hub_cold; };
 WorkModel work_model(const GraphLayout& L) {
-    WorkModel m = L.mode == kLayoutLocal ? WorkModel{8, 40, 15} : WorkModel{2, 64, 25};
+    WorkModel m = L.mode == kLayoutLocal ? WorkModel{8, 40, 15, 8} : WorkModel{2, 64, 25, 2};
+    if (L.push) m.cold = 3;          // a pushed cold link of a SELL agent: sorted gather + shared-memory reduction, ~1.2 per clock per SM;
+                                     // a hub's cold links stay on the pull path (hub_cold)
+    if (const char* e = getenv("MVB_PART_HUBCOLD")) m.hub_cold = (uint64_t)atoi(e);
     if (const char* e = getenv("MVB_PART_COLD")) m.cold = (uint64_t)atoi(e);          // calibration experiments
     if (const char* e = getenv("MVB_PART_AGENT")) m.per_agent = (uint64_t)atoi(e);
     if (const char* e = getenv("MVB_PART_HUB10")) m.hub10 = (uint64_t)atoi(e);
@@ -415,7 +436,7 @@ void partition_slices(const GraphLayout& L, uint32_t world, std::vector<uint32_t
         uint64_t w = 0;
         for (uint32_t k = 0; k < 32; ++k) {
             const uint32_t* dg = &L.hub_deg[(size_t)4 * (hs * 32 + k)];
-            w += m.hub10 * ((uint64_t)dg[0] + dg[1] + m.cold * (dg[2] + dg[3])) / 10 + m.per_agent;
+            w += m.hub10 * ((uint64_t)dg[0] + dg[1] + m.hub_cold * (dg[2] + dg[3])) / 10 + m.per_agent;
         }
         work[hs] = w;
     }

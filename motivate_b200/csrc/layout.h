@@ -99,6 +99,21 @@ enum LayoutMode : uint32_t { kLayoutGlobal = 0, kLayoutLocal = 1 };
 // fixed cost outweighs the cold links it saves on populations just above the capacity).  MVB_LAYOUT=global|local overrides.
 LayoutMode pick_layout_mode(uint32_t N_pad, uint32_t capacity_agents, uint32_t n_replicas);
 
+// PUSH mode for the cold links of SELL agents (large single populations).  A divergent gather from the L2-resident vector
+// costs ~2 clocks per link whatever the path (L1TEX wavefronts: tools/microbench_cold.cu), so where most links are cold
+// they are turned round: the SELL slices a handle updates are cut into chunks of <= kPushChunkMax agents whose packed
+// counters fit in shared memory; a chunk's cold links are stored as (target code u32, source u16 = social/neighbour bit
+// << 15 | agent index in the chunk) SORTED BY TARGET, so that the 32 gathers of a warp fall into a few 128-byte lines, and
+// push_kernel (day_kernels.cuh) adds every gathered mode to its source's counter with a shared-memory reduction
+// (tools/microbench_push.cu: 1.0-1.9 links per clock per SM against 0.5-0.85 for the pull).  The day kernel then finds
+// the counts of an agent's cold links in push_cnt[slot] and its SELL block holds hot rows only (Kc rows are not stored;
+// sell_K keeps Kc for the work model).  Hub agents keep their cold rows (pull).  MVB_PUSH=0|1 overrides the choice.
+constexpr uint32_t kPushChunkMax = 24576;    // agents per chunk: 8 bytes of counters each = 192 KB of shared memory; index < 2^15
+bool pick_push_mode(uint32_t N_pad, uint32_t n_replicas);
+// agents per chunk for a handle that updates `own_slots` SELL slots on a grid of `grid` blocks: as large as allowed (the
+// longer a chunk's list, the closer its sorted targets), a whole number of rounds of the grid, a multiple of 32
+uint32_t push_chunk_agents(uint64_t own_slots, uint32_t grid);
+
 struct uint4x { uint32_t x, y, z, w; };   // host-side mirror of CUDA's uint4 (16 bytes)
 
 struct StageRange {                // one contiguous piece of the mode vector staged in shared memory
@@ -124,6 +139,7 @@ struct GraphLayout {
                                       // only its own blocks stage, placed behind the n_common = 1 + H common ranges
     uint32_t n_common_ranges = 0;     // ranges every block stages (all of them in the GLOBAL layout)
     uint32_t mode = kLayoutGlobal;
+    bool push = false;                // cold links of SELL agents go through push_kernel: SELL blocks hold hot rows only (see above)
     std::vector<uint32_t> nb_slice_begin;  // [H + 1] SELL slices of neighbourhood h: [nb_slice_begin[h], nb_slice_begin[h + 1])
     std::vector<uint32_t> tcold;      // LOCAL, with tcode: the cold code of every target (a neighbourhood-prefix target is hot
                                       // only for sources of its own neighbourhood)

@@ -169,17 +169,17 @@ __global__ void __launch_bounds__(kRsThreads) radix_scatter_kernel(const uint32_
 }
 inline uint32_t radix_tiles(uint32_t n) { return (n + kRsTile - 1) / kRsTile; }
 inline size_t radix_scratch_u32(uint32_t n) { const size_t c = (size_t)256 * radix_tiles(n); return c + scan_blocks(c) + 8; }
-// Sorts by the low `bits` bits of the key, stable.  keys/vals are ping-pong buffers [2][n]; returns in *result which
-// half holds the output (0 or 1).  scratch: radix_scratch_u32(n) words.
+// Sorts by bits [shift0, shift0 + bits) of the key, stable.  keys/vals are ping-pong buffers [2][n]; returns in *result
+// which half holds the output (0 or 1; `start` = the half that holds the input).  scratch: radix_scratch_u32(n) words.
 inline cudaError_t radix_sort_pairs(uint32_t* keys[2], uint32_t* vals[2], uint32_t n, uint32_t bits, uint32_t* scratch,
-                                    int* result, cudaStream_t st) {
-    int cur = 0;
+                                    int* result, cudaStream_t st, uint32_t shift0 = 0, int start = 0) {
+    int cur = start;
     if (n) {
         const uint32_t ntiles = radix_tiles(n);
         const size_t c = (size_t)256 * ntiles;
         uint32_t* counts = scratch;
         uint32_t* sums = scratch + c;
-        for (uint32_t shift = 0; shift < bits; shift += 8) {
+        for (uint32_t shift = shift0; shift < shift0 + bits; shift += 8) {
             radix_hist_kernel<<<ntiles, kRsThreads, 0, st>>>(keys[cur], n, shift, ntiles, counts);
             cudaError_t e = exclusive_scan<uint32_t>(counts, counts, c, sums, nullptr, st);
             if (e != cudaSuccess) return e;
@@ -290,23 +290,23 @@ __global__ void place_agents_kernel(uint32_t n2, const uint32_t* __restrict__ ke
 // one warp per SELL slice: K = longest hot list, Kc = longest cold list of its 32 agents
 __global__ void slice_dims_kernel(uint32_t n_hub_slices, uint32_t n_sell_slices, const uint32_t* __restrict__ int2ext,
                                   const uint32_t* __restrict__ deg, const uint32_t* __restrict__ nsh, const uint32_t* __restrict__ nnh,
-                                  uint32_t* __restrict__ sell_K, uint64_t* __restrict__ sell_len) {
+                                  uint32_t push, uint32_t* __restrict__ sell_K, uint64_t* __restrict__ sell_len) {
     const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
     if (s >= n_sell_slices) return;
     const uint32_t e = int2ext[(n_hub_slices + s) * 32 + lane];
     uint32_t hot = 0, cold = 0;
     if (e != kInvalid) { hot = nsh[e] + nnh[e]; cold = deg[e] - hot; }
     const uint32_t K = __reduce_max_sync(0xFFFFFFFFu, hot), Kc = __reduce_max_sync(0xFFFFFFFFu, cold);
-    if (lane == 0) { sell_K[s] = K | Kc << 16; sell_len[s] = (uint64_t)32 * (K + Kc); }
+    if (lane == 0) { sell_K[s] = K | Kc << 16; sell_len[s] = (uint64_t)32 * (K + (push ? 0u : Kc)); }   // push mode: hot rows only (layout.h)
 }
 // what the day kernel reads per slice (+ 64 zero records of slack); `rebase` is subtracted (agent-partitioned handles
 // store only their own slices' codes)
 __global__ void sell_meta_kernel(uint32_t n_sell_slices, const uint64_t* __restrict__ sell_off, const uint32_t* __restrict__ sell_K,
-                                 uint64_t rebase, uint32_t own_begin, uint32_t own_end, uint4* __restrict__ meta) {
+                                 uint64_t rebase, uint32_t own_begin, uint32_t own_end, uint32_t push, uint4* __restrict__ meta) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_sell_slices + 64) return;
     uint4 m = make_uint4(0, 0, 0, 0);
-    if (s >= own_begin && s < own_end) { const uint64_t o = sell_off[s] - rebase; m = make_uint4((uint32_t)o, (uint32_t)(o >> 32), sell_K[s], 0); }
+    if (s >= own_begin && s < own_end) { const uint64_t o = sell_off[s] - rebase; m = make_uint4((uint32_t)o, (uint32_t)(o >> 32), push ? sell_K[s] & 0xFFFFu : sell_K[s], 0); }
     meta[s] = m;
 }
 // per hub slot: the four list lengths, how many units its lists are cut into and how many code words they take
@@ -354,6 +354,59 @@ __global__ void hub_units_kernel(uint32_t n_hub_rows, const uint4* __restrict__ 
         dh += 32 * K; dc += 32 * Kc;
     }
 }
+// ---- push mode (layout.h): the cold links of the SELL agents a handle updates, as chunk-wise target-sorted lists ----
+// cold links of every owned SELL slot (own_slot0 = first owned slot, counted from the start of the SELL region)
+__global__ void push_count_kernel(uint32_t n_hub_slices, uint32_t own_slot0, uint32_t n_own_slots, const uint32_t* __restrict__ int2ext,
+                                  const uint32_t* __restrict__ deg, const uint32_t* __restrict__ nsh, const uint32_t* __restrict__ nnh,
+                                  uint32_t* __restrict__ cold_cnt) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_own_slots) return;
+    const uint32_t e = int2ext[n_hub_slices * 32 + own_slot0 + k];
+    cold_cnt[k] = e == kInvalid ? 0u : deg[e] - nsh[e] - nnh[e];
+}
+// The chunks: consecutive owned SELL slots with about `target_links` cold links each (so that every block of push_kernel
+// gets the same work: the cold lists of a neighbourhood's first, high-degree agents are ten times longer than those of its
+// last), at most max_agents agents (their counters must fit in shared memory), cut at slice boundaries.  One thread, a
+// binary search in the exclusive prefix `emit_off` per chunk.  first[c] = first slot of chunk c, first[n_chunks] = n_own_slots.
+__global__ void push_plan_kernel(uint32_t n_own_slots, const uint32_t* __restrict__ emit_off, const uint32_t* __restrict__ total,
+                                 uint32_t grid, uint32_t max_agents, uint32_t cap, uint32_t* __restrict__ first,
+                                 uint32_t* __restrict__ n_chunks_out) {
+    if (blockIdx.x || threadIdx.x) return;
+    const uint32_t tot = *total;
+    auto prefix = [&](uint32_t k) { return k < n_own_slots ? emit_off[k] : tot; };
+    uint64_t rounds = 1;
+    while (((uint64_t)n_own_slots + rounds * grid - 1) / (rounds * grid) > max_agents) ++rounds;
+    const uint32_t target = (uint32_t)(((uint64_t)tot + rounds * grid - 1) / (rounds * grid)) + 1;
+    uint32_t pos = 0, c = 0;
+    while (pos < n_own_slots && c < cap) {
+        first[c++] = pos;
+        const uint64_t want = (uint64_t)prefix(pos) + target;
+        uint32_t lo = pos + 32, hi = min(n_own_slots, pos + max_agents);         // end in [lo, hi], the largest with prefix(end) <= want
+        if (lo > hi) lo = hi;
+        while (lo < hi) {
+            const uint32_t mid = lo + (hi - lo + 1) / 2;
+            if (prefix(mid) <= want) lo = mid; else hi = mid - 1;
+        }
+        pos = min(n_own_slots, (lo + 31u) & ~31u);
+        if (pos - first[c - 1] > max_agents) pos = first[c - 1] + max_agents;
+    }
+    first[c] = n_own_slots;
+    *n_chunks_out = pos < n_own_slots ? 0xFFFFFFFFu : c;                        // (cap too small: the caller reports it)
+}
+// first list entry of every chunk (+ the total behind the last)
+__global__ void push_chunk_begin_kernel(uint32_t n_chunks, uint32_t n_own_slots, const uint32_t* __restrict__ first,
+                                        const uint32_t* __restrict__ emit_off, const uint32_t* __restrict__ total,
+                                        uint32_t* __restrict__ chunk_begin) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > n_chunks) return;
+    const uint32_t k = first[c];
+    chunk_begin[c] = k >= n_own_slots ? *total : emit_off[k];
+}
+// the sorted (chunk << 16 | source) words -> the u16 the push kernel reads
+__global__ void push_src_kernel(uint32_t n, const uint32_t* __restrict__ val, uint16_t* __restrict__ src) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) src[i] = (uint16_t)(val[i] & 0xFFFFu);
+}
+
 __global__ void rebase_u64_kernel(uint64_t* __restrict__ p, uint32_t n, uint64_t rebase) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] -= rebase;

@@ -83,6 +83,9 @@ struct Graph {
     DevBuf deg, ranges, hub_off, hub_deg, hub_codes, hub_units, hub_unit_begin, sell_meta, sell_codes, int2ext, nb_slice_begin;
     const void* key[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // caller pointers it was built from
     uint32_t common_words = 0;     // words of the staged vector every block copies (layout.h)
+    // push mode (layout.h): the cold links of the owned SELL agents, chunk by chunk, sorted by target
+    DevBuf push_code, push_src, push_chunk_begin, push_chunk_first;
+    uint32_t push_chunks = 0, push_chunk_agents = 0, push_own_slots = 0, push_links = 0, push_first_slot = 0;
 };
 
 struct Replica {
@@ -90,6 +93,7 @@ struct Replica {
     uint32_t rec_width = 0, rec_off = 0;
     std::shared_ptr<Graph> graph;
     DevBuf state, vec[2], normvec, pa, tables_f, tables_u, cong, hub_cnt;     // state = slice records (layout.h)
+    DevBuf push_cnt;                     // push mode: {social, neighbour} counts of every owned SELL agent's cold links, per weekday
     bool per_agent = false;
 };
 
@@ -274,6 +278,15 @@ int launch_day(mvb_sim* s, uint8_t weather, uint8_t changed, bool with_norms = t
 #define MVB_LAUNCH_X(PA, T, G, X) MVB_CUDA(cudaLaunchKernelEx(&cfg, day_kernel<PA, T, G, X>, s->rep_args[c], R, P, s->parity, prev, (uint32_t*)next, \
         (uint32_t)weather, (uint32_t)changed, uw, s->vec_cap_words))
 #define MVB_LAUNCH(PA, T, G) do { if (p2p) MVB_LAUNCH_X(PA, T, G, true); else MVB_LAUNCH_X(PA, T, G, false); } while (0)
+    // push mode (one large population, layout.h): the cold links of the SELL agents are counted first, by push_kernel
+    for (Replica& rp : s->reps) {
+        const Graph& g = *rp.graph;
+        if (!g.push_chunks) continue;
+        PushDesc pd{g.push_code.as<uint32_t>(), g.push_src.as<uint16_t>(), g.push_chunk_begin.as<uint32_t>(), g.push_chunk_first.as<uint32_t>(),
+                    rp.push_cnt.as<uint2>(), g.push_chunks, s->h_reps[&rp - s->reps.data()].cold_cg};
+        push_kernel<<<std::min(s->grid, g.push_chunks), 1024, 8 * (size_t)g.push_chunk_agents, s->stream>>>(pd, rp.vec[s->parity].as<uint32_t>());
+        MVB_CUDA(cudaGetLastError());
+    }
     for (size_t c = 0; c < s->rep_args.size(); ++c) {
         const uint32_t R = std::min<uint32_t>(kMaxRepsPerLaunch, (uint32_t)s->reps.size() - (uint32_t)c * kMaxRepsPerLaunch);
         const uint32_t P = s->local_P[c] ? s->local_P[c] : choose_parts(s, (uint32_t)c * kMaxRepsPerLaunch, R);

@@ -31,8 +31,8 @@ def stage_env():
         if layout:
             os.environ["MVB_LAYOUT"] = layout
     yield set_env
-    os.environ.pop("MVB_STAGE_AGENTS", None)
-    os.environ.pop("MVB_LAYOUT", None)
+    for k in ("MVB_STAGE_AGENTS", "MVB_LAYOUT", "MVB_PUSH", "MVB_PUSH_CHUNK"):
+        os.environ.pop(k, None)
 
 
 # (agents, subcultures, neighbourhoods, staged agents or None = what the GPU's shared memory holds, seed)
@@ -96,6 +96,54 @@ def test_partly_staged_small_population_equals_oracle(stage_env, stage, layout):
         prev = w[day]
         assert_state_equal(g.get_state(0), o.get_state(), f"day {day}")
     g.close()
+
+
+@pytest.mark.parametrize("layout", ["global", "local"])
+@pytest.mark.parametrize("stage,chunk", [(64, 96), (1024, 4096), (6400, 24576)])
+def test_push_mode_small_population_equals_oracle(stage_env, stage, chunk, layout):
+    """PUSH mode (layout.h): the cold links of the SELL agents are counted by push_kernel from chunk-wise target-sorted
+    lists instead of being gathered by their source's lane.  Forced on a small population with a small staged set and
+    small chunks (many chunks per block, a ragged last chunk); every day, full state, an intervention on the way."""
+    stage_env(stage, layout)
+    os.environ["MVB_PUSH"] = "1"
+    os.environ["MVB_PUSH_CHUNK"] = str(chunk)
+    n = 12000
+    pop = mb.synth_population(n, 4, 6, 5, 10, seed=stage + 1)
+    tab = mb.synth_tables(4, 6, n, seed=stage + 1)
+    w = mb.weather_pattern(30, seed=stage)
+    g = mb.Simulation(pop, tab, mb.make_params())
+    compare_with_host(g, pop)
+    o = OracleSimulation(pop, tab, mb.make_params())
+    prev = w[0]
+    for day in range(1, 30):
+        if day == 12:
+            car = (1 - pop["owns_car"]).astype(np.uint8)
+            g.set_ownership(0, car, None); o.set_ownership(car, None)
+        if day % 7 >= 5:
+            continue
+        g.step(w[day], prev != w[day]); o.step(w[day], prev != w[day])
+        prev = w[day]
+        assert_state_equal(g.get_state(0), o.get_state(), f"day {day}")
+        assert np.array_equal(g.stats_row(0), o.stats_row())
+    g.close()
+
+
+def test_push_mode_run_equals_pull_run_200k(stage_env):
+    """The same 200k-agent population through the pull path and through the push path (one third of the agents staged,
+    LOCAL layout, default chunk size): rows and full state identical after a 3-week run with mvb_run."""
+    n = 200_000
+    pop = mb.synth_population(n, 4, 10, 5, 10, seed=31)
+    tab = mb.synth_tables(4, 10, n, seed=31)
+    w = mb.weather_pattern(22, seed=31)
+    out = []
+    for push in ("0", "1"):
+        stage_env(64000, "local")
+        os.environ["MVB_PUSH"] = push
+        with mb.Simulation(pop, tab, mb.make_params()) as sim:
+            days, rows = sim.run(w)
+            out.append((rows[0].copy(), sim.get_state(0)))
+    assert np.array_equal(out[0][0], out[1][0])
+    assert_state_equal(out[0][1], out[1][1], "push vs pull")
 
 
 def test_device_generated_population_statistics_and_structure():

@@ -107,6 +107,8 @@ def wait_for_id(rank, idfile):
 def nccl_worker(rank, world, idfile, out, exchange):
     if exchange == "nccl":
         os.environ["MVB_EXCHANGE"] = "nccl"                       # force the NCCL all-gather / all-reduce path
+    if exchange == "p2p-push":                                    # + the cold links through push_kernel (layout.h), small staged set and chunks
+        os.environ.update(MVB_PUSH="1", MVB_PUSH_CHUNK="512", MVB_STAGE_AGENTS="1024", MVB_LAYOUT="local")
     pop, tab, prm, w = inputs()
     sim = mb.Simulation.partitioned(pop, tab, prm, device=rank, rank=rank, world=world, unique_id=wait_for_id(rank, idfile))
     days, rows = sim.run(w)
@@ -132,7 +134,7 @@ def nccl_worker(rank, world, idfile, out, exchange):
 
 @pytest.mark.gpu
 @pytest.mark.skipif(_ffi.load().mvb_device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
-@pytest.mark.parametrize("exchange", ["p2p", "nccl"])
+@pytest.mark.parametrize("exchange", ["p2p", "nccl", "p2p-push"])
 def test_partitioned_two_gpus_equal_oracle(tmp_path, exchange):
     out, idfile = str(tmp_path / "state"), str(tmp_path / "nccl_id")
     mp.spawn(nccl_worker, args=(2, idfile, out, exchange), nprocs=2, join=True)
@@ -143,7 +145,7 @@ def test_partitioned_two_gpus_equal_oracle(tmp_path, exchange):
     z = [np.load(out + f".{r}.npz") for r in range(2)]
     assert np.array_equal(z[0]["owner"], z[1]["owner"]) and set(np.unique(z[0]["owner"])) == {0, 1}
     for r in range(2):
-        assert str(z[r]["exchange"]) == exchange, "the GPUs of one B200 box can map each other's memory"
+        assert str(z[r]["exchange"]) == exchange.split("-")[0], "the GPUs of one B200 box can map each other's memory"
         assert np.array_equal(z[r]["days"], days) and np.array_equal(z[r]["rows"], rows), f"rows on rank {r}"
         for k in ("current_mode", "norm", "hist"):
             assert np.array_equal(z[r][k], ref[k]), (r, k)              # every rank holds the full vectors
