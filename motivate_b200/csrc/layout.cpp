@@ -413,7 +413,7 @@ namespace {
 struct WorkModel { uint64_t cold, per_agent, hub10, hub_cold; };
 WorkModel work_model(const GraphLayout& L) {
     WorkModel m = L.mode == kLayoutLocal ? WorkModel{8, 40, 15, 8} : WorkModel{2, 64, 25, 2};
-    if (L.push) m.cold = 3;          // a pushed cold link of a SELL agent: sorted gather + shared-memory reduction, ~1.2 per clock per SM;
+    if (L.push) m.cold = 4;          // a pushed cold link of a SELL agent: sorted gather + shared-memory reduction, ~1.2 per clock per SM;
                                      // a hub's cold links stay on the pull path (hub_cold)
     if (const char* e = getenv("MVB_PART_HUBCOLD")) m.hub_cold = (uint64_t)atoi(e);
     if (const char* e = getenv("MVB_PART_COLD")) m.cold = (uint64_t)atoi(e);          // calibration experiments
