@@ -585,7 +585,7 @@ static int create_impl(uint32_t R, const mvb_population* const* pops, const mvb_
             uint32_t n_push = 0, n_chunks = 0;
             const uint32_t push_max_agents = push_chunk_agents(~0ull, s->grid);       // (the cap itself: kPushChunkMax unless a test lowers it)
             if (L.push && n_own_slots) {
-                const uint32_t chunk_cap = std::min<uint64_t>(65535, 4 * ((uint64_t)n_own_slots / push_max_agents + s->grid) + 8);
+                const uint32_t chunk_cap = std::min<uint32_t>(65535, n_own_slots / 32 + 1);        // chunk ids travel in 16 bits
                 MVB_CUDA(pcnt.alloc(4 * (size_t)n_own_slots, S)); MVB_CUDA(poff.alloc(4 * (size_t)n_own_slots + 4, S));
                 MVB_CUDA(psums.alloc(4 * ((size_t)scan_blocks(n_own_slots) + 8), S));
                 MVB_CUDA(pfirst.alloc(4 * ((size_t)chunk_cap + 1), S));
@@ -761,7 +761,12 @@ static int create_impl(uint32_t R, const mvb_population* const* pops, const mvb_
             // (replicas in the GLOBAL layout that share the launch take class p of the same P = T parts: any P works for them)
             const RepDev& d0 = s->h_reps[first_local];
             const uint32_t own0 = d0.sell_end - d0.sell_begin;
-            uint32_t rounds = std::max<uint32_t>(1, std::min<uint32_t>(8, (uint32_t)((uint64_t)own0 * (r1 - r0) / ((uint64_t)s->grid * 32 * 8))));
+            // ONE round of the grid: every extra round costs each block another staging pass and another ragged end (measured
+            // with MVB_LOCAL_ROUNDS = 1, 2, 6 on one B200: 3M agents 0.194 / 0.200 / 0.299 ms per weekday, 6M 0.356 / 0.382 /
+            // 0.426, 8M 0.487 / 0.512 / 0.561, 50M 4.28 / 4.41 / 4.64); the work model below balances the parts instead
+            uint32_t rounds = 1;
+            (void)own0;
+            if (const char* e = getenv("MVB_LOCAL_ROUNDS")) rounds = (uint32_t)std::max(1, atoi(e));       // tuning experiments
             uint32_t T = std::max<uint32_t>(d0.H, rounds * s->grid / (r1 - r0));
             for (uint32_t r = r0; r < r1; ++r) if (s->h_reps[r].local_mode) T = std::max(T, s->h_reps[r].H);
             s->local_P[c] = T;

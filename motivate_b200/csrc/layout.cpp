@@ -413,8 +413,11 @@ namespace {
 struct WorkModel { uint64_t cold, per_agent, hub10, hub_cold; };
 WorkModel work_model(const GraphLayout& L) {
     WorkModel m = L.mode == kLayoutLocal ? WorkModel{8, 40, 15, 8} : WorkModel{2, 64, 25, 2};
-    if (L.push) m.cold = 4;          // a pushed cold link of a SELL agent: sorted gather + shared-memory reduction, ~1.2 per clock per SM;
-                                     // a hub's cold links stay on the pull path (hub_cold)
+    // push mode: a SELL agent's cold link costs a sorted gather + a shared-memory reduction (~1.2 per clock per SM), a
+    // hub's cold links stay on the pull path (hub_cold), and with the cold links cheap the per-agent work weighs more
+    // (tools/partition_balance.py, 50M agents over 8 ranks, one round of parts: 0.45-0.50 ms per rank at H = 64 and
+    // 0.50-0.59 at H = 10 with these values; 0.45-0.55 and 0.54-0.68 with {4, 40, 15})
+    if (L.push) { m.cold = 3; m.per_agent = 80; m.hub10 = 22; }
     if (const char* e = getenv("MVB_PART_HUBCOLD")) m.hub_cold = (uint64_t)atoi(e);
     if (const char* e = getenv("MVB_PART_COLD")) m.cold = (uint64_t)atoi(e);          // calibration experiments
     if (const char* e = getenv("MVB_PART_AGENT")) m.per_agent = (uint64_t)atoi(e);

@@ -374,24 +374,41 @@ __global__ void push_plan_kernel(uint32_t n_own_slots, const uint32_t* __restric
     if (blockIdx.x || threadIdx.x) return;
     const uint32_t tot = *total;
     auto prefix = [&](uint32_t k) { return k < n_own_slots ? emit_off[k] : tot; };
+    // one greedy pass for a given number of rounds of the grid; returns the number of chunks (cap + 1: too many)
+    auto pass = [&](uint64_t rounds, bool write) -> uint32_t {
+        const uint32_t target = (uint32_t)(((uint64_t)tot + rounds * grid - 1) / (rounds * grid)) + 1;
+        uint32_t pos = 0, c = 0;
+        while (pos < n_own_slots) {
+            if (c == cap) return cap + 1;
+            if (write) first[c] = pos;
+            const uint32_t begin = pos;
+            ++c;
+            const uint64_t want = (uint64_t)prefix(pos) + target;
+            uint32_t lo = min(n_own_slots, pos + 32), hi = min(n_own_slots, pos + max_agents);   // end in [lo, hi], the largest with prefix(end) <= want
+            while (lo < hi) {
+                const uint32_t mid = lo + (hi - lo + 1) / 2;
+                if (prefix(mid) <= want) lo = mid; else hi = mid - 1;
+            }
+            pos = min(n_own_slots, (lo + 31u) & ~31u);
+            if (pos - begin > max_agents) pos = begin + max_agents;
+        }
+        if (write) first[c] = n_own_slots;
+        return c;
+    };
+    // Chunks that stop at the agent limit hold fewer links than the target, so a pass may end with a few chunks more than
+    // `rounds` per block, and the blocks that get one more set the pace: take more rounds (smaller targets) until the chunks
+    // fill whole rounds of the grid again.
     uint64_t rounds = 1;
     while (((uint64_t)n_own_slots + rounds * grid - 1) / (rounds * grid) > max_agents) ++rounds;
-    const uint32_t target = (uint32_t)(((uint64_t)tot + rounds * grid - 1) / (rounds * grid)) + 1;
-    uint32_t pos = 0, c = 0;
-    while (pos < n_own_slots && c < cap) {
-        first[c++] = pos;
-        const uint64_t want = (uint64_t)prefix(pos) + target;
-        uint32_t lo = pos + 32, hi = min(n_own_slots, pos + max_agents);         // end in [lo, hi], the largest with prefix(end) <= want
-        if (lo > hi) lo = hi;
-        while (lo < hi) {
-            const uint32_t mid = lo + (hi - lo + 1) / 2;
-            if (prefix(mid) <= want) lo = mid; else hi = mid - 1;
-        }
-        pos = min(n_own_slots, (lo + 31u) & ~31u);
-        if (pos - first[c - 1] > max_agents) pos = first[c - 1] + max_agents;
+    uint64_t best = rounds;
+    for (uint64_t r = rounds; r < rounds + 12; ++r) {
+        const uint32_t c = pass(r, false);
+        if (c > cap) break;                                                      // (keep the last plan that fits the chunk table)
+        best = r;
+        if (c <= r * grid) break;
     }
-    first[c] = n_own_slots;
-    *n_chunks_out = pos < n_own_slots ? 0xFFFFFFFFu : c;                        // (cap too small: the caller reports it)
+    const uint32_t c = pass(best, true);
+    *n_chunks_out = c > cap ? 0xFFFFFFFFu : c;                                  // (cap too small: the caller reports it)
 }
 // first list entry of every chunk (+ the total behind the last)
 __global__ void push_chunk_begin_kernel(uint32_t n_chunks, uint32_t n_own_slots, const uint32_t* __restrict__ first,

@@ -262,14 +262,14 @@ int launch_day(mvb_sim* s, uint8_t weather, uint8_t changed, bool with_norms = t
     // replica descriptors travel as kernel parameters, kMaxRepsPerLaunch at a time
     // Programmatic dependent launch: the next weekday's blocks may start (and run their day-independent prologue) while
     // this one's last blocks finish; the kernel waits with griddepcontrol.wait before it touches anything a previous
-    // launch wrote (day_kernels.cuh).  Not in the agent-partitioned mode, where NCCL kernels sit between the days.
+    // launch wrote (day_kernels.cuh).  Not in the agent-partitioned mode over NCCL, where NCCL's kernels sit between the days.
     static const bool no_pdl = getenv("MVB_NO_PDL") != nullptr;
     cudaLaunchAttribute pdl_attr[1];
     pdl_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     pdl_attr[0].val.programmaticStreamSerializationAllowed = 1;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(s->grid); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = s->smem_bytes; cfg.stream = s->stream;
-    cfg.attrs = pdl_attr; cfg.numAttrs = (s->world == 1 && !no_pdl) ? 1 : 0;
+    cfg.attrs = pdl_attr; cfg.numAttrs = ((s->world == 1 || s->exchange_mode == MVB_EXCHANGE_P2P) && !no_pdl) ? 1 : 0;
     const bool p2p = s->exchange_mode == MVB_EXCHANGE_P2P;
     if (p2p) {                                                   // (one replica, one launch per weekday in this mode)
         RepDev& r0 = s->rep_args[0].r[0];

@@ -132,8 +132,10 @@ int main(int argc, char** argv) {
             links += deg(e);
         }
         CHECK(L.sell_K[s] == (K | Kc << 16) && L.sell_off[s] == off, "slice %u: K %u Kc %u off %llu", s, K, Kc, (unsigned long long)off);
-        CHECK(L.sell_meta[s].x == (uint32_t)off && L.sell_meta[s].y == (uint32_t)(off >> 32) && L.sell_meta[s].z == L.sell_K[s], "slice record %u", s);
-        off += 32ull * (K + Kc); rows += K + Kc;
+        // push mode (layout.h): the block holds hot rows only and the record says so; sell_K keeps Kc for the work model
+        CHECK(L.sell_meta[s].x == (uint32_t)off && L.sell_meta[s].y == (uint32_t)(off >> 32) &&
+              L.sell_meta[s].z == (L.push ? L.sell_K[s] & 0xFFFFu : L.sell_K[s]), "slice record %u", s);
+        off += 32ull * (K + (L.push ? 0u : Kc)); rows += K + Kc;
     }
     CHECK(L.sell_codes_len >= off, "sell_codes_len");
     const double padding = links ? (double)rows * 32 / (double)links : 1.0;
@@ -181,7 +183,7 @@ int main(int argc, char** argv) {
     }
     uint64_t all_links = 0, hot_links = 0;
     for (uint32_t e = 0; e < N; ++e) { all_links += deg(e); hot_links += n_hot_links[e]; }
-    printf("ok N_pad %u hubs %u hot %u ranges %zu sell_padding %.3f hub_slice_balance %.2f mode %s hot_link_share %.3f\n", L.N_pad, n_hubs, n_hot, L.ranges.size(), padding, hub_balance,
+    printf("ok push %d N_pad %u hubs %u hot %u ranges %zu sell_padding %.3f hub_slice_balance %.2f mode %s hot_link_share %.3f\n", (int)L.push, L.N_pad, n_hubs, n_hot, L.ranges.size(), padding, hub_balance,
            local ? "local" : "global", all_links ? (double)hot_links / (double)all_links : 1.0);
     mvb_synth_destroy(syn);
     return 0;

@@ -49,3 +49,15 @@ def test_layout_invariants(checker, n, s, h, cap, seed, mode):
         assert share > 0.6 if mode == "local" else share < 0.5, out.stdout
     balance = float(fields[fields.index("hub_slice_balance") + 1])
     assert balance < 2.0, out.stdout                  # hubs are dealt round the hub slices
+    assert fields[fields.index("push") + 1] == "0"    # small populations keep the pull path
+
+
+@pytest.mark.parametrize("mode", ["global", "local"])
+def test_layout_invariants_push_mode(checker, mode):
+    """PUSH mode (layout.h), forced on a small population: the SELL blocks hold hot rows only (offsets and slice records
+    without the cold rows), sell_K still carries the cold lengths for the work model, everything else is unchanged."""
+    out = subprocess.run([checker, "40000", "4", "10", "8192", "2"], capture_output=True, text=True,
+                         env=dict(os.environ, MVB_LAYOUT=mode, MVB_PUSH="1"))
+    assert out.returncode == 0 and out.stdout.startswith("ok "), out.stdout + out.stderr
+    fields = out.stdout.split()
+    assert fields[fields.index("push") + 1] == "1"
