@@ -43,9 +43,11 @@ LayoutMode pick_layout_mode(uint32_t N_pad, uint32_t capacity_agents, uint32_t n
 
 bool pick_push_mode(uint32_t N_pad, uint32_t n_replicas) {
     if (const char* e = getenv("MVB_PUSH")) return atoi(e) != 0;
-    // one large population per handle (BASELINE config 4): measured on B200, see layout.h; with several replicas per
-    // launch the populations are small enough for the pull path
-    return n_replicas == 1 && N_pad > 4u * 1000u * 1000u;
+    // one large population per handle (BASELINE config 4).  Measured on one B200, ms per weekday pull / push (S=4, H=10, BA
+    // 5+10, profiles/r02_push_threshold.txt): 2M agents 0.1135 / 0.1108, 3M 0.196 / 0.167, 4M 0.284 / 0.235, 5M 0.369 /
+    // 0.282, 8M 0.698 / 0.487, 50M 8.04 / 4.28; at 1M agents only 4 % of the links are cold and the extra launch costs more
+    // than it saves.  With several replicas per launch the populations are small enough for the pull path.
+    return n_replicas == 1 && N_pad > 1800u * 1000u;
 }
 uint32_t push_chunk_agents(uint64_t own_slots, uint32_t grid) {
     uint32_t cap = kPushChunkMax;

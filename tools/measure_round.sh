@@ -4,7 +4,7 @@
 #   1  default bench line (521 weekdays: the sustained, power-capped number) with its extra legs (c1, c2, c5)
 #   2  the driver's setting (20 weekdays)
 #   3  few-replica configurations with and without programmatic dependent launch
-#   4  one large population: GLOBAL vs LOCAL staging layout, 1M .. 50M agents
+#   4  one large population, 2M .. 50M agents: the library's own choices, then the cold links pulled (MVB_PUSH=0) and pushed (=1)
 #   5  set-up: mvb_create_batch next to the plain copy of the same pinned buffers
 #   6  ncu launch list of the 8-replica bench command (plain run first, as the profiling rules ask)
 O=gpurun_out/round2
@@ -13,7 +13,7 @@ python bench.py > $O/bench_default_521.json 2> $O/bench_default_521.err
 python bench.py --steps 20 --warmup 5 > $O/bench_driver_20.json 2> $O/bench_driver_20.err
 python tools/ab_pdl.py > $O/pdl_ab.txt 2>&1
 python tools/time_big_population.py > $O/big_population.txt 2>&1
-for a in "2000000 10" "3000000 10" "6000000 10" "12000000 10" "50000000 64"; do set -- $a; python tools/run_big.py $1 local 6 $2; python tools/run_big.py $1 global 6 $2; done >> $O/big_population.txt 2>&1
+for p in 0 1; do MVB_PUSH=$p python tools/time_big_population.py 2000000:10 8000000:10 50000000:64 50000000:10 | sed "s/^/MVB_PUSH=$p /"; done >> $O/big_population.txt 2>&1
 MVB_TIMING=1 python tools/time_create.py > $O/create.txt 2>&1
 MVB_TIMING=1 python tools/time_create.py --replicas 8 --repeat 3 >> $O/create.txt 2>&1
 CMD="python bench.py --replicas 8 --steps 6 --warmup 3 --no-cpu-baseline --no-extra"
