@@ -48,7 +48,8 @@ def parse():
     ap.add_argument("--replicas", type=int, default=64, help="total replicas over all ranks (BASELINE config 3)")
     ap.add_argument("--agents", type=int, default=1_000_000)
     ap.add_argument("--partitioned", action="store_true",
-                    help="BASELINE config 4: ONE population of --agents agents partitioned over the ranks (NCCL exchange per weekday)")
+                    help="BASELINE config 4: ONE population of --agents agents partitioned over the ranks (modes and counters exchanged every weekday: "
+                         "inside the weekday kernel over peer memory, or over NCCL with MVB_EXCHANGE=nccl)")
     ap.add_argument("--sweep", action="store_true",
                     help="BASELINE config 5: --replicas scenario variants (tables + ownership differ) over ONE shared population")
     ap.add_argument("--no-e2e", action="store_true")
@@ -598,7 +599,7 @@ def leg_c4(args, rank, local_rank, world, torch, dist, mb, peak):
 
 def run_partitioned(args, rank, local_rank, world, torch, dist, mb):
     """BASELINE config 4: one population, agents partitioned over the ranks; per weekday each rank updates its agents,
-    then the ranks exchange packed modes (NCCL broadcast per owner) and all-reduce the counters."""
+    and the ranks exchange packed modes and counters (inside the weekday kernel over peer memory, or NCCL all-gather + all-reduce)."""
     pop = mb.synth_population(args.agents, 4, 10, 5, 10, seed=0)          # same population on every rank
     tab = mb.synth_tables(4, 10, args.agents, seed=0)
     prm = mb.make_params()
@@ -610,6 +611,7 @@ def run_partitioned(args, rank, local_rank, world, torch, dist, mb):
         dist.broadcast_object_list(uid, src=0)
     sim = mb.Simulation.partitioned(pop, tab, prm, device=local_rank, rank=rank, world=world, unique_id=uid[0])
     alg_bytes = sim.algorithmic_bytes_per_day(0)
+    exchange = sim.exchange_mode()
     if args.warmup:
         sim.run_async(w, 0, warm_end)
     sim.sync()
@@ -640,13 +642,14 @@ def run_partitioned(args, rank, local_rank, world, torch, dist, mb):
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": max_ms / args.steps, "higher_is_better": True,
            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": f"C4: ONE population of {args.agents} agents (4 subcultures, 10 neighbourhoods, BA links 5+10) "
-                                  f"agent-partitioned over {world} ranks; per weekday: NCCL broadcast of each rank's packed "
-                                  "2-bit modes + allreduce of the counters", "agents": args.agents,
+                                  f"agent-partitioned over {world} ranks; exchange of the packed 2-bit modes and the day's counters: "
+                                  + ("fused into the weekday kernel over NVLink peer memory" if exchange == "p2p" else
+                                     "one NCCL all-gather + one all-reduce per weekday"), "agents": args.agents, "exchange": exchange,
                       "parallelism": f"agent-partitioned x{world}", "l2": "inputs larger than L2; no flush needed"},
            "gpu_launches": int(launches),
            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes / world,
-                        "kernel": "day kernel + NCCL exchange, per rank"},
+                        "kernel": "push kernel + day kernel + exchange, per rank"},
            "clocks": clocks, "active_mode_last_row": int(rows[0][-1, 0]),
            "ms_per_step_by_rank": [float(x.item()) / args.steps for x in per_rank]}
     if rank == 0:

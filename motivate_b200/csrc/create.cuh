@@ -709,7 +709,7 @@ static int create_impl(uint32_t R, const mvb_population* const* pops, const mvb_
         d.cap = rp.tables_u.as<uint32_t>(); d.nres = rp.tables_u.as<uint32_t>() + 4 * rp.H;
         d.cong = rp.cong.as<float>();
         d.int2ext = g->int2ext.as<uint32_t>();
-        d.push_cnt = g->push_chunks ? rp.push_cnt.as<uint2>() - g->push_first_slot : nullptr;      // indexed by internal slot
+        if (g->push_chunks) s->solo.push_cnt = rp.push_cnt.as<uint2>() - g->push_first_slot;      // indexed by internal slot (R == 1 in push mode)
         d.local_mode = L.mode == kLayoutLocal ? 1u : 0u;
         // cold gathers bypass L1 when the vector is several times what shared memory + L1 hold (day_kernels.cuh: ld_cold;
         // tools/ab_cold_cg.sh: 8M agents -4.8 %, 2M +0.6 %, 1M +1 % with the bypass)
@@ -722,11 +722,15 @@ static int create_impl(uint32_t R, const mvb_population* const* pops, const mvb_
     MVB_CUDA(cudaFuncSetAttribute(day_kernel<true, 1024, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
     MVB_CUDA(cudaFuncSetAttribute(day_kernel<false, 1024, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
     MVB_CUDA(cudaFuncSetAttribute(day_kernel<false, 1024, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
-    if (world > 1) {
-        MVB_CUDA(cudaFuncSetAttribute(day_kernel<true, 1024, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
-        MVB_CUDA(cudaFuncSetAttribute(day_kernel<true, 1024, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
-        MVB_CUDA(cudaFuncSetAttribute(day_kernel<false, 1024, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
-        MVB_CUDA(cudaFuncSetAttribute(day_kernel<false, 1024, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
+    if (R == 1) {      // the SOLO instantiations (push mode, L1-bypassing cold gathers, fused exchange)
+        MVB_CUDA(cudaFuncSetAttribute(day_kernel<true, 1024, 2, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
+        MVB_CUDA(cudaFuncSetAttribute(day_kernel<true, 1024, 4, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
+        MVB_CUDA(cudaFuncSetAttribute(day_kernel<false, 1024, 2, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
+        MVB_CUDA(cudaFuncSetAttribute(day_kernel<false, 1024, 4, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
+        MVB_CUDA(cudaFuncSetAttribute(day_kernel<true, 1024, 2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
+        MVB_CUDA(cudaFuncSetAttribute(day_kernel<true, 1024, 4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
+        MVB_CUDA(cudaFuncSetAttribute(day_kernel<false, 1024, 2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
+        MVB_CUDA(cudaFuncSetAttribute(day_kernel<false, 1024, 4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
     }
     MVB_CUDA(cudaFuncSetAttribute(push_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * kPushChunkMax)));
     if (s->census_smem > 48 * 1024)
@@ -739,7 +743,7 @@ static int create_impl(uint32_t R, const mvb_population* const* pops, const mvb_
         memcpy(&id, unique_id, sizeof id);
         MVB_NCCL(n->CommInitRank(&s->comm, (int)world, id, (int)rank));
         if (int rc = setup_peer_exchange(s, vec_piece, S)) return rc;      // sets s->exchange_mode: P2P, or NCCL if any rank could not map the others
-        if (s->exchange_mode == MVB_EXCHANGE_P2P) s->h_reps[0].px = s->d_px.as<PeerExchange>();
+        if (s->exchange_mode == MVB_EXCHANGE_P2P) s->solo.px = s->d_px.as<PeerExchange>();
         for (uint32_t k = 0; k < world; ++k) s->xchg_words = std::max(s->xchg_words, s->bounds[k + 1] - s->bounds[k]);
         if (s->exchange_mode == MVB_EXCHANGE_NCCL) MVB_CUDA(s->xchg.alloc((size_t)world * 2 * s->xchg_words * sizeof(uint2)));
         MVB_CUDA(s->d_bounds.alloc(4 * ((size_t)world + 1)));

@@ -75,6 +75,10 @@ struct RepDev {                     // device-side descriptor of one replica
     const uint32_t* nb_slice_begin; // [H + 1] SELL slices of every neighbourhood (LOCAL layout: parts are neighbourhood-pure)
     uint32_t local_mode, cold_cg;   // layout.h LayoutMode; cold gathers bypass L1 (ld_cold)
     const uint4* part_table;        // LOCAL layout: part p of a launch = {neighbourhood, class q, classes Q of that neighbourhood, 0}
+};
+// What only a handle with ONE population needs (push mode, agent-partitioned mode): a kernel parameter of its own, so that
+// the 64 replica descriptors of the headline launches stay as small as they were (the parameter block is copied per launch).
+struct SoloExtra {
     const uint2* push_cnt;          // push mode (layout.h): per-mode counts {social, neighbour} of an agent's cold links, filled by
                                     // push_kernel before the day kernel, indexed by internal slot (pointer pre-offset); else nullptr
     const PeerExchange* px;         // agent-partitioned mode, exchange over peer memory (day_kernel<.., XCHG = true>), else nullptr
@@ -327,7 +331,7 @@ __device__ __forceinline__ void flush_stats(uint32_t lane, uint32_t H, uint32_t 
 
 // Everything that happens once the link counts of 32 agents (one per lane) are known.
 template <bool PER_AGENT, bool XCHG>
-__device__ __forceinline__ void finish_slice(const RepDev& r, uint32_t slice, uint32_t lane, bool uniform_nbhd,
+__device__ __forceinline__ void finish_slice(const RepDev& r, const SoloExtra& solo, uint32_t slice, uint32_t lane, bool uniform_nbhd,
                                              const uint32_t cs[4], uint32_t ds, const uint32_t cn[4], uint32_t dn,
                                              uint32_t stat, float wsv, float4 hv, uint32_t last,
                                              const AgentWeights& uw, const float* s_cong, const float* s_cost,
@@ -359,10 +363,10 @@ __device__ __forceinline__ void finish_slice(const RepDev& r, uint32_t slice, ui
     if (XCHG) {
         // exchange fused into the update: lane p stores the word into rank p's vector (its own included), one store
         // instruction for all ranks; norm words only travel when asked (no rank's update reads another agent's norm)
-        const PeerExchange* px = r.px;
+        const PeerExchange* px = solo.px;
         const uint32_t world = px->world;
         if (lane < world) px->vec[parity ^ 1u][lane][slice] = make_uint2(mlo, mhi);
-        if (lane >= 16u && lane - 16u < world && (r.px_norms || lane - 16u == px->rank)) px->normvec[lane - 16u][slice] = make_uint2(nlo, nhi);
+        if (lane >= 16u && lane - 16u < world && (solo.px_norms || lane - 16u == px->rank)) px->normvec[lane - 16u][slice] = make_uint2(nlo, nhi);
     } else {
         if (lane == 0) r.vec[parity ^ 1u][slice] = make_uint2(mlo, mhi);
         if (lane == 1) r.normvec[slice] = make_uint2(nlo, nhi);
@@ -405,11 +409,14 @@ __device__ __forceinline__ void stamp_launch(const uint32_t* rec_next, int end) 
 #endif
 
 // ---- the weekday kernel ----------------------------------------------------------------------------
-template <bool PER_AGENT, int THREADS, uint32_t G, bool XCHG = false>
+// SOLO: the handle holds ONE population and uses what only such handles have: push mode, cold gathers that bypass L1, the
+// peer-to-peer exchange (XCHG).  A compile-time switch: on the headline launches (many replicas of 1M agents) the run-time
+// tests of these features cost 3 % (8 x 1M agents 252 -> 260 us per weekday), so those launches get the kernel without them.
+template <bool PER_AGENT, int THREADS, uint32_t G, bool SOLO = false, bool XCHG = false>
 __global__ void __launch_bounds__(THREADS, 1)
 day_kernel(const __grid_constant__ RepArray reps, uint32_t R, uint32_t P, uint32_t parity,
            const uint32_t* __restrict__ rec_prev, uint32_t* __restrict__ rec_next, uint32_t weather,
-           uint32_t changed, AgentWeights uw, uint32_t vec_cap_words) {
+           uint32_t changed, AgentWeights uw, uint32_t vec_cap_words, const SoloExtra solo) {
     extern __shared__ __align__(128) uint32_t smem[];
     uint32_t* s_vec = smem;
     uint32_t* s_tail = smem + vec_cap_words;
@@ -572,7 +579,7 @@ day_kernel(const __grid_constant__ RepArray reps, uint32_t R, uint32_t P, uint32
             uint32_t acc_s = 0, acc_n = 0;
             accumulate_block(blk, K, Kc, lane, min(max((int)(unit0.z >> 16) - oh, 0), (int)K),
                              min(max((int)(unit0.w & 0xFFFFu) - oc, 0), (int)Kc), min(max((int)(unit0.w >> 16) - oc, 0), (int)Kc),
-                             s_vec, g_vec, r.cold_cg != 0, acc_s, acc_n);
+                             s_vec, g_vec, SOLO && r.cold_cg != 0, acc_s, acc_n);
             uint32_t mine = 0;                         // lane 1..3: social count of mode lane; lane 5..7: neighbour count
 #pragma unroll
             for (int m = 1; m < 4; ++m) {
@@ -607,7 +614,7 @@ day_kernel(const __grid_constant__ RepArray reps, uint32_t R, uint32_t P, uint32
                 const uint32_t stat = rec[kRecStat + lane];
                 const uint2 own = r.vec[parity][hs];
                 const uint32_t last = ((lane < 16 ? own.x : own.y) >> ((lane & 15u) * 2u)) & 3u;
-                finish_slice<PER_AGENT, XCHG>(r, hs, lane, false, hcs, ad.x + ad.z, hcn, ad.y + ad.w, stat, __uint_as_float(rec[kRecWs + lane]),
+                finish_slice<PER_AGENT, XCHG>(r, solo, hs, lane, false, hcs, ad.x + ad.z, hcn, ad.y + ad.w, stat, __uint_as_float(rec[kRecWs + lane]),
                                         reinterpret_cast<const float4*>(rec + kRecHabit)[lane], last, uw, s_cong, s_cost, s_crank, s_des, s_rec, weather, changed, parity, st);
             } else {
             const uint32_t s = sell_b + q + Q * (it0 - n_my_hub_slices);
@@ -626,18 +633,18 @@ day_kernel(const __grid_constant__ RepArray reps, uint32_t R, uint32_t P, uint32
             const int ds_h = (int)(dg & 0xFFu), dn_h = (int)((dg >> 8) & 0xFFu), ds_c = (int)((dg >> 16) & 0xFFu), dn_c = (int)(dg >> 24);
             uint32_t acc_s = 0, acc_n = 0;
             int d_c = ds_c + dn_c;
-            if (r.push_cnt) {                          // the cold links were counted by push_kernel; the block has hot rows only
-                const uint2 pc = ld_stream_v2(r.push_cnt + (size_t)slice * 32 + lane);
+            if (SOLO && solo.push_cnt) {                       // the cold links were counted by push_kernel; the block has hot rows only
+                const uint2 pc = ld_stream_v2(solo.push_cnt + (size_t)slice * 32 + lane);
                 acc_s = pc.x; acc_n = pc.y; d_c = 0;
             }
-            accumulate_block(blk, KK & 0xFFFFu, KK >> 16, lane, ds_h, ds_c, d_c, s_vec, g_vec, r.cold_cg != 0, acc_s, acc_n);
+            accumulate_block(blk, KK & 0xFFFFu, KK >> 16, lane, ds_h, ds_c, d_c, s_vec, g_vec, SOLO && r.cold_cg != 0, acc_s, acc_n);
             acc_s = car_counts(acc_s, (uint32_t)(ds_h + ds_c));
             acc_n = car_counts(acc_n, (uint32_t)(dn_h + dn_c));
             uint32_t cs[4], cn[4];
 #pragma unroll
             for (int m = 0; m < 4; ++m) { cs[m] = (acc_s >> (8 * m)) & 0xFFu; cn[m] = (acc_n >> (8 * m)) & 0xFFu; }
             const uint32_t last = ((lane < 16 ? own.x : own.y) >> ((lane & 15u) * 2u)) & 3u;
-            finish_slice<PER_AGENT, XCHG>(r, slice, lane, true, cs, (uint32_t)(ds_h + ds_c), cn, (uint32_t)(dn_h + dn_c), stat, wsv, hv,
+            finish_slice<PER_AGENT, XCHG>(r, solo, slice, lane, true, cs, (uint32_t)(ds_h + ds_c), cn, (uint32_t)(dn_h + dn_c), stat, wsv, hv,
                                     last, uw, s_cong, s_cost, s_crank, s_des, s_rec, weather, changed, parity, st);
             }
             it0 = it1; it1 = it2; meta = meta1; meta1 = meta2;
@@ -650,8 +657,8 @@ day_kernel(const __grid_constant__ RepArray reps, uint32_t R, uint32_t P, uint32
     if (XCHG) {
         // Peer-to-peer exchange, second half.  The mode words are already on their way (finish_slice); when the LAST block
         // of this rank has finished, it hands the rank's partial record to every rank and raises the rank's flag there.
-        const PeerExchange* px = reps.r[0].px;
-        const uint32_t epoch = reps.r[0].px_epoch, world = px->world, W = px->rec_stride;
+        const PeerExchange* px = solo.px;
+        const uint32_t epoch = solo.px_epoch, world = px->world, W = px->rec_stride;
         uint32_t* s_last = s_tail + 3;                 // (a free word next to the work counter: no static shared memory here)
         __threadfence_system();                        // this thread's stores to the other ranks have been performed
         __syncthreads();

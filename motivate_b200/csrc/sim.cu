@@ -183,6 +183,7 @@ struct mvb_sim {
     DevBuf px_vec, px_ctl, d_px;         // {vec[0], vec[1], normvec}; {landing zone for partial records, flags, done, error, scratch}; PeerExchange
     std::vector<void*> px_open;          // cudaIpcOpenMemHandle results, closed by mvb_destroy
     uint32_t epoch = 0;                  // day-kernel launches so far: the flag value a rank raises when it has finished one
+    SoloExtra solo{nullptr, nullptr, 0, 0};   // what a handle with ONE population passes to the day kernel besides the replica descriptors
     // interventions of the current run, staged before the day loop (apply_interventions_kernel)
     DevBuf d_ivreps;                     // IvRep[R]
     char* iv_pinned = nullptr;           // library-owned pinned staging: the caller's arrays are only borrowed for the call
@@ -271,13 +272,14 @@ int launch_day(mvb_sim* s, uint8_t weather, uint8_t changed, bool with_norms = t
     cfg.gridDim = dim3(s->grid); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = s->smem_bytes; cfg.stream = s->stream;
     cfg.attrs = pdl_attr; cfg.numAttrs = ((s->world == 1 || s->exchange_mode == MVB_EXCHANGE_P2P) && !no_pdl) ? 1 : 0;
     const bool p2p = s->exchange_mode == MVB_EXCHANGE_P2P;
-    if (p2p) {                                                   // (one replica, one launch per weekday in this mode)
-        RepDev& r0 = s->rep_args[0].r[0];
-        r0.px_epoch = ++s->epoch; r0.px_norms = with_norms ? 1u : 0u;
-    }
-#define MVB_LAUNCH_X(PA, T, G, X) MVB_CUDA(cudaLaunchKernelEx(&cfg, day_kernel<PA, T, G, X>, s->rep_args[c], R, P, s->parity, prev, (uint32_t*)next, \
-        (uint32_t)weather, (uint32_t)changed, uw, s->vec_cap_words))
-#define MVB_LAUNCH(PA, T, G) do { if (p2p) MVB_LAUNCH_X(PA, T, G, true); else MVB_LAUNCH_X(PA, T, G, false); } while (0)
+    SoloExtra solo = s->solo;                                    // push mode / agent-partitioned mode: handles with one population
+    if (p2p) { solo.px_epoch = ++s->epoch; solo.px_norms = with_norms ? 1u : 0u; }
+    // SOLO instantiation (day_kernels.cuh): one population per handle with push mode, L1-bypassing cold gathers or the fused exchange
+    const bool solo_kernel = s->reps.size() == 1 && (solo.push_cnt || p2p || s->h_reps[0].cold_cg);
+#define MVB_LAUNCH_X(PA, T, G, SO, X) MVB_CUDA(cudaLaunchKernelEx(&cfg, day_kernel<PA, T, G, SO, X>, s->rep_args[c], R, P, s->parity, prev, (uint32_t*)next, \
+        (uint32_t)weather, (uint32_t)changed, uw, s->vec_cap_words, solo))
+#define MVB_LAUNCH(PA, T, G) do { if (p2p) MVB_LAUNCH_X(PA, T, G, true, true); else if (solo_kernel) MVB_LAUNCH_X(PA, T, G, true, false); \
+                                  else MVB_LAUNCH_X(PA, T, G, false, false); } while (0)
     // push mode (one large population, layout.h): the cold links of the SELL agents are counted first, by push_kernel
     for (Replica& rp : s->reps) {
         const Graph& g = *rp.graph;
