@@ -440,10 +440,11 @@ void mvb_destroy(mvb_sim* s) {
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     const double t1 = now();
+    // nobody writes into this rank's memory any more (its last exchange_finish_kernel saw every rank's flag); unmap the
+    // other ranks' buffers (also after a set-up that failed half way), and free the exported ones only when every rank has
+    for (void* p : s->px_open) cudaIpcCloseMemHandle(p);
+    s->px_open.clear();
     if (s->exchange_mode == MVB_EXCHANGE_P2P) {
-        // nobody writes into this rank's memory any more (its last exchange_finish_kernel saw every rank's flag); unmap the
-        // other ranks' buffers, and free the exported ones only when every rank has done so
-        for (void* p : s->px_open) cudaIpcCloseMemHandle(p);
         uint32_t* scratch = s->px_ctl.as<uint32_t>() + (s->px_ctl.bytes - 256) / 4;
         if (s->comm && nccl() && nccl()->AllReduce(scratch, scratch, 1, ncclUint32, ncclSum, s->comm, s->stream) == ncclSuccess)
             cudaStreamSynchronize(s->stream);
@@ -853,6 +854,7 @@ int mvb_get_state(mvb_sim* s, uint32_t r, float* habit, uint8_t* cur, uint8_t* l
     if (!s || r >= s->reps.size()) { set_error("bad handle/replica"); return MVB_ERR_ARG; }
     MVB_CUDA(cudaSetDevice(s->device));
     MVB_CUDA(cudaStreamSynchronize(s->stream));
+    if (int rc = check_peer_exchange(s)) return rc;
     Replica& rp = s->reps[r];
     if (int rc = host_int2ext(s, *rp.graph)) return rc;
     const std::vector<uint32_t>& int2ext = rp.graph->L.int2ext;

@@ -95,6 +95,75 @@ def test_exchange_protocol_two_gloo_ranks(tmp_path):
     assert np.array_equal(np.load(out), rows)
 
 
+def p2p_worker(rank, world, port, vec, normvec, xrec, flags, out):
+    """The peer-to-peer exchange protocol of day_kernel<.., XCHG> + exchange_finish_kernel (day_kernels.cuh), emulated on
+    the oracle with shared host memory standing in for the ranks' mapped device memory: vec[p][parity] / normvec[p] /
+    xrec[p][epoch parity][source] / flags[p][source] are rank p's buffers, which every rank can write."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)        # start-up barrier only: the protocol itself uses the flags
+    import time
+    pop, tab, prm, w = inputs()
+    owner = mb.partition_plan(pop, S, H, world)
+    mine = np.flatnonzero(owner == rank)
+    o = OracleSimulation(pop, tab, prm)
+    st = o.get_state()
+    parity, epoch, rows, prev = 0, 0, [o.stats_row()], w[0]
+    vec[rank][parity][:] = torch.from_numpy(st["current_mode"])          # every rank starts from the same state
+    dist.barrier()
+    for day in range(1, N_DAYS):
+        if day % 7 >= 5:
+            continue
+        # the rank's copy of yesterday's modes is what the others stored into it: the update must see exactly the oracle's state
+        assert np.array_equal(vec[rank][parity].numpy(), o.get_state()["current_mode"]), (rank, day)
+        o.step(w[day], prev != w[day]); prev = w[day]
+        st = o.get_state()
+        epoch += 1
+        a, an = st["current_mode"] >= 2, st["norm"] >= 2
+        part = np.zeros(7 + S + H, np.int64)                             # this rank's partial statistics row: its own agents only
+        for i in mine:
+            part[0] += a[i]; part[1] += an[i]; part[2] += a[i] and not an[i]; part[3] += (not a[i]) and an[i]
+            if a[i]:
+                part[4 + pop["commute"][i]] += 1; part[7 + pop["subculture"][i]] += 1; part[7 + S + pop["neighbourhood"][i]] += 1
+        for p in range(world):                                           # the kernel: new mode words into EVERY rank's vector,
+            vec[p][parity ^ 1][mine] = torch.from_numpy(st["current_mode"][mine])
+            normvec[p][mine] = torch.from_numpy(st["norm"][mine])
+        for p in range(world):                                           # its last block: partial counters, then the flag
+            xrec[p][epoch & 1][rank][:] = torch.from_numpy(part)
+        for p in range(world):
+            flags[p][rank] = epoch
+        t0 = time.time()                                                 # exchange_finish_kernel: wait for every rank's flag ...
+        while any(int(flags[rank][q]) - epoch < 0 for q in range(world)):
+            assert time.time() - t0 < 60, "a rank never raised its flag"
+            time.sleep(0.0005)
+        total = xrec[rank][epoch & 1].sum(dim=0).numpy()                 # ... and add the partial rows up
+        assert np.array_equal(total, o.stats_row().astype(np.int64)), (rank, day)
+        rows.append(total.copy())
+        parity ^= 1
+    # nobody may be a whole weekday ahead while a rank still reads: that is what the flag wait guarantees; final state
+    assert np.array_equal(vec[rank][parity].numpy(), o.get_state()["current_mode"])
+    dist.barrier()
+    assert np.array_equal(normvec[rank].numpy(), o.get_state()["norm"])
+    if rank == 0:
+        np.save(out, np.array(rows))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_peer_to_peer_exchange_protocol_on_shared_memory(tmp_path, world):
+    """CPU, `world` processes: double buffering by day parity (vectors) and epoch parity (landing zones) with the flags as
+    the only synchronisation reproduces the oracle's rows and state on every rank."""
+    out = str(tmp_path / "rows.npy")
+    W = 7 + S + H
+    vec = [[torch.zeros(N, dtype=torch.uint8).share_memory_() for _ in range(2)] for _ in range(world)]
+    normvec = [torch.zeros(N, dtype=torch.uint8).share_memory_() for _ in range(world)]
+    xrec = [torch.zeros(2, world, W, dtype=torch.int64).share_memory_() for _ in range(world)]
+    flags = [torch.zeros(world, dtype=torch.int64).share_memory_() for _ in range(world)]
+    mp.spawn(p2p_worker, args=(world, free_port(), vec, normvec, xrec, flags, out), nprocs=world, join=True)
+    pop, tab, prm, w = inputs()
+    _, rows = OracleSimulation(pop, tab, prm).run(w)
+    assert np.array_equal(np.load(out), rows)
+
+
 def wait_for_id(rank, idfile):
     if rank == 0:
         open(idfile + ".tmp", "wb").write(mb.comm_unique_id()); os.rename(idfile + ".tmp", idfile)
