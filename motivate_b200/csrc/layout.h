@@ -108,7 +108,9 @@ LayoutMode pick_layout_mode(uint32_t N_pad, uint32_t capacity_agents, uint32_t n
 // (tools/microbench_push.cu: 1.0-1.9 links per clock per SM against 0.5-0.85 for the pull).  The day kernel then finds
 // the counts of an agent's cold links in push_cnt[slot] and its SELL block holds hot rows only (Kc rows are not stored;
 // sell_K keeps Kc for the work model).  Hub agents keep their cold rows (pull).  MVB_PUSH=0|1 overrides the choice.
-constexpr uint32_t kPushChunkMax = 24576;    // agents per chunk: 8 bytes of counters each = 192 KB of shared memory; index < 2^15
+constexpr uint32_t kPushChunkMax = 16384;    // agents per chunk: 8 bytes of counters each = 128 KB of shared memory; index < 2^15.  Measured
+                                             // 8 192 / 12 288 / 16 384 / 20 480 / 24 576 (one B200, ms per weekday): 8M agents 0.516 / 0.507 / 0.486 / 0.490 /
+                                             // 0.501, 50M H=64 3.60 / 3.58 / 3.43 / 3.47 / 3.71, 50M H=10 - / 4.08 / 4.03 / 4.12 / 4.26
 bool pick_push_mode(uint32_t N_pad, uint32_t n_replicas);
 // agents per chunk for a handle that updates `own_slots` SELL slots on a grid of `grid` blocks: as large as allowed (the
 // longer a chunk's list, the closer its sorted targets), a whole number of rounds of the grid, a multiple of 32
