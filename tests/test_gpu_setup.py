@@ -128,6 +128,30 @@ def test_push_mode_small_population_equals_oracle(stage_env, stage, chunk, layou
     g.close()
 
 
+def test_push_mode_with_per_agent_weights(stage_env):
+    """The general kernel (per-agent weights, plain IEEE division) in its single-population instantiation: unstructured
+    inputs (duplicate links, empty lists, exact ties), a 64-agent staged set, push mode, several chunks; every day."""
+    from common import random_population, random_tables
+    stage_env(64, "local")
+    os.environ["MVB_PUSH"] = "1"
+    os.environ["MVB_PUSH_CHUNK"] = "256"
+    n, S, H, n_days = 3000, 5, 7, 25
+    pop = random_population(n, S, H, 3, per_agent=True, max_deg=9)
+    tab = random_tables(S, H, n, 3)
+    w = mb.weather_pattern(n_days, seed=3, p_good_given_good=0.6, p_good_given_bad=0.5)
+    prm = mb.make_params(days_in_habit_average=4)
+    g = mb.Simulation(pop, tab, prm)
+    o = OracleSimulation(pop, tab, prm)
+    prev = w[0]
+    for day in range(1, n_days):
+        if day % 7 >= 5:
+            continue
+        g.step(w[day], prev != w[day]); o.step(w[day], prev != w[day])
+        prev = w[day]
+        assert_state_equal(g.get_state(0), o.get_state(), f"day {day}")
+    g.close()
+
+
 def test_push_mode_run_equals_pull_run_200k(stage_env):
     """The same 200k-agent population through the pull path and through the push path (one third of the agents staged,
     LOCAL layout, default chunk size): rows and full state identical after a 3-week run with mvb_run."""
