@@ -720,7 +720,7 @@ struct PushDesc {
 __global__ void __launch_bounds__(1024, 1) push_kernel(const PushDesc d, const uint32_t* __restrict__ g_vec) {
     extern __shared__ __align__(16) uint32_t s_cnt[];                    // [chunk_agents][2]
     const uint32_t tid = threadIdx.x;
-    constexpr uint32_t U = 4;
+    constexpr uint32_t U = 8;                               // (8M agents 0.489 -> 0.479 ms per weekday against 4; 64 registers)
     for (uint32_t c = blockIdx.x; c < d.n_chunks; c += gridDim.x) {
         const uint32_t first = d.chunk_first[c], n_ag = d.chunk_first[c + 1] - first;
         for (uint32_t k = tid; k < 2 * n_ag; k += 1024) s_cnt[k] = 0;
